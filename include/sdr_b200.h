@@ -1,0 +1,118 @@
+/* sdr_b200.h -- C ABI of the B200 IQ->PCM demodulation engine.
+ *
+ * The reference (wizardyesterday/RtlSdrDiags) has no FFI layer: its boundary for
+ * this path is a set of C++ classes, one object per radio. This header is the
+ * boundary a maintainer binds instead; one engine stands for a BANK of
+ * n_channels independent radios on one GPU. Each entry point names the
+ * reference interface it replaces.
+ *
+ *   reference (radioDiags/)                               this ABI
+ *   ----------------------------------------------------  -------------------------
+ *   new IqDataProcessor + new {Am,Fm,WbFm,Ssb}Demodulator  sdr_engine_create
+ *     (src_diags/Radio.cc:150-181)
+ *   IqDataProcessor::setDemodulatorMode                    sdr_set_mode / sdr_set_modes
+ *     (src_diags/IqDataProcessor.cc:236-262)
+ *   XDemodulator::setDemodulatorGain                       sdr_set_gain / sdr_set_gain_all
+ *     (AmDemodulator.cc:267, FmDemodulator.cc:304,
+ *      WbFmDemodulator.cc:341, SsbDemodulator.cc:390)
+ *   XDemodulator::resetDemodulator                         sdr_reset
+ *     (AmDemodulator.cc:232, FmDemodulator.cc:271,
+ *      WbFmDemodulator.cc:304, SsbDemodulator.cc:297)
+ *   IqDataProcessor::acceptIqData(ts, u8*, n)              sdr_accept_iq(.., SDR_IQ_U8_OFFSET)
+ *     (src_diags/IqDataProcessor.cc:722-840)
+ *   XDemodulator::acceptIqData(int8_t*, n)                 sdr_accept_iq(.., SDR_IQ_S8_ROTATED)
+ *     (e.g. FmDemodulator.cc:334-352)
+ *   pcmCallbackPtr(int16_t*, n)  (radioApp.cc:103-111)     sdr_get_pcm / sdr_pcm_device
+ *
+ * All functions return 0 on success or a negative SDR_E_* code; none throws.
+ * Calls on one engine must be serialised by the caller (the reference calls
+ * acceptIqData from one thread, DataConsumer.cc:342). There is no CPU fallback:
+ * without a usable CUDA device sdr_engine_create fails with SDR_E_CUDA.
+ */
+#ifndef SDR_B200_H
+#define SDR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sdr_engine sdr_engine;
+
+/* IqDataProcessor::demodulatorType, hdr_diags/IqDataProcessor.h:20 */
+enum { SDR_MODE_NONE = 0, SDR_MODE_AM = 1, SDR_MODE_FM = 2, SDR_MODE_WBFM = 3,
+       SDR_MODE_LSB = 4, SDR_MODE_USB = 5 };
+/* which of a channel's four demodulator objects a gain / reset addresses */
+enum { SDR_KIND_AM = 1, SDR_KIND_FM = 2, SDR_KIND_WBFM = 3, SDR_KIND_SSB = 4 };
+/* FM/WBFM PCM scaling: radioDiags/ (gain/deviation*32767, FmDemodulator.cc:465-471)
+ * or demodulatorResearch/ (gain used directly; WBFM default gain 64000/2pi) */
+enum { SDR_SCALING_RADIODIAGS = 0, SDR_SCALING_RESEARCH = 1 };
+
+/* sdr_accept_iq flags */
+enum {
+  SDR_IQ_HOST = 0,        /* iq points to host memory; the engine copies it to the GPU */
+  SDR_IQ_DEVICE = 1,      /* iq points to device memory on the engine's GPU */
+  SDR_IQ_U8_OFFSET = 0,   /* u8 offset-binary, not yet rotated: IqDataProcessor entry */
+  SDR_IQ_S8_ROTATED = 2   /* signed, already Fs/4-rotated: demodulator entry, .iq file format */
+};
+
+enum {
+  SDR_OK = 0,
+  SDR_E_ARG = -1,      /* bad handle, channel, mode, kind, size or alignment */
+  SDR_E_CUDA = -2,     /* CUDA runtime error (sdr_last_error has the text) */
+  SDR_E_NOMEM = -3,
+  SDR_E_TOO_LONG = -4  /* bytes_per_channel exceeds the engine's max_bytes_per_channel */
+};
+
+/* One engine = n_channels radios on CUDA device `device`. max_bytes_per_channel
+ * bounds a single sdr_accept_iq (the reference block is 32768 bytes). All
+ * channels start like a fresh reference object: mode None, gains 300 / 64000/2pi /
+ * 256000/2pi / 300, LSB selected, all filter state zero. */
+int sdr_engine_create(uint32_t n_channels, int device, uint64_t max_bytes_per_channel,
+                      sdr_engine **out);
+int sdr_engine_destroy(sdr_engine *e);
+
+/* Run on a caller-owned cudaStream_t (NULL = the engine's own stream). */
+int sdr_set_stream(sdr_engine *e, void *cuda_stream);
+int sdr_set_scaling(sdr_engine *e, int scaling);
+
+int sdr_set_mode(sdr_engine *e, uint32_t channel, int mode);
+int sdr_set_modes(sdr_engine *e, const uint8_t *modes /* [n_channels] */);
+int sdr_set_gain(sdr_engine *e, uint32_t channel, int kind, float gain);
+int sdr_set_gain_all(sdr_engine *e, int kind, float gain);
+int sdr_reset(sdr_engine *e, uint32_t channel, int kind);
+
+/* One block for every channel: iq is [n_channels][channel_stride] bytes of
+ * interleaved I,Q of which the first bytes_per_channel are consumed.
+ * bytes_per_channel must be a multiple of 64 (one PCM sample); pointers and
+ * stride multiples of 16. Asynchronous: returns once the work is queued. Each
+ * channel is demodulated by the mode it is in, exactly as the reference's
+ * switch does; channels in mode None produce nothing. Filter state carries
+ * over to the next call. */
+int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes_per_channel,
+                  uint64_t channel_stride, uint32_t flags);
+
+/* PCM of the last sdr_accept_iq: row ch holds counts[ch] samples (bytes/64, or 0
+ * in mode None), rows are samples_per_row = bytes_per_channel/64 apart.
+ * Synchronises. Either pointer may be NULL. */
+int sdr_get_pcm(sdr_engine *e, int16_t *pcm, uint32_t *counts);
+/* Device-resident PCM of the last call: [n_channels][*stride] int16. */
+int sdr_pcm_device(sdr_engine *e, int16_t **pcm, uint64_t *stride);
+int sdr_sync(sdr_engine *e);
+
+/* Launch shape of one demodulator kind: channels per CTA (1..32) and threads
+ * per CTA (multiple of 32). 0 = let the engine choose. For tuning and tests. */
+int sdr_set_launch_shape(sdr_engine *e, int kind, uint32_t channels_per_cta, uint32_t threads);
+/* Kernels launched by this engine so far. */
+uint64_t sdr_launch_count(const sdr_engine *e);
+/* Bytes of continuation state one channel keeps for `kind`. */
+int sdr_state_bytes(int kind);
+/* Text of the last error on this engine (or of the last failed create if e is NULL). */
+const char *sdr_last_error(const sdr_engine *e);
+const char *sdr_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDR_B200_H */

@@ -1,0 +1,184 @@
+"""B200-native IQ->PCM demodulation engine: Python binding of the C ABI in
+include/sdr_b200.h (ctypes over rtlsdrdiags_b200/libsdr_b200.so).
+
+The binding is thin on purpose: the product is the CUDA library. There is no
+CPU fallback -- importing works anywhere, but creating an Engine without the
+compiled library or without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+MODE_NONE, MODE_AM, MODE_FM, MODE_WBFM, MODE_LSB, MODE_USB = range(6)
+KIND_AM, KIND_FM, KIND_WBFM, KIND_SSB = 1, 2, 3, 4
+SCALING_RADIODIAGS, SCALING_RESEARCH = 0, 1
+IQ_HOST, IQ_DEVICE, IQ_U8_OFFSET, IQ_S8_ROTATED = 0, 1, 0, 2
+MODE_TO_KIND = {MODE_AM: KIND_AM, MODE_FM: KIND_FM, MODE_WBFM: KIND_WBFM,
+                MODE_LSB: KIND_SSB, MODE_USB: KIND_SSB}
+BLOCK_BYTES = 32768  # the reference's IQ block: 16384 complex samples = 64 ms -> 512 PCM samples
+
+# every symbol include/sdr_b200.h declares
+ABI_SYMBOLS = ["sdr_engine_create", "sdr_engine_destroy", "sdr_set_stream", "sdr_set_scaling",
+               "sdr_set_mode", "sdr_set_modes", "sdr_set_gain", "sdr_set_gain_all", "sdr_reset",
+               "sdr_accept_iq", "sdr_get_pcm", "sdr_pcm_device", "sdr_sync", "sdr_set_launch_shape",
+               "sdr_launch_count", "sdr_state_bytes", "sdr_last_error", "sdr_version"]
+
+
+class SdrError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library(build_if_missing=True):
+    """dlopen libsdr_b200.so (building it in-tree first if it is absent or stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if build_if_missing and _build.is_stale():
+        _build.build()
+    if not os.path.exists(_build.LIB):
+        raise SdrError("libsdr_b200.so is not built (run `python -m rtlsdrdiags_b200._build`); "
+                       "there is no CPU fallback")
+    L = C.CDLL(_build.LIB)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    L.sdr_engine_create.argtypes = [u32, i32, u64, C.POINTER(vp)]
+    L.sdr_engine_destroy.argtypes = [vp]
+    L.sdr_set_stream.argtypes = [vp, vp]
+    L.sdr_set_scaling.argtypes = [vp, i32]
+    L.sdr_set_mode.argtypes = [vp, u32, i32]
+    L.sdr_set_modes.argtypes = [vp, vp]
+    L.sdr_set_gain.argtypes = [vp, u32, i32, C.c_float]
+    L.sdr_set_gain_all.argtypes = [vp, i32, C.c_float]
+    L.sdr_reset.argtypes = [vp, u32, i32]
+    L.sdr_accept_iq.argtypes = [vp, vp, u64, u64, u32]
+    L.sdr_get_pcm.argtypes = [vp, vp, vp]
+    L.sdr_pcm_device.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+    L.sdr_sync.argtypes = [vp]
+    L.sdr_set_launch_shape.argtypes = [vp, i32, u32, u32]
+    L.sdr_launch_count.argtypes = [vp]
+    L.sdr_launch_count.restype = u64
+    L.sdr_state_bytes.argtypes = [i32]
+    L.sdr_last_error.argtypes = [vp]
+    L.sdr_last_error.restype = C.c_char_p
+    L.sdr_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+class Engine:
+    """A bank of `n_channels` radios on one GPU (one IqDataProcessor plus the four
+    demodulators per channel in the reference's terms)."""
+
+    def __init__(self, n_channels, device=0, max_bytes_per_channel=BLOCK_BYTES):
+        self.L = load_library()
+        self.n = int(n_channels)
+        self.max_bytes = int(max_bytes_per_channel)
+        h = C.c_void_p()
+        rc = self.L.sdr_engine_create(self.n, int(device), self.max_bytes, C.byref(h))
+        if rc != 0:
+            raise SdrError("sdr_engine_create failed (%d): %s" % (rc, self.L.sdr_last_error(None).decode()))
+        self.h = h
+        self._keep = None
+        self.last_samples = 0  # PCM samples per channel produced by the last accept
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.sdr_engine_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SdrError("sdr error %d: %s" % (rc, self.L.sdr_last_error(self.h).decode()))
+
+    # ---- control surface (the reference's setters) ----
+    def set_stream(self, cuda_stream_handle):
+        self._ck(self.L.sdr_set_stream(self.h, C.c_void_p(cuda_stream_handle or 0)))
+
+    def set_scaling(self, scaling):
+        self._ck(self.L.sdr_set_scaling(self.h, scaling))
+
+    def set_mode(self, channel, mode):
+        self._ck(self.L.sdr_set_mode(self.h, channel, mode))
+
+    def set_modes(self, modes):
+        m = np.ascontiguousarray(modes, dtype=np.uint8)
+        if m.size != self.n:
+            raise SdrError("modes must have one entry per channel")
+        self._ck(self.L.sdr_set_modes(self.h, m.ctypes.data_as(C.c_void_p)))
+
+    def set_gain(self, channel, kind, gain):
+        self._ck(self.L.sdr_set_gain(self.h, channel, kind, float(gain)))
+
+    def set_gain_all(self, kind, gain):
+        self._ck(self.L.sdr_set_gain_all(self.h, kind, float(gain)))
+
+    def reset(self, channel, kind):
+        self._ck(self.L.sdr_reset(self.h, channel, kind))
+
+    def set_launch_shape(self, kind, channels_per_cta=0, threads=0):
+        self._ck(self.L.sdr_set_launch_shape(self.h, kind, channels_per_cta, threads))
+
+    # ---- data path ----
+    def accept_iq_host(self, iq, fmt=IQ_U8_OFFSET):
+        """iq: numpy [n_channels][bytes] uint8 or int8 in host memory (pinned or not)."""
+        a = np.ascontiguousarray(iq)
+        if a.ndim != 2 or a.shape[0] != self.n or a.itemsize != 1:
+            raise SdrError("iq must be [n_channels][bytes] of 1-byte samples")
+        self._keep = a  # the copy is asynchronous
+        self._ck(self.L.sdr_accept_iq(self.h, a.ctypes.data_as(C.c_void_p), a.shape[1], a.strides[0],
+                                      IQ_HOST | fmt))
+        self.last_samples = a.shape[1] // 64
+
+    def accept_iq_ptr(self, ptr, bytes_per_channel, channel_stride, flags):
+        self._ck(self.L.sdr_accept_iq(self.h, C.c_void_p(ptr), bytes_per_channel, channel_stride, flags))
+        self.last_samples = bytes_per_channel // 64
+
+    def accept_iq_device(self, iq_tensor, fmt=IQ_U8_OFFSET):
+        """iq_tensor: torch uint8/int8 CUDA tensor [n_channels][bytes], row-contiguous."""
+        if iq_tensor.dim() != 2 or iq_tensor.shape[0] != self.n or iq_tensor.stride(1) != 1:
+            raise SdrError("iq tensor must be [n_channels][bytes] with unit inner stride")
+        self.accept_iq_ptr(iq_tensor.data_ptr(), iq_tensor.shape[1], iq_tensor.stride(0), IQ_DEVICE | fmt)
+
+    def get_pcm(self, out=None):
+        """Returns (pcm [n_channels][samples] int16, counts [n_channels] uint32). Synchronises."""
+        samples = self.last_samples
+        if out is None:
+            out = np.empty((self.n, samples), dtype=np.int16)
+        counts = np.empty(self.n, dtype=np.uint32)
+        self._ck(self.L.sdr_get_pcm(self.h, out.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p)))
+        return out, counts
+
+    def get_pcm_ptr(self, host_ptr):
+        self._ck(self.L.sdr_get_pcm(self.h, C.c_void_p(host_ptr), None))
+
+    def pcm_device(self):
+        p, s = C.c_void_p(), C.c_uint64()
+        self._ck(self.L.sdr_pcm_device(self.h, C.byref(p), C.byref(s)))
+        return p.value, s.value
+
+    def sync(self):
+        self._ck(self.L.sdr_sync(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.L.sdr_launch_count(self.h))
+
+    def demodulate(self, iq, fmt=IQ_U8_OFFSET):
+        """Convenience: one accept + get_pcm on host arrays. Long streams are cut into
+        max_bytes_per_channel pieces; state carries across pieces and calls."""
+        a = np.ascontiguousarray(iq)
+        total = a.shape[1]
+        outs = []
+        for off in range(0, total, self.max_bytes):
+            piece = np.ascontiguousarray(a[:, off:off + self.max_bytes])
+            self.accept_iq_host(piece, fmt)
+            pcm, counts = self.get_pcm()
+            outs.append(pcm)
+        return np.concatenate(outs, axis=1), counts

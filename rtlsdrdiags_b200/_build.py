@@ -1,0 +1,49 @@
+"""Builds rtlsdrdiags_b200/libsdr_b200.so (CUDA kernels + engine + C ABI) in-tree
+with nvcc for sm_100a. nvcc cross-compiles without a GPU."""
+import os
+import shutil
+import subprocess
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "libsdr_b200.so")
+
+NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-fmad=false", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
+
+
+def _nvcc():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(ROOT, "include", "sdr_b200.h")]
+
+
+def is_stale():
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    return any(os.path.getmtime(s) > t for s in sources())
+
+
+def build(force=False, defines=(), verbose=False):
+    """Compile the shared library if it is missing or older than its sources."""
+    if not force and not defines and not is_stale():
+        return LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D%s" % d for d in defines]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += ["-o", LIB, os.path.join(CSRC, "sdr_engine.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), r.stderr))
+    if verbose:
+        print(r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+    print(build(force=True, verbose="-v" in sys.argv))

@@ -72,10 +72,10 @@ SDR_DEV float hdr_scale(const Ctx &t, int c) { return lds<float>(t.hdr + HDR_SCA
 SDR_DEV uint32_t hdr_u32(const Ctx &t, int off, int c) { return lds<uint32_t>(t.hdr + off + 4 * c); }
 SDR_DEV void hdr_set(const Ctx &t, int off, int c, uint32_t v) { sts<uint32_t>(t.hdr + off + 4 * c, v); }
 
-constexpr int round_up(int v, int m) { return (v + m - 1) / m * m; }
+SDR_HD constexpr int round_up(int v, int m) { return (v + m - 1) / m * m; }
 // per-channel stride == 16 (mod 128): 128-bit lane-per-channel accesses are
 // bank-conflict free, and every channel base stays 16-byte aligned.
-constexpr int channel_stride(int end) { return round_up(end, 128) + 16; }
+SDR_HD constexpr int channel_stride(int end) { return round_up(end, 128) + 16; }
 
 #define SDR_FOR_ITEMS(t, ITEMS, c, j)                                                 \
   for (int _idx = (t).tid, _tot = (t).Gc * (ITEMS); _idx < _tot; _idx += (t).nt)      \
@@ -148,11 +148,11 @@ SDR_DEV void phase_front_end(const Ctx &t, int XI, int XQ, int STRIDE) {
 // ---------------------------------------------------------------------------
 // Q15 FIR cores
 // ---------------------------------------------------------------------------
-constexpr uint32_t pack16(int lo, int hi) {
+SDR_HD constexpr uint32_t pack16(int lo, int hi) {
   return ((uint32_t)lo & 0xffffu) | (((uint32_t)hi & 0xffffu) << 16);
 }
 // int16 tap split into a signed high byte and an unsigned low byte: t = 256*hi + lo
-constexpr uint32_t tap_bytes(int t0, int t1) {
+SDR_HD constexpr uint32_t tap_bytes(int t0, int t1) {
   return ((uint32_t)(t0 >> 8) & 0xffu) | (((uint32_t)(t1 >> 8) & 0xffu) << 8) |
          (((uint32_t)t0 & 0xffu) << 16) | (((uint32_t)t1 & 0xffu) << 24);
 }
@@ -163,8 +163,9 @@ template <class F, int P, int I>
 SDR_DEV int fir_s8_word(int acc, uint32_t w) {
   constexpr int t0 = F::tap(P - 4 * I), t1 = F::tap(P - 4 * I - 1);
   constexpr int t2 = F::tap(P - 4 * I - 2), t3 = F::tap(P - 4 * I - 3);
-  if constexpr (t0 != 0 || t1 != 0) acc = dp2a_lo_ss(pack16(t0, t1), w, acc);
-  if constexpr (t2 != 0 || t3 != 0) acc = dp2a_hi_ss(pack16(t2, t3), w, acc);
+  constexpr uint32_t lo = pack16(t0, t1), hi = pack16(t2, t3);
+  if constexpr (t0 != 0 || t1 != 0) acc = dp2a_lo_ss(lo, w, acc);
+  if constexpr (t2 != 0 || t3 != 0) acc = dp2a_hi_ss(hi, w, acc);
   return acc;
 }
 template <class F, int P, int NW, int I = 0>
@@ -888,7 +889,7 @@ SDR_DEV void cta_state(const Ctx &t) {
   }
 }
 
-template <class M> constexpr int smem_bytes(int G) { return HDR_BYTES + G * M::STRIDE; }
+template <class M> SDR_HD constexpr int smem_bytes(int G) { return HDR_BYTES + G * M::STRIDE; }
 
 #if SDR_DEVICE_BUILD
 template <class M, int PH = 0>

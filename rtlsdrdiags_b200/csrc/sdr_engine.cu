@@ -1,0 +1,451 @@
+// Host side of the demodulation engine and its C ABI (include/sdr_b200.h).
+//
+// One engine owns, for a bank of n_channels radios on one GPU:
+//   * per-kind continuation state blobs in HBM ([n_channels][STATE_BYTES] each;
+//     the reference keeps four demodulator objects per radio and a mode switch
+//     leaves the idle ones untouched, IqDataProcessor.cc:793-835),
+//   * per-channel mode / gain / sideband tables, mirrored on the host,
+//   * per-kind channel lists (channels bucketed by mode so every CTA is
+//     mode-uniform), the two atan2 tables, an IQ staging buffer and the PCM buffer.
+// sdr_accept_iq queues at most four kernel launches (one per demodulator kind
+// that has channels) on one stream. No CPU path exists.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sdr_b200.h"
+#include "sdr_config.h"
+
+namespace {
+
+using namespace sdr;
+
+thread_local std::string g_create_error;
+
+struct Shape { uint32_t G = 0, NT = 0; };  // 0 = choose
+
+}  // namespace
+
+struct sdr_engine {
+  int device = 0;
+  uint32_t n = 0;
+  uint64_t max_bytes = 0;
+  int n_sm = 148;
+  int smem_optin = 227 * 1024;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  int scaling = SDR_SCALING_RADIODIAGS;
+
+  // host mirrors (index 1..4 = kind)
+  std::vector<uint8_t> mode, lsb;
+  std::vector<float> gain[5], scale[5];
+  std::vector<uint32_t> list[5];
+  bool lists_dirty = true, lsb_dirty = true, scale_dirty[5] = {true, true, true, true, true};
+
+  // device
+  uint8_t *d_state[5] = {};
+  float *d_scale[5] = {};
+  uint32_t *d_list[5] = {};
+  uint8_t *d_lsb = nullptr;
+  float *d_lut_fm = nullptr, *d_lut_wbfm = nullptr;
+  uint8_t *d_iq = nullptr;
+  int16_t *d_pcm = nullptr;
+  uint64_t pcm_stride = 0;
+
+  Shape shape[5];
+  uint32_t last_samples = 0;  // PCM samples per channel of the last accept
+  uint64_t launches = 0;
+  std::string err;
+};
+
+namespace {
+
+int fail(sdr_engine *e, int code, const char *what, cudaError_t ce = cudaSuccess) {
+  char buf[512];
+  if (ce != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(ce));
+  else snprintf(buf, sizeof buf, "%s", what);
+  if (e) e->err = buf;
+  else g_create_error = buf;
+  return code;
+}
+
+#define SDR_CK(e, call)                                                 \
+  do {                                                                  \
+    cudaError_t _ce = (call);                                           \
+    if (_ce != cudaSuccess) return fail((e), SDR_E_CUDA, #call, _ce);   \
+  } while (0)
+
+int state_bytes(int kind) {
+  switch (kind) {
+    case SDR_KIND_AM: return AmPipe::STATE_BYTES;
+    case SDR_KIND_FM: return FmPipe::STATE_BYTES;
+    case SDR_KIND_WBFM: return WbFmPipe::STATE_BYTES;
+    case SDR_KIND_SSB: return SsbPipe::STATE_BYTES;
+  }
+  return -1;
+}
+int stride_bytes(int kind) {
+  switch (kind) {
+    case SDR_KIND_AM: return AmPipe::STRIDE;
+    case SDR_KIND_FM: return FmPipe::STRIDE;
+    case SDR_KIND_WBFM: return WbFmPipe::STRIDE;
+    case SDR_KIND_SSB: return SsbPipe::STRIDE;
+  }
+  return -1;
+}
+int kind_of_mode(int mode) {
+  switch (mode) {
+    case SDR_MODE_AM: return SDR_KIND_AM;
+    case SDR_MODE_FM: return SDR_KIND_FM;
+    case SDR_MODE_WBFM: return SDR_KIND_WBFM;
+    case SDR_MODE_LSB:
+    case SDR_MODE_USB: return SDR_KIND_SSB;
+  }
+  return 0;
+}
+
+// reference constructor defaults: AmDemodulator.cc:102, FmDemodulator.cc:154,
+// WbFmDemodulator.cc:173 (research tree: 64000), SsbDemodulator.cc:146
+float default_gain(int kind, int scaling) {
+  switch (kind) {
+    case SDR_KIND_AM: return 300;
+    case SDR_KIND_FM: return (float)(64000 / (2 * M_PI));
+    case SDR_KIND_WBFM:
+      return scaling == SDR_SCALING_RESEARCH ? (float)(64000 / (2 * M_PI)) : (float)(256000 / (2 * M_PI));
+    case SDR_KIND_SSB: return 300;
+  }
+  return 0;
+}
+
+// what the kernels multiply by. FM/WBFM: frequencyDeviationToPcm, two float ops
+// (FmDemodulator.cc:465-471, WbFmDemodulator.cc:444-450).
+float scale_of(int kind, float gain, int scaling) {
+  if (kind == SDR_KIND_AM || kind == SDR_KIND_SSB || scaling == SDR_SCALING_RESEARCH) return gain;
+  volatile float k = gain / (kind == SDR_KIND_FM ? 15000.0f : 75000.0f);
+  k = k * 32767.0f;
+  return k;
+}
+
+// Channels per CTA (G), threads per CTA (NT): pick the number of co-resident
+// CTAs per SM (R) and of waves (W) that wastes the fewest channel slots; prefer
+// more co-resident CTAs so one CTA's sequential phase overlaps another's FIRs.
+Shape choose_shape(const sdr_engine *e, int kind, uint32_t n_list) {
+  Shape best;
+  double best_score = -1;
+  const int stride = stride_bytes(kind);
+  for (int R = 1; R <= 4; ++R) {
+    long gmax = ((long)e->smem_optin / R - HDR_BYTES - 1024) / stride;
+    if (gmax > MAX_G) gmax = MAX_G;
+    if (gmax < 1) continue;
+    const long slots = (long)e->n_sm * R;
+    const long W = ((long)n_list + slots * gmax - 1) / (slots * gmax);
+    const long G = ((long)n_list + slots * W - 1) / (slots * W);
+    const long ctas = ((long)n_list + G - 1) / G;
+    const long waves = (ctas + slots - 1) / slots;
+    const double eff = (double)n_list / (double)(waves * slots * G);
+    const double score = eff + (R == 2 ? 0.02 : 0.0) - (R > 2 ? 0.01 * (R - 2) : 0.0);
+    if (score > best_score) {
+      best_score = score;
+      best.G = (uint32_t)G;
+      best.NT = (uint32_t)(1024 / R);
+    }
+  }
+  if (best.G == 0) { best.G = 1; best.NT = 256; }
+  return best;
+}
+
+template <class M>
+int launch_kind(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples,
+                int fmt) {
+  const uint32_t n_list = (uint32_t)e->list[kind].size();
+  if (n_list == 0) return SDR_OK;
+  Shape s = choose_shape(e, kind, n_list);
+  if (e->shape[kind].G) s.G = e->shape[kind].G;
+  if (e->shape[kind].NT) s.NT = e->shape[kind].NT;
+  if (s.G > MAX_G) s.G = MAX_G;
+  const int smem = smem_bytes<M>((int)s.G);
+  if (smem > e->smem_optin) return fail(e, SDR_E_ARG, "launch shape needs more shared memory than an SM has");
+  LaunchParams p;
+  p.iq = iq;
+  p.ch_stride = ch_stride;
+  p.n_samples = n_samples;
+  p.fmt = fmt;
+  p.chan_ids = e->d_list[kind];
+  p.n_list = n_list;
+  p.G = s.G;
+  p.state = e->d_state[kind];
+  p.state_stride = (uint32_t)M::STATE_BYTES;
+  p.scale = e->d_scale[kind];
+  p.lsb = e->d_lsb;
+  p.pcm = e->d_pcm;
+  p.pcm_stride = e->pcm_stride;
+  p.lut = kind == SDR_KIND_FM ? e->d_lut_fm : e->d_lut_wbfm;
+  SDR_CK(e, cudaFuncSetAttribute(demod_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const uint32_t grid = (n_list + s.G - 1) / s.G;
+  demod_kernel<M><<<grid, s.NT, smem, e->stream>>>(p);
+  SDR_CK(e, cudaGetLastError());
+  e->launches++;
+  return SDR_OK;
+}
+
+int upload_tables(sdr_engine *e) {
+  if (e->lists_dirty) {
+    for (int k = 1; k <= 4; ++k) e->list[k].clear();
+    for (uint32_t ch = 0; ch < e->n; ++ch) {
+      const int k = kind_of_mode(e->mode[ch]);
+      if (k) e->list[k].push_back(ch);
+    }
+    for (int k = 1; k <= 4; ++k)
+      if (!e->list[k].empty())
+        SDR_CK(e, cudaMemcpyAsync(e->d_list[k], e->list[k].data(), e->list[k].size() * 4,
+                                  cudaMemcpyHostToDevice, e->stream));
+    e->lists_dirty = false;
+  }
+  if (e->lsb_dirty) {
+    SDR_CK(e, cudaMemcpyAsync(e->d_lsb, e->lsb.data(), e->n, cudaMemcpyHostToDevice, e->stream));
+    e->lsb_dirty = false;
+  }
+  for (int k = 1; k <= 4; ++k) {
+    if (!e->scale_dirty[k]) continue;
+    for (uint32_t ch = 0; ch < e->n; ++ch) e->scale[k][ch] = scale_of(k, e->gain[k][ch], e->scaling);
+    SDR_CK(e, cudaMemcpyAsync(e->d_scale[k], e->scale[k].data(), (size_t)e->n * 4, cudaMemcpyHostToDevice,
+                              e->stream));
+    e->scale_dirty[k] = false;
+  }
+  // the host vectors above must outlive the async copies from pageable memory;
+  // cudaMemcpyAsync from pageable memory has returned only after staging them.
+  return SDR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *sdr_version(void) { return "sdr_b200 0.1 (sm_100a)"; }
+
+const char *sdr_last_error(const sdr_engine *e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int sdr_state_bytes(int kind) { return state_bytes(kind); }
+
+int sdr_engine_create(uint32_t n_channels, int device, uint64_t max_bytes_per_channel, sdr_engine **out) {
+  if (!out) return SDR_E_ARG;
+  *out = nullptr;
+  if (n_channels == 0 || max_bytes_per_channel == 0 || max_bytes_per_channel % 64 ||
+      max_bytes_per_channel / 2 > 0xffffffe0ull)
+    return fail(nullptr, SDR_E_ARG, "n_channels and max_bytes_per_channel (multiple of 64) must be positive");
+  int count = 0;
+  cudaError_t ce = cudaGetDeviceCount(&count);
+  if (ce != cudaSuccess || count == 0)
+    return fail(nullptr, SDR_E_CUDA, "no CUDA device: this engine has no CPU path", ce);
+  if (device < 0 || device >= count) return fail(nullptr, SDR_E_ARG, "device index out of range");
+  sdr_engine *e = new (std::nothrow) sdr_engine();
+  if (!e) return SDR_E_NOMEM;
+  e->device = device;
+  e->n = n_channels;
+  e->max_bytes = max_bytes_per_channel;
+#define SDR_CK_CREATE(call)                                                       \
+  do {                                                                            \
+    cudaError_t _ce = (call);                                                     \
+    if (_ce != cudaSuccess) {                                                     \
+      fail(nullptr, SDR_E_CUDA, #call, _ce);                                      \
+      sdr_engine_destroy(e);                                                      \
+      return _ce == cudaErrorMemoryAllocation ? SDR_E_NOMEM : SDR_E_CUDA;         \
+    }                                                                             \
+  } while (0)
+  SDR_CK_CREATE(cudaSetDevice(device));
+  SDR_CK_CREATE(cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device));
+  SDR_CK_CREATE(cudaDeviceGetAttribute(&e->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  SDR_CK_CREATE(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+  e->stream = e->own_stream;
+
+  e->mode.assign(n_channels, SDR_MODE_NONE);  // IqDataProcessor.cc:38
+  e->lsb.assign(n_channels, 1);               // SsbDemodulator.cc:143
+  for (int k = 1; k <= 4; ++k) {
+    e->gain[k].assign(n_channels, default_gain(k, e->scaling));
+    e->scale[k].assign(n_channels, 0.f);
+    const size_t sb = (size_t)state_bytes(k) * n_channels;
+    SDR_CK_CREATE(cudaMalloc(&e->d_state[k], sb));
+    SDR_CK_CREATE(cudaMemsetAsync(e->d_state[k], 0, sb, e->stream));
+    SDR_CK_CREATE(cudaMalloc(&e->d_scale[k], (size_t)n_channels * 4));
+    SDR_CK_CREATE(cudaMalloc(&e->d_list[k], (size_t)n_channels * 4));
+  }
+  SDR_CK_CREATE(cudaMalloc(&e->d_lsb, n_channels));
+  e->pcm_stride = (max_bytes_per_channel / 64 + 1) & ~1ull;
+  SDR_CK_CREATE(cudaMalloc(&e->d_pcm, (size_t)n_channels * e->pcm_stride * 2));
+  SDR_CK_CREATE(cudaMemsetAsync(e->d_pcm, 0, (size_t)n_channels * e->pcm_stride * 2, e->stream));
+
+  // atan2 tables, built with the host libm exactly as the reference builds its
+  // WBFM table (WbFmDemodulator.cc:159-170). NBFM calls atan2 per sample on
+  // tuner outputs that lie in [-140, 139] for 8-bit input (FmDemodulator.cc:476),
+  // so a 280x280 table of (float)atan2((double)q,(double)i) is the same function.
+  {
+    std::vector<float> t((size_t)FM_LUT_DIM * FM_LUT_DIM);
+    for (int q = 0; q < FM_LUT_DIM; ++q)
+      for (int i = 0; i < FM_LUT_DIM; ++i)
+        t[(size_t)q * FM_LUT_DIM + i] = (float)atan2((double)(q + FM_LUT_MIN), (double)(i + FM_LUT_MIN));
+    SDR_CK_CREATE(cudaMalloc(&e->d_lut_fm, t.size() * 4));
+    SDR_CK_CREATE(cudaMemcpy(e->d_lut_fm, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+  }
+  {
+    std::vector<float> t(256 * 256);
+    for (int y = 0; y < 256; ++y)
+      for (int x = 0; x < 256; ++x) t[(size_t)y * 256 + x] = (float)atan2((double)y - 128, (double)x - 128);
+    SDR_CK_CREATE(cudaMalloc(&e->d_lut_wbfm, t.size() * 4));
+    SDR_CK_CREATE(cudaMemcpy(e->d_lut_wbfm, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+  }
+  SDR_CK_CREATE(cudaStreamSynchronize(e->stream));
+#undef SDR_CK_CREATE
+  *out = e;
+  return SDR_OK;
+}
+
+int sdr_engine_destroy(sdr_engine *e) {
+  if (!e) return SDR_E_ARG;
+  cudaSetDevice(e->device);
+  if (e->own_stream) cudaStreamSynchronize(e->own_stream);
+  for (int k = 1; k <= 4; ++k) {
+    cudaFree(e->d_state[k]);
+    cudaFree(e->d_scale[k]);
+    cudaFree(e->d_list[k]);
+  }
+  cudaFree(e->d_lsb);
+  cudaFree(e->d_lut_fm);
+  cudaFree(e->d_lut_wbfm);
+  cudaFree(e->d_iq);
+  cudaFree(e->d_pcm);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  delete e;
+  return SDR_OK;
+}
+
+int sdr_set_stream(sdr_engine *e, void *cuda_stream) {
+  if (!e) return SDR_E_ARG;
+  SDR_CK(e, cudaStreamSynchronize(e->stream));
+  e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+  return SDR_OK;
+}
+
+int sdr_set_scaling(sdr_engine *e, int scaling) {
+  if (!e || (scaling != SDR_SCALING_RADIODIAGS && scaling != SDR_SCALING_RESEARCH)) return SDR_E_ARG;
+  // the two trees also differ in the WBFM constructor gain; channels still at
+  // the old default follow the tree
+  const float old_def = default_gain(SDR_KIND_WBFM, e->scaling), new_def = default_gain(SDR_KIND_WBFM, scaling);
+  for (auto &g : e->gain[SDR_KIND_WBFM])
+    if (g == old_def) g = new_def;
+  e->scaling = scaling;
+  e->scale_dirty[SDR_KIND_FM] = e->scale_dirty[SDR_KIND_WBFM] = true;
+  return SDR_OK;
+}
+
+int sdr_set_mode(sdr_engine *e, uint32_t ch, int mode) {
+  if (!e || ch >= e->n || mode < SDR_MODE_NONE || mode > SDR_MODE_USB) return SDR_E_ARG;
+  if (e->mode[ch] != mode) {
+    e->mode[ch] = (uint8_t)mode;
+    e->lists_dirty = true;
+  }
+  // IqDataProcessor.cc:247-258: selecting Lsb/Usb also flips the SSB object's sideband
+  if (mode == SDR_MODE_LSB && !e->lsb[ch]) { e->lsb[ch] = 1; e->lsb_dirty = true; }
+  if (mode == SDR_MODE_USB && e->lsb[ch]) { e->lsb[ch] = 0; e->lsb_dirty = true; }
+  return SDR_OK;
+}
+
+int sdr_set_modes(sdr_engine *e, const uint8_t *modes) {
+  if (!e || !modes) return SDR_E_ARG;
+  for (uint32_t ch = 0; ch < e->n; ++ch)
+    if (modes[ch] > SDR_MODE_USB) return SDR_E_ARG;
+  for (uint32_t ch = 0; ch < e->n; ++ch) sdr_set_mode(e, ch, modes[ch]);
+  return SDR_OK;
+}
+
+int sdr_set_gain(sdr_engine *e, uint32_t ch, int kind, float gain) {
+  if (!e || ch >= e->n || kind < SDR_KIND_AM || kind > SDR_KIND_SSB) return SDR_E_ARG;
+  e->gain[kind][ch] = gain;
+  e->scale_dirty[kind] = true;
+  return SDR_OK;
+}
+
+int sdr_set_gain_all(sdr_engine *e, int kind, float gain) {
+  if (!e || kind < SDR_KIND_AM || kind > SDR_KIND_SSB) return SDR_E_ARG;
+  e->gain[kind].assign(e->n, gain);
+  e->scale_dirty[kind] = true;
+  return SDR_OK;
+}
+
+int sdr_reset(sdr_engine *e, uint32_t ch, int kind) {
+  if (!e || ch >= e->n || kind < SDR_KIND_AM || kind > SDR_KIND_SSB) return SDR_E_ARG;
+  SDR_CK(e, cudaSetDevice(e->device));
+  size_t sb = (size_t)state_bytes(kind), n = sb;
+  // WbFmDemodulator::resetDemodulator leaves the de-emphasis IIR alone
+  // (WbFmDemodulator.cc:304-320); its state is the last 16 bytes of the blob.
+  if (kind == SDR_KIND_WBFM) n -= 16;
+  SDR_CK(e, cudaMemsetAsync(e->d_state[kind] + sb * ch, 0, n, e->stream));
+  return SDR_OK;
+}
+
+int sdr_set_launch_shape(sdr_engine *e, int kind, uint32_t G, uint32_t NT) {
+  if (!e || kind < SDR_KIND_AM || kind > SDR_KIND_SSB || G > (uint32_t)MAX_G || NT > 1024 || NT % 32)
+    return SDR_E_ARG;
+  e->shape[kind].G = G;
+  e->shape[kind].NT = NT;
+  return SDR_OK;
+}
+
+uint64_t sdr_launch_count(const sdr_engine *e) { return e ? e->launches : 0; }
+
+int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_stride, uint32_t flags) {
+  if (!e || !iq) return SDR_E_ARG;
+  if (bytes == 0 || bytes % 64) return fail(e, SDR_E_ARG, "bytes_per_channel must be a positive multiple of 64");
+  if (bytes > e->max_bytes) return fail(e, SDR_E_TOO_LONG, "bytes_per_channel exceeds max_bytes_per_channel");
+  if (ch_stride < bytes || ch_stride % 16 || ((uintptr_t)iq & 15))
+    return fail(e, SDR_E_ARG, "iq pointer and channel_stride must be multiples of 16, stride >= bytes");
+  SDR_CK(e, cudaSetDevice(e->device));
+  int rc = upload_tables(e);
+  if (rc) return rc;
+  const uint8_t *dev_iq = (const uint8_t *)iq;
+  uint64_t dev_stride = ch_stride;
+  if (!(flags & SDR_IQ_DEVICE)) {
+    if (!e->d_iq) SDR_CK(e, cudaMalloc(&e->d_iq, (size_t)e->n * e->max_bytes));
+    SDR_CK(e, cudaMemcpy2DAsync(e->d_iq, bytes, iq, ch_stride, bytes, e->n, cudaMemcpyHostToDevice, e->stream));
+    dev_iq = e->d_iq;
+    dev_stride = bytes;
+  }
+  const int fmt = (flags & SDR_IQ_S8_ROTATED) ? FMT_S8_ROTATED : FMT_U8_OFFSET_ROTATE;
+  const uint32_t n_samples = (uint32_t)(bytes / 2);
+  if ((rc = launch_kind<AmPipe>(e, SDR_KIND_AM, dev_iq, dev_stride, n_samples, fmt))) return rc;
+  if ((rc = launch_kind<SsbPipe>(e, SDR_KIND_SSB, dev_iq, dev_stride, n_samples, fmt))) return rc;
+  if ((rc = launch_kind<FmPipe>(e, SDR_KIND_FM, dev_iq, dev_stride, n_samples, fmt))) return rc;
+  if ((rc = launch_kind<WbFmPipe>(e, SDR_KIND_WBFM, dev_iq, dev_stride, n_samples, fmt))) return rc;
+  e->last_samples = (uint32_t)(bytes / 64);
+  return SDR_OK;
+}
+
+int sdr_get_pcm(sdr_engine *e, int16_t *pcm, uint32_t *counts) {
+  if (!e) return SDR_E_ARG;
+  SDR_CK(e, cudaSetDevice(e->device));
+  if (pcm && e->last_samples)
+    SDR_CK(e, cudaMemcpy2DAsync(pcm, (size_t)e->last_samples * 2, e->d_pcm, e->pcm_stride * 2,
+                                (size_t)e->last_samples * 2, e->n, cudaMemcpyDeviceToHost, e->stream));
+  SDR_CK(e, cudaStreamSynchronize(e->stream));
+  if (counts)
+    for (uint32_t ch = 0; ch < e->n; ++ch) counts[ch] = e->mode[ch] == SDR_MODE_NONE ? 0 : e->last_samples;
+  return SDR_OK;
+}
+
+int sdr_pcm_device(sdr_engine *e, int16_t **pcm, uint64_t *stride) {
+  if (!e) return SDR_E_ARG;
+  if (pcm) *pcm = e->d_pcm;
+  if (stride) *stride = e->pcm_stride;
+  return SDR_OK;
+}
+
+int sdr_sync(sdr_engine *e) {
+  if (!e) return SDR_E_ARG;
+  SDR_CK(e, cudaStreamSynchronize(e->stream));
+  return SDR_OK;
+}
+
+}  // extern "C"

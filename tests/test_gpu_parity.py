@@ -1,0 +1,196 @@
+"""GPU parity: the CUDA engine, called through the C ABI, against the oracle on
+the same seeded inputs. Bit-exact for every mode (the float stages are written
+to round exactly like the reference, so the +-1 LSB allowance is not used).
+"""
+import numpy as np
+import pytest
+
+import _oracle as O
+import _signals as S
+
+pytestmark = pytest.mark.gpu
+
+KINDS = {1: "am", 2: "fm", 3: "wbfm", 4: "lsb", 5: "usb"}
+
+
+def _engine(n, max_bytes=32768):
+    import rtlsdrdiags_b200 as R
+    return R, R.Engine(n, 0, max_bytes)
+
+
+def _oracle_rows(modes, iq, gains=None):
+    rows = []
+    for ch, m in enumerate(modes):
+        c = O.OracleChain()
+        c.set_mode(int(m))
+        if gains is not None and int(m):
+            c.set_gain(O.MODE_TO_KIND[int(m)], float(gains[ch]))
+        rows.append(c.accept_u8(iq[ch]))
+    return rows
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("signal", ["noise", "tone"])
+def test_single_mode_bank_matches_oracle(mode, signal):
+    n, nbytes = 37, 32768 * 3
+    R, e = _engine(n)
+    e.set_modes(np.full(n, mode, dtype=np.uint8))
+    iq = S.noise(n, nbytes, seed=mode) if signal == "noise" else S.tone_bank([mode] * n, nbytes, seed=mode)
+    iq[0, : nbytes // 2] = 0
+    iq[1, : nbytes // 2] = 255
+    pcm, counts = e.demodulate(iq)
+    assert (counts == 512).all()
+    exp = _oracle_rows([mode] * n, iq)
+    for ch in range(n):
+        assert np.array_equal(pcm[ch], exp[ch]), "channel %d differs (max |d| = %d)" % (
+            ch, np.abs(pcm[ch].astype(int) - exp[ch].astype(int)).max())
+    assert e.launch_count == 3
+
+
+def test_mixed_mode_bank_and_none():
+    n, nbytes = 64, 32768 * 2
+    R, e = _engine(n)
+    modes = np.array([ch % 6 for ch in range(n)], dtype=np.uint8)
+    e.set_modes(modes)
+    iq = S.noise(n, nbytes, seed=99)
+    pcm, counts = e.demodulate(iq)
+    exp = _oracle_rows(modes, iq)
+    for ch in range(n):
+        if modes[ch] == 0:
+            assert counts[ch] == 0 and exp[ch].size == 0
+        else:
+            assert np.array_equal(pcm[ch], exp[ch]), "channel %d mode %d" % (ch, modes[ch])
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
+@pytest.mark.parametrize("shape", [(1, 32), (5, 96), (32, 1024), (7, 1024)])
+def test_launch_shapes(mode, shape):
+    n, nbytes = 45, 32768
+    R, e = _engine(n)
+    e.set_modes(np.full(n, mode, dtype=np.uint8))
+    e.set_launch_shape(R.MODE_TO_KIND[mode], *shape)
+    iq = S.noise(n, nbytes * 2, seed=7)
+    pcm, _ = e.demodulate(iq)
+    exp = _oracle_rows([mode] * n, iq)
+    for ch in range(n):
+        assert np.array_equal(pcm[ch], exp[ch])
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 5])
+def test_gains_large_and_small(mode):
+    n, nbytes = 12, 32768 * 2
+    R, e = _engine(n)
+    e.set_modes(np.full(n, mode, dtype=np.uint8))
+    base = {1: 300.0, 2: 10185.916, 3: 40743.664, 5: 300.0}[mode]
+    gains = [base * g for g in (0.0, 0.01, 0.5, 1.0, 2.0, 3.7, 10.0, 100.0, 1e4, 1e7, 1e12, 1e30)]
+    for ch, g in enumerate(gains):
+        e.set_gain(ch, R.MODE_TO_KIND[mode], g)
+    iq = S.noise(n, nbytes, seed=3)
+    pcm, _ = e.demodulate(iq)
+    exp = _oracle_rows([mode] * n, iq, gains=[np.float32(g) for g in gains])
+    for ch in range(n):
+        assert np.array_equal(pcm[ch], exp[ch]), "gain %g" % gains[ch]
+
+
+def test_block_partition_invariance_and_ragged_blocks():
+    """cutting the stream differently must not change the PCM."""
+    n = 10
+    R, e1 = _engine(n)
+    _, e2 = _engine(n)
+    modes = np.array([1 + ch % 5 for ch in range(n)], dtype=np.uint8)
+    e1.set_modes(modes)
+    e2.set_modes(modes)
+    # rotation phase restarts per call: pieces must be multiples of 8 bytes; the
+    # engine needs multiples of 64
+    sizes = [64, 128, 32768, 4096 + 64, 192, 8192]
+    iq = S.noise(n, sum(sizes), seed=5)
+    a = []
+    off = 0
+    for s in sizes:
+        p, _ = e1.demodulate(iq[:, off:off + s])
+        a.append(p)
+        off += s
+    a = np.concatenate(a, axis=1)
+    b, _ = e2.demodulate(iq)
+    assert np.array_equal(a, b)
+    exp = _oracle_rows(modes, iq)
+    for ch in range(n):
+        assert np.array_equal(b[ch], exp[ch])
+
+
+def test_mode_switch_preserves_idle_state_and_reset():
+    """IqDataProcessor.cc:793-835: idle demodulators keep their state; reset quirks."""
+    n, nb = 6, 32768
+    R, e = _engine(n)
+    chains = [O.OracleChain() for _ in range(n)]
+    rng = np.random.default_rng(17)
+    script = [("mode", 3), ("run",), ("mode", 2), ("run",), ("mode", 3), ("run",), ("reset", 3), ("run",),
+              ("mode", 4), ("run",), ("mode", 1), ("run",), ("mode", 5), ("run",), ("reset", 4), ("run",),
+              ("mode", 0), ("run",), ("mode", 2), ("reset", 2), ("run",)]
+    for step in script:
+        if step[0] == "mode":
+            for ch in range(n):
+                e.set_mode(ch, step[1])
+                chains[ch].set_mode(step[1])
+        elif step[0] == "reset":
+            kind = {1: 1, 2: 2, 3: 3, 4: 4}[step[1]]
+            for ch in range(0, n, 2):
+                e.reset(ch, kind)
+                chains[ch].reset(kind)
+        else:
+            iq = rng.integers(0, 256, size=(n, nb), dtype=np.uint8)
+            pcm, counts = e.demodulate(iq)
+            for ch in range(n):
+                exp = chains[ch].accept_u8(iq[ch])
+                assert counts[ch] == exp.size
+                if exp.size:
+                    assert np.array_equal(pcm[ch], exp)
+
+
+def test_signed_rotated_entry_and_research_scaling():
+    """The demodulator classes' own entry (signed, rotated IQ) and the research tree's scaling."""
+    n, nb = 8, 32768 * 2
+    R, e = _engine(n)
+    e.set_scaling(R.SCALING_RESEARCH)
+    modes = np.array([1, 2, 3, 4, 5, 2, 3, 1], dtype=np.uint8)
+    e.set_modes(modes)
+    iq = np.random.default_rng(23).integers(-128, 128, size=(n, nb), dtype=np.int8)
+    pcm, _ = e.demodulate(iq, fmt=R.IQ_S8_ROTATED)
+    for ch in range(n):
+        c = O.OracleChain(O.VARIANT_RESEARCH)
+        assert np.array_equal(pcm[ch], c.accept_s8(int(modes[ch]), iq[ch]))
+
+
+def test_device_resident_input_and_argument_errors():
+    import torch
+    n, nb = 16, 32768
+    R, e = _engine(n)
+    e.set_modes(np.full(n, 2, dtype=np.uint8))
+    iq = S.noise(n, nb, seed=2)
+    d = torch.from_numpy(iq).cuda()
+    e.accept_iq_device(d)
+    pcm, _ = e.get_pcm()
+    exp = _oracle_rows([2] * n, iq)
+    for ch in range(n):
+        assert np.array_equal(pcm[ch], exp[ch])
+    with pytest.raises(R.SdrError):
+        e.accept_iq_ptr(d.data_ptr(), 100, nb, R.IQ_DEVICE)          # not a multiple of 64
+    with pytest.raises(R.SdrError):
+        e.accept_iq_ptr(d.data_ptr(), nb * 2, nb * 2, R.IQ_DEVICE)   # longer than max_bytes
+    with pytest.raises(R.SdrError):
+        e.set_mode(n, 1)
+    with pytest.raises(R.SdrError):
+        e.set_mode(0, 6)
+
+
+def test_channel_permutation_and_duplicates():
+    """Identical channels give identical rows; permuting channels permutes rows."""
+    n, nb = 40, 32768
+    R, e = _engine(n)
+    modes = np.array([1 + ch % 5 for ch in range(n)], dtype=np.uint8)
+    e.set_modes(modes)
+    base = S.noise(5, nb, seed=77)
+    iq = base[np.arange(n) % 5]
+    pcm, _ = e.demodulate(iq)
+    for ch in range(5, n):
+        assert np.array_equal(pcm[ch], pcm[ch % 5])
