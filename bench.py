@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the IQ->PCM hot path on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload am|fm|wbfm|ssb|mixed]
+                    [--signal tone|noise] [--blocks T] [--impl reference] [--no-extras]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic IQ: every channel
+of the bank gets T reference blocks (T x 32768 bytes = T x 64 ms of signal) and comes
+out as T x 512 PCM samples. Channels shard across ranks with no data-path collective
+(weak scaling: the per-GPU bank is fixed); torch.distributed is used for the barrier
+and the max-over-ranks of the device-timed region only.
+
+Prints ONE JSON line (rank 0). `value` is whole-job complex-IQ Msamples/s with the
+input already resident in HBM; `e2e` is the same metric through the C ABI with host
+buffers (H2D of the IQ and D2H of the PCM inside the timed region); `roofline` puts
+the kernel against the measured HBM copy bandwidth; `cpu_baseline` is the reference's
+own CPU chain (oracle/_ref) on this box's host cores over a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_SAMPLE = 2.0 + 2.0 / 32.0  # 2 B of IQ read + one int16 PCM sample per 32
+BLOCK_BYTES = 32768
+METRIC = "aggregate_iq_msamples_per_s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=0, help="timed steps (0 = enough for ~2 s of device time)")
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="am", choices=["am", "fm", "wbfm", "ssb", "mixed"])
+    ap.add_argument("--signal", default="tone", choices=["tone", "noise"])
+    ap.add_argument("--blocks", type=int, default=0, help="reference blocks per channel per step (0 = auto)")
+    ap.add_argument("--channels", type=int, default=0, help="channels per GPU (0 = the workload's)")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary per-mode lines")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+def default_blocks(workload, channels):
+    # keep one step's input above the 126 MB L2 (and <= 4 GiB)
+    t = 1
+    while channels * t * BLOCK_BYTES < 512 * 1024 * 1024:
+        t *= 2
+    return t
+
+
+class ClockSampler:
+    """nvidia-smi samples DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def run_cpu_reference(workload, modes_np, n_blocks, seconds_target=6.0, signal="tone"):
+    """The reference's CPU chain on this box's host cores over a bounded sample of the
+    workload. Returns (Msamples/s, descriptor dict). Uses oracle/_ref (the unmodified
+    reference) when it was built, else the oracle port."""
+    import numpy as np
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_binding as O
+    from rtlsdrdiags_b200 import synth
+    cores = os.cpu_count() or 1
+    n_ch = min(int(modes_np.size), 8 * cores)
+    modes = np.ascontiguousarray(modes_np[:n_ch])
+    t_blocks = min(n_blocks, 4)
+    nbytes = t_blocks * BLOCK_BYTES
+    iq = synth.make_bank(signal, torch.from_numpy(modes.copy()), nbytes, 1234, "cpu").numpy()
+    use_ref = O.ref("radiodiags") is not None
+    kind = "reference" if use_ref else "port"
+    done, elapsed, reps = 0, 0.0, 0
+    while elapsed < seconds_target and reps < 1000:
+        if use_ref:
+            _, secs = O.ref_bank(modes, iq, BLOCK_BYTES, cores, want_pcm=False)
+        else:
+            _, secs = O.oracle_bank(modes, iq, BLOCK_BYTES, cores, want_pcm=False)
+        elapsed += secs
+        done += n_ch * nbytes // 2
+        reps += 1
+    msps = done / elapsed / 1e6
+    return msps, {"value": round(msps, 3), "unit": "Msamples/s", "cores": cores, "kind": kind,
+                  "sample": "%d channels x %d blocks of the %s workload, %d repetitions, %d host threads"
+                            % (n_ch, t_blocks, workload, reps, cores)}
+
+
+def bench_one(torch, R, synth, workload, channels, n_blocks, steps, warmup, signal, device, rank, world,
+              dist, want_e2e=True):
+    """Times `steps` passes of one workload on this rank. Returns a dict of local results."""
+    modes = synth.modes_for(workload, channels, first_channel=rank * channels)
+    nbytes = n_blocks * BLOCK_BYTES
+    eng = R.Engine(channels, device.index, nbytes)
+    eng.set_modes(modes.numpy())
+    # a dedicated (non-default) stream: the kernels are launched on it and the CUDA
+    # events that time them are recorded on it
+    stream = torch.cuda.Stream(device)
+    eng.set_stream(stream.cuda_stream)
+    iq = synth.make_bank(signal, modes, nbytes, 0xB200 + rank, device)
+    torch.cuda.synchronize(device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def timed(n):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(n):
+            eng.accept_iq_device(iq)
+        b.record(stream)
+        return a, b
+
+    # ---- device-resident: the kernel(s) alone ----
+    a, b = timed(max(warmup, 3))
+    barrier()
+    if steps <= 0:  # auto: about two seconds of device time, identical on every rank
+        per = reduce_max(torch, dist, world, device, a.elapsed_time(b) / max(warmup, 3))
+        steps = int(min(20000, max(30, 2000.0 / max(per, 1e-3))))
+    l0 = eng.launch_count
+    sampler = ClockSampler(device.index) if rank == 0 else None
+    barrier()
+    e0, e1 = timed(steps)
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count - l0
+    if clocks is not None:
+        clocks["sampled"] = "timed region"
+        if clocks["samples"] < 5:  # region too short for nvidia-smi: soak the same call for 1.5 s
+            sampler = ClockSampler(device.index)
+            t_end = time.time() + 1.5
+            while time.time() < t_end:
+                timed(20)
+                torch.cuda.synchronize(device)
+            clocks = sampler.stop()
+            clocks["sampled"] = "1.5 s soak of the same launch right after the timed region (region too short)"
+    res = {"ms_total": ms, "launches": launches, "clocks": clocks, "steps": steps,
+           "samples_per_step": channels * nbytes // 2, "h2d": channels * nbytes,
+           "d2h": channels * (nbytes // 64) * 2}
+
+    # ---- end to end through the C ABI: pinned host IQ in, host PCM out, every step ----
+    if want_e2e:
+        h_iq = torch.empty((channels, nbytes), dtype=torch.uint8, pin_memory=True)
+        h_iq.copy_(iq)
+        h_pcm = torch.empty((channels, nbytes // 64), dtype=torch.int16, pin_memory=True)
+        torch.cuda.synchronize(device)
+        for _ in range(min(warmup, 3)):
+            eng.accept_iq_ptr(h_iq.data_ptr(), nbytes, nbytes, R.IQ_HOST)
+            eng.get_pcm_ptr(h_pcm.data_ptr())
+        barrier()
+        n_e2e = 10
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            eng.accept_iq_ptr(h_iq.data_ptr(), nbytes, nbytes, R.IQ_HOST)
+            eng.get_pcm_ptr(h_pcm.data_ptr())  # synchronises: the step's result is on the host
+        torch.cuda.synchronize(device)
+        res["e2e_ms_total"] = (time.perf_counter() - t0) * 1e3
+        res["e2e_steps"] = n_e2e
+        res["pcm_checksum"] = int(h_pcm.to(torch.int64).sum().item())
+        del h_iq, h_pcm
+    eng.set_stream(0)
+    eng.close()
+    del iq
+    torch.cuda.empty_cache()
+    return res
+
+
+def reduce_max(torch, dist, world, device, x):
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    import numpy as np
+    from rtlsdrdiags_b200 import synth
+    wl_channels, _, wl_desc = synth.WORKLOADS[args.workload]
+    channels = args.channels or wl_channels
+    n_blocks = args.blocks or default_blocks(args.workload, channels)
+
+    if args.impl == "reference":
+        # the reference's own CPU implementation of the path, all host threads; rank 0 only
+        if rank != 0:
+            return 0
+        modes = synth.modes_for(args.workload, channels).numpy()
+        vals = []
+        desc = None
+        t_begin = time.time()
+        n_steps = args.steps if args.steps > 0 else 5
+        for i in range(args.warmup + n_steps):
+            v, desc = run_cpu_reference(args.workload, modes, n_blocks, seconds_target=1.0, signal=args.signal)
+            if i >= args.warmup:
+                vals.append(v)
+            if time.time() - t_begin > 150:
+                break
+        value = float(np.mean(vals)) if vals else v
+        desc["value"] = round(value, 3)
+        line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Msamples/s",
+                "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
+                "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "q15 int32 + f32", "data": "synthetic",
+                "config": {"workload": args.workload, "description": wl_desc, "signal": args.signal,
+                           "channels_per_gpu": channels, "blocks_per_channel_per_step": n_blocks},
+                "realtime_channels": round(value / 0.256, 1), "cpu_baseline": desc,
+                "e2e": {"value": round(value, 3), "unit": "Msamples/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    import torch
+    import rtlsdrdiags_b200 as R
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    if world != args.gpus and rank == 0:
+        print("note: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
+
+    res = bench_one(torch, R, synth, args.workload, channels, n_blocks, args.steps, args.warmup, args.signal,
+                    device, rank, world, dist)
+    ms_total = reduce_max(torch, dist, world, device, res["ms_total"])
+    e2e_ms_total = reduce_max(torch, dist, world, device, res["e2e_ms_total"])
+    total_samples_step = res["samples_per_step"] * world
+    steps = res["steps"]
+    value = total_samples_step * steps / (ms_total * 1e-3) / 1e6
+    e2e_value = total_samples_step * res["e2e_steps"] / (e2e_ms_total * 1e-3) / 1e6
+    peak, peak_src = peaks()
+    # the dominant kernel: one launch per demodulator kind per step; for single-mode
+    # workloads that is the only kernel in the timed region
+    kernel_ms = res["ms_total"] / steps
+    achieved = res["samples_per_step"] * ALGO_BYTES_PER_SAMPLE / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(args.workload)
+    except Exception:
+        pass
+
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        for wl in ["fm", "wbfm", "ssb", "mixed", "am"]:
+            if wl == args.workload:
+                continue
+            ch = synth.WORKLOADS[wl][0]
+            nb = default_blocks(wl, ch)
+            r = bench_one(torch, R, synth, wl, ch, nb, 40, 3, args.signal, device, 0, 1, None, want_e2e=False)
+            v = r["samples_per_step"] * r["steps"] / (r["ms_total"] * 1e-3) / 1e6
+            extras[wl] = {"value": round(v, 1), "unit": "Msamples/s", "channels": ch, "blocks": nb,
+                          "realtime_channels": round(v / 0.256),
+                          "roofline_frac": round(v * 1e6 * ALGO_BYTES_PER_SAMPLE / 1e9 / peak, 4)}
+        if args.signal == "tone":
+            r = bench_one(torch, R, synth, args.workload, channels, n_blocks, 40, 3, "noise", device, 0, 1,
+                          None, want_e2e=False)
+            v = r["samples_per_step"] * r["steps"] / (r["ms_total"] * 1e-3) / 1e6
+            extras[args.workload + "_noise_input"] = {"value": round(v, 1), "unit": "Msamples/s"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        modes = synth.modes_for(args.workload, channels).numpy()
+        _, cpu = run_cpu_reference(args.workload, modes, n_blocks, seconds_target=12.0, signal=args.signal)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "Msamples/s",
+            "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms_total / steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "q15 int32 + f32", "data": "synthetic",
+            "config": {"workload": args.workload, "description": wl_desc, "signal": args.signal,
+                       "channels_per_gpu": channels, "blocks_per_channel_per_step": n_blocks,
+                       "block_bytes": BLOCK_BYTES, "iq_bytes_per_gpu_per_step": res["h2d"],
+                       "l2": "input per step (%d MiB) exceeds the 126 MB L2; no flush needed" % (res["h2d"] >> 20),
+                       "sharding": "contiguous channel ranges per rank, no data-path collective"},
+            "realtime_channels": round(value / 0.256),
+            "realtime_channels_per_gpu": round(value / 0.256 / world),
+            "clocks": res["clocks"],
+            "e2e": {"value": round(e2e_value, 2), "unit": "Msamples/s", "h2d_bytes_per_step": res["h2d"] * world,
+                    "d2h_bytes_per_step": res["d2h"] * world, "steps": res["e2e_steps"],
+                    "api": "sdr_accept_iq(SDR_IQ_HOST) + sdr_get_pcm, pinned host buffers"},
+            "gpu_launches": res["launches"],
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE,
+                         "kernel_ms": round(kernel_ms, 4), "kernel": "demod_kernel<%s>" % args.workload},
+            "cpu_baseline": cpu,
+            "other_workloads": extras,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,272 @@
+"""ctypes bindings for the CHECKERS: oracle/liboracle.so (our C restatement) and,
+when present, oracle/_ref/libref_*.so (the unmodified reference compiled in place).
+
+Test infrastructure only: imported by tests/ (through tests/_oracle.py),
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+Nothing under rtlsdrdiags_b200/ imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ORACLE_DIR = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(ORACLE_DIR)
+
+MODE_NONE, MODE_AM, MODE_FM, MODE_WBFM, MODE_LSB, MODE_USB = range(6)
+KIND_AM, KIND_FM, KIND_WBFM, KIND_SSB = 1, 2, 3, 4
+VARIANT_RADIODIAGS, VARIANT_RESEARCH = 0, 1
+MODE_TO_KIND = {MODE_AM: KIND_AM, MODE_FM: KIND_FM, MODE_WBFM: KIND_WBFM,
+                MODE_LSB: KIND_SSB, MODE_USB: KIND_SSB}
+
+_vp, _u32, _i32, _f32 = C.c_void_p, C.c_uint32, C.c_int, C.c_float
+_pf = C.POINTER(C.c_float)
+_pi16 = C.POINTER(C.c_int16)
+_pi8 = C.POINTER(C.c_int8)
+_pu8 = C.POINTER(C.c_uint8)
+
+
+def build_oracle():
+    """(Re)build liboracle.so and, if /root/reference is mounted, oracle/_ref."""
+    subprocess.run(["make", "-s", "-C", ORACLE_DIR], check=True,
+                   stdout=subprocess.DEVNULL)
+
+
+def _ptr(a, t):
+    return a.ctypes.data_as(t)
+
+
+_oracle = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is not None:
+        return _oracle
+    path = os.path.join(ORACLE_DIR, "liboracle.so")
+    if not os.path.exists(path):
+        build_oracle()
+    L = C.CDLL(path)
+    L.sdro_dec16_new.restype = _vp
+    L.sdro_dec16_new.argtypes = [_i32, _pf, _i32]
+    L.sdro_dec16_free.argtypes = [_vp]
+    L.sdro_dec16_reset.argtypes = [_vp]
+    L.sdro_dec16_run.restype = _u32
+    L.sdro_dec16_run.argtypes = [_vp, _pi16, _u32, _pi16]
+    L.sdro_fir16_new.restype = _vp
+    L.sdro_fir16_new.argtypes = [_i32, _pf]
+    L.sdro_fir16_free.argtypes = [_vp]
+    L.sdro_fir16_run.argtypes = [_vp, _pi16, _u32, _pi16]
+    L.sdro_fir_new.restype = _vp
+    L.sdro_fir_new.argtypes = [_i32, _pf]
+    L.sdro_fir_free.argtypes = [_vp]
+    L.sdro_fir_run.argtypes = [_vp, _pf, _u32, _pf]
+    L.sdro_iir_new.restype = _vp
+    L.sdro_iir_new.argtypes = [_i32, _pf, _i32, _pf]
+    L.sdro_iir_free.argtypes = [_vp]
+    L.sdro_iir_run.argtypes = [_vp, _pf, _u32, _pf]
+    L.sdro_chain_new.restype = _vp
+    L.sdro_chain_new.argtypes = [_i32]
+    L.sdro_chain_free.argtypes = [_vp]
+    L.sdro_chain_set_mode.argtypes = [_vp, _i32]
+    L.sdro_chain_set_gain.argtypes = [_vp, _i32, _f32]
+    L.sdro_chain_reset.argtypes = [_vp, _i32]
+    L.sdro_chain_accept_u8.restype = _u32
+    L.sdro_chain_accept_u8.argtypes = [_vp, _pu8, _u32, _pi16, _u32]
+    L.sdro_chain_accept_s8.restype = _u32
+    L.sdro_chain_accept_s8.argtypes = [_vp, _i32, _pi8, _u32, _pi16, _u32]
+    L.sdro_q15_taps.restype = _i32
+    L.sdro_q15_taps.argtypes = [_i32, _pi16]
+    L.sdro_atan2f.restype = _f32
+    L.sdro_atan2f.argtypes = [_i32, _i32]
+    L.sdro_bank_run.restype = C.c_double
+    L.sdro_bank_run.argtypes = [_pu8, _u32, _pu8, C.c_uint64, _u32, _pi16, _u32, _i32]
+    _oracle = L
+    return L
+
+
+_refs = {}
+
+
+def ref(tree="radiodiags"):
+    """The compiled reference, or None when oracle/_ref was never built."""
+    if tree in _refs:
+        return _refs[tree]
+    path = os.path.join(ORACLE_DIR, "_ref", "libref_%s.so" % tree)
+    if not os.path.exists(path):
+        _refs[tree] = None
+        return None
+    L = C.CDLL(path)
+    L.ref_demod_new.restype = _vp
+    L.ref_demod_new.argtypes = [_i32]
+    L.ref_demod_free.argtypes = [_vp]
+    L.ref_demod_set_gain.argtypes = [_vp, _f32]
+    L.ref_demod_reset.argtypes = [_vp]
+    L.ref_ssb_set_lsb.argtypes = [_vp, _i32]
+    L.ref_demod_accept.restype = _u32
+    L.ref_demod_accept.argtypes = [_vp, _pi8, _u32, _pi16, _u32]
+    L.ref_dec16_new.restype = _vp
+    L.ref_dec16_new.argtypes = [_i32, _pf, _i32]
+    L.ref_dec16_free.argtypes = [_vp]
+    L.ref_dec16_run.restype = _u32
+    L.ref_dec16_run.argtypes = [_vp, _pi16, _u32, _pi16]
+    L.ref_fir16_new.restype = _vp
+    L.ref_fir16_new.argtypes = [_i32, _pf]
+    L.ref_fir16_free.argtypes = [_vp]
+    L.ref_fir16_run.argtypes = [_vp, _pi16, _u32, _pi16]
+    L.ref_fir_new.restype = _vp
+    L.ref_fir_new.argtypes = [_i32, _pf]
+    L.ref_fir_free.argtypes = [_vp]
+    L.ref_fir_run.argtypes = [_vp, _pf, _u32, _pf]
+    L.ref_iir_new.restype = _vp
+    L.ref_iir_new.argtypes = [_i32, _pf, _i32, _pf]
+    L.ref_iir_free.argtypes = [_vp]
+    L.ref_iir_run.argtypes = [_vp, _pf, _u32, _pf]
+    if tree == "radiodiags":
+        L.ref_iqp_new.restype = _vp
+        L.ref_iqp_free.argtypes = [_vp]
+        L.ref_iqp_set_mode.argtypes = [_vp, _i32]
+        L.ref_iqp_set_gain.argtypes = [_vp, _i32, _f32]
+        L.ref_iqp_reset.argtypes = [_vp, _i32]
+        L.ref_iqp_accept.restype = _u32
+        L.ref_iqp_accept.argtypes = [_vp, _pu8, _u32, _pi16, _u32]
+        L.ref_bank_run.restype = C.c_double
+        L.ref_bank_run.argtypes = [_pu8, _u32, _pu8, C.c_uint64, _u32, _pi16, _u32]
+    _refs[tree] = L
+    return L
+
+
+# ---------------------------------------------------------------- wrappers
+class OracleChain:
+    """One channel of the restated path (IqDataProcessor + four demodulators)."""
+
+    def __init__(self, variant=VARIANT_RADIODIAGS):
+        self.L = oracle()
+        self.h = self.L.sdro_chain_new(variant)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.sdro_chain_free(self.h)
+            self.h = None
+
+    def set_mode(self, mode):
+        self.L.sdro_chain_set_mode(self.h, mode)
+
+    def set_gain(self, kind, gain):
+        self.L.sdro_chain_set_gain(self.h, kind, gain)
+
+    def reset(self, kind):
+        self.L.sdro_chain_reset(self.h, kind)
+
+    def accept_u8(self, iq):
+        buf = np.array(iq, dtype=np.uint8, copy=True)
+        out = np.empty(buf.size // 64 + 2, dtype=np.int16)
+        n = self.L.sdro_chain_accept_u8(self.h, _ptr(buf, _pu8), buf.size, _ptr(out, _pi16), out.size)
+        return out[:n].copy()
+
+    def accept_s8(self, mode, iq):
+        buf = np.array(iq, dtype=np.int8, copy=True)
+        out = np.empty(buf.size // 64 + 2, dtype=np.int16)
+        n = self.L.sdro_chain_accept_s8(self.h, mode, _ptr(buf, _pi8), buf.size, _ptr(out, _pi16), out.size)
+        return out[:n].copy()
+
+
+class RefChain:
+    """One channel of the compiled reference product path (radioDiags tree)."""
+
+    def __init__(self):
+        self.L = ref("radiodiags")
+        if self.L is None:
+            raise RuntimeError("oracle/_ref not built")
+        self.h = self.L.ref_iqp_new()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_iqp_free(self.h)
+            self.h = None
+
+    def set_mode(self, mode):
+        self.L.ref_iqp_set_mode(self.h, mode)
+
+    def set_gain(self, kind, gain):
+        self.L.ref_iqp_set_gain(self.h, kind, gain)
+
+    def reset(self, kind):
+        self.L.ref_iqp_reset(self.h, kind)
+
+    def accept_u8(self, iq, block=32768):
+        buf = np.array(iq, dtype=np.uint8, copy=True)
+        out = np.empty(buf.size // 64 + 2, dtype=np.int16)
+        done = 0
+        for off in range(0, buf.size, block):
+            piece = buf[off:off + block]
+            done += self.L.ref_iqp_accept(self.h, _ptr(piece, _pu8), piece.size,
+                                          _ptr(out[done:], _pi16), out.size - done)
+        return out[:done].copy()
+
+
+class RefDemod:
+    """One reference demodulator object (either tree), fed signed rotated IQ."""
+
+    def __init__(self, kind, tree="radiodiags"):
+        self.L = ref(tree)
+        if self.L is None:
+            raise RuntimeError("oracle/_ref not built")
+        self.h = self.L.ref_demod_new(kind)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ref_demod_free(self.h)
+            self.h = None
+
+    def set_gain(self, g):
+        self.L.ref_demod_set_gain(self.h, g)
+
+    def reset(self):
+        self.L.ref_demod_reset(self.h)
+
+    def set_lsb(self, lsb):
+        self.L.ref_ssb_set_lsb(self.h, int(lsb))
+
+    def accept(self, iq, block=32768):
+        buf = np.array(iq, dtype=np.int8, copy=True)
+        out = np.empty(buf.size // 64 + 2, dtype=np.int16)
+        done = 0
+        for off in range(0, buf.size, block):
+            piece = buf[off:off + block]
+            done += self.L.ref_demod_accept(self.h, _ptr(piece, _pi8), piece.size,
+                                            _ptr(out[done:], _pi16), out.size - done)
+        return out[:done].copy()
+
+
+def oracle_bank(modes, iq_u8, block_bytes=32768, nthreads=1, variant=VARIANT_RADIODIAGS,
+                want_pcm=True):
+    """Run the restated path over a [n_channels][bytes] u8 bank. Returns (pcm, seconds)."""
+    L = oracle()
+    iq = np.array(iq_u8, dtype=np.uint8, copy=True)
+    n_ch, nbytes = iq.shape
+    modes = np.ascontiguousarray(modes, dtype=np.uint8)
+    pcm = np.zeros((n_ch, nbytes // 64), dtype=np.int16) if want_pcm else None
+    secs = L.sdro_bank_run(_ptr(modes, _pu8), n_ch, _ptr(iq, _pu8), nbytes, block_bytes,
+                           _ptr(pcm, _pi16) if want_pcm else None, nthreads, variant)
+    return pcm, secs
+
+
+def ref_bank(modes, iq_u8, block_bytes=32768, nthreads=1, want_pcm=True):
+    L = ref("radiodiags")
+    if L is None:
+        raise RuntimeError("oracle/_ref not built")
+    iq = np.array(iq_u8, dtype=np.uint8, copy=True)
+    n_ch, nbytes = iq.shape
+    modes = np.ascontiguousarray(modes, dtype=np.uint8)
+    pcm = np.zeros((n_ch, nbytes // 64), dtype=np.int16) if want_pcm else None
+    secs = L.ref_bank_run(_ptr(modes, _pu8), n_ch, _ptr(iq, _pu8), nbytes, block_bytes,
+                          _ptr(pcm, _pi16) if want_pcm else None, nthreads)
+    return pcm, secs
+
+
+def q15_taps(filter_id):
+    q = np.zeros(64, dtype=np.int16)
+    n = oracle().sdro_q15_taps(filter_id, _ptr(q, _pi16))
+    return q[:n].copy()

@@ -1,0 +1,116 @@
+"""Pins the oracle (oracle/sdr_oracle.c) to the reference.
+
+1. against tests/golden/golden_v1.npz -- outputs the UNMODIFIED reference produced
+   when compiled in place (tests/golden/make_golden.py); always runs;
+2. against the compiled reference itself (oracle/_ref) on fresh random inputs,
+   quirk vectors, gains and ragged blocks -- runs where oracle/_ref was built;
+3. against the md5s of the only IQ capture the reference ships
+   (demodulatorResearch/yoyo.iq) -- runs where /root/reference is mounted.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import _oracle as O
+
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_v1.npz"))
+NAMES = {1: "am", 2: "fm", 3: "wbfm", 4: "lsb", 5: "usb"}
+have_ref = O.ref("radiodiags") is not None and O.ref("research") is not None
+YOYO = "/root/reference/demodulatorResearch/yoyo.iq"
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5])
+def test_oracle_matches_golden_product_path(mode):
+    iq = GOLD["iq_u8"]
+    exp = GOLD["pcm_" + NAMES[mode]]
+    for ch in range(iq.shape[0]):
+        c = O.OracleChain()
+        c.set_mode(mode)
+        assert np.array_equal(c.accept_u8(iq[ch]), exp[ch]), "channel %d" % ch
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5])
+def test_oracle_matches_golden_research_tree(mode):
+    iq = GOLD["iq_s8"]
+    exp = GOLD["research_" + NAMES[mode]]
+    for ch in range(iq.shape[0]):
+        c = O.OracleChain(O.VARIANT_RESEARCH)
+        assert np.array_equal(c.accept_s8(mode, iq[ch]), exp[ch])
+
+
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("gmul", [1.0, 4.0, 1e6, 0.0])
+def test_oracle_matches_compiled_reference_noise_and_quirks(mode, gmul):
+    rng = np.random.default_rng(1000 * mode + int(gmul))
+    u8 = rng.integers(0, 256, size=32768 * 4, dtype=np.uint8)
+    u8[:4096] = 0
+    u8[4096:8192] = 255
+    u8[8192:12288:2] = 0
+    u8[8193:12288:2] = 255
+    kind = O.MODE_TO_KIND[mode]
+    base = {1: 300.0, 2: 10185.916, 3: 40743.664, 4: 300.0}[kind]
+    r, c = O.RefChain(), O.OracleChain()
+    for x in (r, c):
+        x.set_mode(mode)
+        x.set_gain(kind, base * gmul)
+    assert np.array_equal(r.accept_u8(u8), c.accept_u8(u8))
+
+
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref not built")
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
+def test_oracle_matches_compiled_reference_ragged_blocks_and_resets(mode):
+    rng = np.random.default_rng(mode)
+    r, c = O.RefChain(), O.OracleChain()
+    r.set_mode(mode)
+    c.set_mode(mode)
+    kind = O.MODE_TO_KIND[mode]
+    for i, n in enumerate([8, 24, 32768, 1000, 4096 + 8, 16, 2, 32768, 6]):
+        u8 = rng.integers(0, 256, size=n, dtype=np.uint8)
+        assert np.array_equal(r.accept_u8(u8), c.accept_u8(u8)), "piece %d" % i
+        if i == 4:
+            r.reset(kind)
+            c.reset(kind)
+
+
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref not built")
+def test_oracle_mode_switch_keeps_idle_state_like_reference():
+    rng = np.random.default_rng(5)
+    r, c = O.RefChain(), O.OracleChain()
+    for mode in [3, 2, 3, 4, 1, 5, 0, 4, 2]:
+        r.set_mode(mode)
+        c.set_mode(mode)
+        u8 = rng.integers(0, 256, size=32768, dtype=np.uint8)
+        assert np.array_equal(r.accept_u8(u8), c.accept_u8(u8)), "mode %d" % mode
+
+
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref not built")
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5])
+def test_oracle_matches_research_tree_direct_entry(mode):
+    s8 = np.random.default_rng(70 + mode).integers(-128, 128, size=32768 * 3, dtype=np.int8)
+    d = O.RefDemod(O.MODE_TO_KIND[mode], "research")
+    if mode in (4, 5):
+        d.set_lsb(mode == 4)
+    c = O.OracleChain(O.VARIANT_RESEARCH)
+    assert np.array_equal(d.accept(s8, block=16384), c.accept_s8(mode, s8))
+
+
+@pytest.mark.skipif(not os.path.exists(YOYO), reason="reference tree not mounted")
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5])
+def test_oracle_reproduces_yoyo_md5s(mode):
+    yoyo = np.fromfile(YOYO, dtype=np.int8)
+    assert hashlib.md5(yoyo.tobytes()).hexdigest() == str(GOLD["yoyo_md5_input"])
+    c = O.OracleChain(O.VARIANT_RESEARCH)
+    got = hashlib.md5(c.accept_s8(mode, yoyo).tobytes()).hexdigest()
+    assert got == str(GOLD["yoyo_md5_research_" + NAMES[mode]])
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "make_golden", os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    c = O.OracleChain()
+    c.set_mode(mode)
+    got = hashlib.md5(c.accept_u8(mg.unrotate_to_u8(yoyo)).tobytes()).hexdigest()
+    assert got == str(GOLD["yoyo_md5_radiodiags_" + NAMES[mode]])
