@@ -44,6 +44,25 @@ def build(force=False, defines=(), verbose=False):
     return LIB
 
 
+HOST = os.path.join(PKG, "host")
+DEMOD = os.path.join(PKG, "b200_demod")
+
+
+def build_host(force=False):
+    """Compile the C++ drop-in classes and the offline driver (g++, links libsdr_b200.so)."""
+    srcs = [os.path.join(HOST, f) for f in ("B200Demodulator.cc", "IqDataProcessor.cc", "demod_main.cc")]
+    deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".h")] + [LIB]
+    if not force and os.path.exists(DEMOD) and all(os.path.getmtime(d) <= os.path.getmtime(DEMOD) for d in deps):
+        return DEMOD
+    cmd = ["g++", "-O2", "-std=c++11", "-Wall", "-I", HOST, "-o", DEMOD] + srcs + \
+          ["-L", PKG, "-lsdr_b200", "-Wl,-rpath,$ORIGIN", "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n%s\n%s" % (" ".join(cmd), r.stderr))
+    return DEMOD
+
+
 if __name__ == "__main__":
     import sys
     print(build(force=True, verbose="-v" in sys.argv))
+    print(build_host(force=True))

@@ -1,0 +1,82 @@
+"""The C++ drop-in classes (rtlsdrdiags_b200/host: AmDemodulator, FmDemodulator,
+WbFmDemodulator, SsbDemodulator, IqDataProcessor) and the offline driver b200_demod,
+the counterpart of the reference's demod.cc."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import _oracle as O
+import _signals as S
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "rtlsdrdiags_b200", "host")
+
+
+def _demod():
+    from rtlsdrdiags_b200 import _build
+    _build.build()
+    return _build.build_host()
+
+
+def test_facade_keeps_the_reference_surface():
+    """Same class names, constructor and method signatures as the reference headers
+    (FmDemodulator.h:23-31, SsbDemodulator.h:24-34, IqDataProcessor.h:16-58)."""
+    _demod()
+    base = open(os.path.join(HOST, "B200Demodulator.h")).read()
+    for sig in ["void resetDemodulator(void);", "void setDemodulatorGain(float gain);",
+                "void acceptIqData(int8_t *bufferPtr, uint32_t bufferLength);"]:
+        assert sig in base
+    for cls in ["Am", "Fm", "WbFm", "Ssb"]:
+        h = open(os.path.join(HOST, cls + "Demodulator.h")).read()
+        assert "class %sDemodulator" % cls in h
+        assert "%sDemodulator(void (*pcmCallbackPtr)(int16_t *bufferPtr, uint32_t bufferLength))" % cls in h
+        assert "void displayInternalInformation(void)" in h
+    ssb = open(os.path.join(HOST, "SsbDemodulator.h")).read()
+    assert "void setLsbDemodulationMode(void)" in ssb and "void setUsbDemodulationMode(void)" in ssb
+    iqp = open(os.path.join(HOST, "IqDataProcessor.h")).read()
+    assert "enum demodulatorType {None = 0, Am = 1, Fm = 2, WbFm = 3, Lsb = 4, Usb = 5};" in iqp
+    assert "void acceptIqData(unsigned long timeStamp, unsigned char *bufferPtr, unsigned long byteCount);" in iqp
+    assert "IqDataProcessor(char *hostIpAddress, int hostPort);" in iqp
+
+
+def test_driver_refuses_to_run_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([_demod(), "-d", "2"], input=b"", capture_output=True)
+    assert r.returncode == 2 and b"no CPU path" in r.stderr
+
+
+def _run(args, data):
+    r = subprocess.run([_demod()] + args, input=data.tobytes(), capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()
+    return np.frombuffer(r.stdout, dtype=np.int16)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [1, 2, 3, 4, 5])
+def test_driver_signed_input_matches_research_tree(mode):
+    """b200_demod -r -d N == demod.cc -d N (research scaling, 16384-byte reads, -d 4 == USB)."""
+    s8 = np.random.default_rng(mode).integers(-128, 128, size=16384 * 9 + 4096 + 40, dtype=np.int8)
+    got = _run(["-d", str(mode), "-r"], s8)
+    c = O.OracleChain(O.VARIANT_RESEARCH)
+    exp = c.accept_s8(5 if mode == 4 else mode, s8)
+    assert np.array_equal(got, exp)
+    if mode == 4:
+        got = _run(["-d", "4", "-r", "-l"], s8)
+        assert np.array_equal(got, O.OracleChain(O.VARIANT_RESEARCH).accept_s8(4, s8))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", [1, 2, 3, 5])
+@pytest.mark.parametrize("block", [32768, 4096 + 8, 1000])
+def test_driver_raw_u8_input_matches_product_path(mode, block):
+    """b200_demod -u: IqDataProcessor -> demodulator, any block size that is a multiple of 8."""
+    u8 = S.noise(1, block * 7, seed=mode)[0]
+    got = _run(["-d", str(mode), "-u", "-b", str(block)], u8)
+    c = O.OracleChain()
+    c.set_mode(mode)
+    exp = np.concatenate([c.accept_u8(u8[o:o + block]) for o in range(0, u8.size, block)])
+    assert np.array_equal(got, exp)
