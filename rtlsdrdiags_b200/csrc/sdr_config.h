@@ -3,6 +3,7 @@
 // (or more CTAs) share an SM's shared memory. Overridable with -D for sweeps.
 #pragma once
 #include "sdr_device.cuh"
+#include "sdr_tile.cuh"
 
 #ifndef SDR_S_AM
 #define SDR_S_AM 1024

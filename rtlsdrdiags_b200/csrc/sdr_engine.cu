@@ -81,10 +81,10 @@ int fail(sdr_engine *e, int code, const char *what, cudaError_t ce = cudaSuccess
 
 int state_bytes(int kind) {
   switch (kind) {
-    case SDR_KIND_AM: return AmPipe::STATE_BYTES;
+    case SDR_KIND_AM: return AmSsbTile<false>::STATE_BYTES;
     case SDR_KIND_FM: return FmPipe::STATE_BYTES;
     case SDR_KIND_WBFM: return WbFmPipe::STATE_BYTES;
-    case SDR_KIND_SSB: return SsbPipe::STATE_BYTES;
+    case SDR_KIND_SSB: return AmSsbTile<true>::STATE_BYTES;
   }
   return -1;
 }
@@ -187,6 +187,59 @@ int launch_kind(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride, 
   SDR_CK(e, cudaFuncSetAttribute(demod_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const uint32_t grid = (n_list + s.G - 1) / s.G;
   demod_kernel<M><<<grid, s.NT, smem, e->stream>>>(p);
+  SDR_CK(e, cudaGetLastError());
+  e->launches++;
+  return SDR_OK;
+}
+
+// Warp-tile kernels: G = worker warps (= channels) per CTA, one more warp runs the
+// recurrences. Pick the CTA size that leaves the fewest idle channel slots per wave.
+uint32_t choose_workers(const sdr_engine *e, uint32_t n_list, int max_workers) {
+  uint32_t best = 1;
+  double best_eff = -1;
+  for (int R = 1; R <= 2; ++R) {
+    const long gmax = R == 1 ? max_workers : max_workers / 2;
+    const long slots = (long)e->n_sm * R;
+    const long W = ((long)n_list + slots * gmax - 1) / (slots * gmax);
+    const long G = ((long)n_list + slots * W - 1) / (slots * W);
+    const long ctas = ((long)n_list + G - 1) / G;
+    const long waves = (ctas + slots - 1) / slots;
+    const double eff = (double)n_list / (double)(waves * slots * G);
+    if (eff > best_eff + 1e-9) {
+      best_eff = eff;
+      best = (uint32_t)G;
+    }
+  }
+  return best;
+}
+
+template <bool SSB>
+int launch_amssb_tile(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples, int fmt) {
+  using T = AmSsbTile<SSB>;
+  const uint32_t n_list = (uint32_t)e->list[kind].size();
+  if (n_list == 0) return SDR_OK;
+  uint32_t G = choose_workers(e, n_list, T::MAX_WORKERS);
+  if (e->shape[kind].G) G = e->shape[kind].G;
+  if (G > (uint32_t)T::MAX_WORKERS) G = T::MAX_WORKERS;
+  const int smem = T::smem_bytes((int)G);
+  LaunchParams p;
+  p.iq = iq;
+  p.ch_stride = ch_stride;
+  p.n_samples = n_samples;
+  p.fmt = fmt;
+  p.chan_ids = e->d_list[kind];
+  p.n_list = n_list;
+  p.G = G;
+  p.state = e->d_state[kind];
+  p.state_stride = (uint32_t)T::STATE_BYTES;
+  p.scale = e->d_scale[kind];
+  p.lsb = e->d_lsb;
+  p.pcm = e->d_pcm;
+  p.pcm_stride = e->pcm_stride;
+  p.lut = nullptr;
+  SDR_CK(e, cudaFuncSetAttribute(amssb_tile_kernel<SSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const uint32_t grid = (n_list + G - 1) / G;
+  amssb_tile_kernel<SSB><<<grid, 32 * (G + 1), smem, e->stream>>>(p);
   SDR_CK(e, cudaGetLastError());
   e->launches++;
   return SDR_OK;
@@ -415,8 +468,8 @@ int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_str
   }
   const int fmt = (flags & SDR_IQ_S8_ROTATED) ? FMT_S8_ROTATED : FMT_U8_OFFSET_ROTATE;
   const uint32_t n_samples = (uint32_t)(bytes / 2);
-  if ((rc = launch_kind<AmPipe>(e, SDR_KIND_AM, dev_iq, dev_stride, n_samples, fmt))) return rc;
-  if ((rc = launch_kind<SsbPipe>(e, SDR_KIND_SSB, dev_iq, dev_stride, n_samples, fmt))) return rc;
+  if ((rc = launch_amssb_tile<false>(e, SDR_KIND_AM, dev_iq, dev_stride, n_samples, fmt))) return rc;
+  if ((rc = launch_amssb_tile<true>(e, SDR_KIND_SSB, dev_iq, dev_stride, n_samples, fmt))) return rc;
   if ((rc = launch_kind<FmPipe>(e, SDR_KIND_FM, dev_iq, dev_stride, n_samples, fmt))) return rc;
   if ((rc = launch_kind<WbFmPipe>(e, SDR_KIND_WBFM, dev_iq, dev_stride, n_samples, fmt))) return rc;
   e->last_samples = (uint32_t)(bytes / 64);

@@ -1,0 +1,340 @@
+// Warp-tile kernels (device only).
+//
+// One WORKER WARP owns one channel and walks its stream in tiles of 1024 complex
+// samples (2048 input bytes). Lane l owns the tile's samples [32 l, 32 l + 32):
+// exactly the input of one 8 kS/s PCM sample, because the reference's three
+// decimators divide by 4 * 4 * 2 = 32. Every FIR stage therefore runs in
+// registers; the few older samples a stage needs come from the lanes below by
+// warp shuffle, and lanes near 0 reach into the PREVIOUS tile, whose registers the
+// warp keeps (shfl_prev). No shared-memory staging of stage data, no CTA barrier
+// between stages.
+//
+// Input arrives by cp.async (LDGSTS, 16 B per lane, fully coalesced) into a
+// double-buffered, XOR-swizzled 2 KB slot per warp, so the tile after the current
+// one is in flight while the current one is computed and both the global reads
+// and the per-lane 64-byte shared reads are conflict free.
+//
+// The strictly sequential recurrences (DC-removal IIR; IirFilter.cc:161-176) run
+// in one extra warp per CTA with lane == channel, one tile behind the workers; a
+// single CTA barrier per tile round hands the 32 values per channel over.
+#pragma once
+#include "sdr_device.cuh"
+
+#if SDR_DEVICE_BUILD
+namespace sdr {
+
+constexpr int TILE = 1024;             // complex samples per tile
+constexpr int TILE_BYTES = 2 * TILE;   // input bytes per tile
+constexpr unsigned FULL = 0xffffffffu;
+
+// value of "virtual lane (lane - j)": lanes below j read the previous tile's register
+template <class T>
+__device__ __forceinline__ T shfl_prev(T cur, T prev, int j, int lane) {
+  return __shfl_sync(FULL, lane >= 32 - j ? prev : cur, (lane - j) & 31);
+}
+// after a tile with r valid lanes (1..32): the registers of the last 32 lanes of the stream
+template <class T>
+__device__ __forceinline__ T roll_prev(T cur, T prev, int r, int lane) {
+  return __shfl_sync(FULL, lane >= r ? prev : cur, (lane + r) & 31);
+}
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// 16-byte chunk q of a tile lives in slot q ^ ((q >> 3) & 3): conflict-free both for
+// the coalesced fill (lane writes chunk 32 j + lane) and for the per-lane read of
+// four consecutive chunks (lane reads chunks 4 lane + j).
+__device__ __forceinline__ int tile_slot(int q) { return q ^ ((q >> 3) & 3); }
+
+__device__ __forceinline__ void tile_fill(char *slot_base, const uint8_t *src, int lane, int valid_chunks) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int q = 32 * j + lane;
+    if (q < valid_chunks) cp_async16(slot_base + 16 * tile_slot(q), src + 16 * q);
+  }
+}
+__device__ __forceinline__ void tile_read(const char *slot_base, int lane, uint32_t (&w)[16]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const u32x4 v = lds_u4(slot_base + 16 * tile_slot(4 * lane + j));
+    w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// AM / SSB
+// ---------------------------------------------------------------------------
+// registers a worker carries from tile to tile (per lane)
+template <bool SSB>
+struct AmSsbCarry {
+  uint32_t a7, b7;            // last rotation group of the lane: I' and Q' words
+  uint32_t s1a0, s1a1, s1b0, s1b1;  // the lane's eight stage-1 outputs per arm (int8 x 4)
+  uint32_t p;                 // stage-2 outputs: I pair in bytes 0-1, Q pair in bytes 2-3
+  int y3a, y3b;               // SSB: stage-3 outputs (delay line and Hilbert history)
+};
+
+template <bool SSB>
+struct AmSsbTile {
+  static constexpr int NREG = SSB ? 9 : 7;
+  // state blob: NREG words per lane, then x[n-1], y[n-1] of the DC-removal IIR
+  static constexpr int STATE_BYTES = NREG * 128 + 16;
+  static constexpr int MAX_WORKERS = 15;
+  // shared memory per CTA for `nw` workers
+  static constexpr int IN_BYTES = 2 * TILE_BYTES;         // per worker: double-buffered input
+  // rows read or written 128 bits at a time with lane == channel: a row stride of
+  // 16 (mod 128) bytes keeps every quarter-warp on distinct banks
+  static constexpr int DEM_WORDS = 36;                    // per worker per parity: 32 values + pad
+  static constexpr int PCM_WORDS = 20;                    // per worker: 32 int16 (16 words) + pad
+  __host__ __device__ static constexpr int smem_bytes(int nw) {
+    return nw * IN_BYTES + 2 * nw * DEM_WORDS * 4 + nw * PCM_WORDS * 4 + 64;
+  }
+
+  __device__ __forceinline__ static void load_carry(AmSsbCarry<SSB> &c, const uint32_t *blob, int lane) {
+    c.a7 = blob[0 * 32 + lane]; c.b7 = blob[1 * 32 + lane];
+    c.s1a0 = blob[2 * 32 + lane]; c.s1a1 = blob[3 * 32 + lane];
+    c.s1b0 = blob[4 * 32 + lane]; c.s1b1 = blob[5 * 32 + lane];
+    c.p = blob[6 * 32 + lane];
+    if constexpr (SSB) { c.y3a = (int)blob[7 * 32 + lane]; c.y3b = (int)blob[8 * 32 + lane]; }
+    else { c.y3a = 0; c.y3b = 0; }
+  }
+  __device__ __forceinline__ static void store_carry(const AmSsbCarry<SSB> &c, uint32_t *blob, int lane) {
+    blob[0 * 32 + lane] = c.a7; blob[1 * 32 + lane] = c.b7;
+    blob[2 * 32 + lane] = c.s1a0; blob[3 * 32 + lane] = c.s1a1;
+    blob[4 * 32 + lane] = c.s1b0; blob[5 * 32 + lane] = c.s1b1;
+    blob[6 * 32 + lane] = c.p;
+    if constexpr (SSB) { blob[7 * 32 + lane] = (uint32_t)c.y3a; blob[8 * 32 + lane] = (uint32_t)c.y3b; }
+  }
+
+  // One tile of one channel. `w` = the lane's 64 input bytes. Returns what the
+  // recurrence warp consumes for this lane's PCM sample: AM the magnitude estimate
+  // (as float bits), SSB the phased sum (float bits). Updates the carry to this
+  // tile's registers rolled by r valid lanes.
+  __device__ __forceinline__ static uint32_t tile(const uint32_t (&w)[16], int fmt, bool lsb, AmSsbCarry<SSB> &pv, int lane, int r) {
+    AmSsbCarry<SSB> cu;
+    uint32_t a[8], b[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) front_end_group(fmt, w[2 * g], w[2 * g + 1], a[g], b[g]);
+    cu.a7 = a[7];
+    cu.b7 = b[7];
+
+    // stage 1: 8 taps, 4:1 (AmDemodulator.cc:349-374 through Decimator_int16)
+    const uint32_t am1 = shfl_prev(a[7], pv.a7, 1, lane), bm1 = shfl_prev(b[7], pv.b7, 1, lane);
+    int ya[8], yb[8];
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const uint32_t wa[2] = {m == 0 ? am1 : a[m == 0 ? 0 : m - 1], a[m]};
+      const uint32_t wb[2] = {m == 0 ? bm1 : b[m == 0 ? 0 : m - 1], b[m]};
+      ya[m] = fir_s8<taps::AM1, 7, 2>(wa) >> 15;
+      yb[m] = fir_s8<taps::AM1, 7, 2>(wb) >> 15;
+    }
+    cu.s1a0 = pack_i8x4(ya[0], ya[1], ya[2], ya[3]);
+    cu.s1a1 = pack_i8x4(ya[4], ya[5], ya[6], ya[7]);
+    cu.s1b0 = pack_i8x4(yb[0], yb[1], yb[2], yb[3]);
+    cu.s1b1 = pack_i8x4(yb[4], yb[5], yb[6], yb[7]);
+
+    // stage 2: 12 taps, 4:1
+    const uint32_t pa0 = shfl_prev(cu.s1a0, pv.s1a0, 1, lane), pa1 = shfl_prev(cu.s1a1, pv.s1a1, 1, lane);
+    const uint32_t pb0 = shfl_prev(cu.s1b0, pv.s1b0, 1, lane), pb1 = shfl_prev(cu.s1b1, pv.s1b1, 1, lane);
+    int za0, za1, zb0, zb1;
+    {
+      const uint32_t w0[3] = {pa0, pa1, cu.s1a0}, w1[3] = {pa1, cu.s1a0, cu.s1a1};
+      za0 = fir_s8<taps::AM2, 11, 3>(w0) >> 15;
+      za1 = fir_s8<taps::AM2, 11, 3>(w1) >> 15;
+      const uint32_t v0[3] = {pb0, pb1, cu.s1b0}, v1[3] = {pb1, cu.s1b0, cu.s1b1};
+      zb0 = fir_s8<taps::AM2, 11, 3>(v0) >> 15;
+      zb1 = fir_s8<taps::AM2, 11, 3>(v1) >> 15;
+    }
+    cu.p = pack_i8x4(za0, za1, zb0, zb1);
+
+    // stage 3: 16 taps, 2:1. Window word i holds stage-2 samples at positions 2i, 2i+1
+    // (I in bytes 0-1, Q in bytes 2-3); position pos meets tap 15 - pos.
+    uint32_t q[8];
+    q[7] = cu.p;
+#pragma unroll
+    for (int j = 1; j < 8; ++j) q[7 - j] = shfl_prev(cu.p, pv.p, j, lane);
+    int acc_i = 1 << 14, acc_q = 1 << 14;
+    stage3<0>(q, acc_i, acc_q);
+    cu.y3a = (int)(int16_t)(acc_i >> 15);
+    cu.y3b = (int)(int16_t)(acc_q >> 15);
+
+    uint32_t out;
+    if constexpr (!SSB) {
+      // magnitude estimate, tie -> q branch (AmDemodulator.cc:441-458)
+      const int im = (int)(int16_t)iabs(cu.y3a), qm = (int)(int16_t)iabs(cu.y3b);
+      const int mag = (int)(int16_t)(im > qm ? im + (qm >> 1) : qm + (im >> 1));
+      out = f2u(i2f(mag));
+    } else {
+      // phasing network (SsbDemodulator.cc:569-590): delay line {0 x15, -32768}, Hilbert 31 taps
+      const int x15 = shfl_prev(cu.y3a, pv.y3a, 15, lane);
+      int acc = (1 << 14) + taps::SSB_DELAY::tap(15) * x15;
+      acc = acc > 0x3fffffff ? 0x3fffffff : acc;
+      acc = acc < -0x40000000 ? -0x40000000 : acc;
+      const int i_delayed = (int)(int16_t)(acc >> 15);
+      int h = (1 << 14) + taps::SSB_HILBERT::tap(0) * cu.y3b;
+      hilbert<2>(h, cu.y3b, pv.y3b, lane);
+      const int q_shifted = (int)(int16_t)(h >> 15);
+      out = f2u(i2f(lsb ? i_delayed - q_shifted : i_delayed + q_shifted));
+    }
+
+    // the last 32 lanes of the stream become the next tile's "previous" registers
+    pv.a7 = roll_prev(cu.a7, pv.a7, r, lane); pv.b7 = roll_prev(cu.b7, pv.b7, r, lane);
+    pv.s1a0 = roll_prev(cu.s1a0, pv.s1a0, r, lane); pv.s1a1 = roll_prev(cu.s1a1, pv.s1a1, r, lane);
+    pv.s1b0 = roll_prev(cu.s1b0, pv.s1b0, r, lane); pv.s1b1 = roll_prev(cu.s1b1, pv.s1b1, r, lane);
+    pv.p = roll_prev(cu.p, pv.p, r, lane);
+    if constexpr (SSB) {
+      pv.y3a = roll_prev(cu.y3a, pv.y3a, r, lane);
+      pv.y3b = roll_prev(cu.y3b, pv.y3b, r, lane);
+    }
+    return out;
+  }
+
+  template <int I>
+  __device__ __forceinline__ static void stage3(const uint32_t (&q)[8], int &acc_i, int &acc_q) {
+    if constexpr (I < 8) {
+      constexpr uint32_t t = pack16(taps::AM3::tap(15 - 2 * I), taps::AM3::tap(14 - 2 * I));
+      acc_i = dp2a_lo_ss(t, q[I], acc_i);
+      acc_q = dp2a_hi_ss(t, q[I], acc_q);
+      stage3<I + 1>(q, acc_i, acc_q);
+    }
+  }
+  // even taps only (odd taps are zero); |x| <= 179 so the per-tap clamp cannot fire
+  template <int K>
+  __device__ __forceinline__ static void hilbert(int &h, int cur, int prev, int lane) {
+    if constexpr (K <= 30) {
+      h += taps::SSB_HILBERT::tap(K) * shfl_prev(cur, prev, K, lane);
+      hilbert<K + 2>(h, cur, prev, lane);
+    }
+  }
+};
+
+// blockDim = 32 * (workers + 1); the last warp runs the recurrences.
+template <bool SSB>
+__global__ void __launch_bounds__(512, 1) amssb_tile_kernel(const __grid_constant__ LaunchParams p) {
+  using T = AmSsbTile<SSB>;
+  extern __shared__ uint4 smem_raw[];
+  char *smem = reinterpret_cast<char *>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nw = (int)(blockDim.x >> 5) - 1;  // workers in this CTA
+  char *in_base = smem;
+  uint32_t *dem = reinterpret_cast<uint32_t *>(smem + nw * T::IN_BYTES);
+  uint32_t *pcm_s = dem + 2 * nw * T::DEM_WORDS;
+
+  const uint32_t list0 = blockIdx.x * (uint32_t)nw;
+  const int n_here = (int)min((uint32_t)nw, p.n_list - list0);  // channels this CTA owns
+  const uint32_t n_tiles = (p.n_samples + TILE - 1) / TILE;
+  const int fmt = p.fmt;
+
+  if (warp < nw) {
+    // ------------------------------ worker ------------------------------
+    const bool active = warp < n_here;
+    uint32_t ch = 0;
+    const uint8_t *src = nullptr;
+    AmSsbCarry<SSB> pv;
+    bool lsb = false;
+    char *slots = in_base + warp * T::IN_BYTES;
+    if (active) {
+      ch = p.chan_ids[list0 + warp];
+      src = p.iq + (uint64_t)ch * p.ch_stride;
+      T::load_carry(pv, reinterpret_cast<const uint32_t *>(p.state + (uint64_t)ch * p.state_stride), lane);
+      if (SSB) lsb = p.lsb[ch] != 0;
+      const int valid0 = (int)min((uint32_t)TILE, p.n_samples) >> 3;  // 16-byte chunks in tile 0
+      tile_fill(slots, src, lane, valid0);
+    }
+    cp_async_commit();
+    for (uint32_t k = 0; k <= n_tiles; ++k) {
+      if (active && k < n_tiles) {
+        if (k + 1 < n_tiles) {
+          const uint32_t s1 = (k + 1) * TILE;
+          const int valid = (int)min((uint32_t)TILE, p.n_samples - s1) >> 3;
+          tile_fill(slots + ((k + 1) & 1) * TILE_BYTES, src + (uint64_t)s1 * 2, lane, valid);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        uint32_t w[16];
+        tile_read(slots + (k & 1) * TILE_BYTES, lane, w);
+        const int r = (int)min((uint32_t)TILE, p.n_samples - k * TILE) >> 5;  // valid lanes
+        const uint32_t v = T::tile(w, fmt, lsb, pv, lane, r);
+        dem[((k & 1) * nw + warp) * T::DEM_WORDS + lane] = v;
+        __syncwarp();  // every lane has read slot k&1 before tile k+2 is copied into it
+      }
+      __syncthreads();
+    }
+    if (active) T::store_carry(pv, reinterpret_cast<uint32_t *>(p.state + (uint64_t)ch * p.state_stride), lane);
+  } else {
+    // ---------------------- recurrence warp: lane == channel ----------------------
+    const bool active = lane < n_here;
+    uint32_t ch = 0;
+    float x1 = 0.f, y1 = 0.f, gain = 0.f;
+    float *iir = nullptr;
+    if (active) {
+      ch = p.chan_ids[list0 + lane];
+      iir = reinterpret_cast<float *>(p.state + (uint64_t)ch * p.state_stride + T::NREG * 128);
+      x1 = iir[0];
+      y1 = iir[1];
+      gain = p.scale[ch];
+    }
+    // PCM row of the channel that word `lane + 32 it` of the CTA's PCM block belongs to
+    const int n_words = n_here * 16;
+    const float a1 = (float)(-0.95);
+    for (uint32_t k = 0; k <= n_tiles; ++k) {
+      if (k >= 1) {
+        const uint32_t t = k - 1;
+        const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
+        if (active) {
+          // all 32 inputs first (eight 128-bit loads), then the dependent chain
+          //   y = fl(fl(x - x1) - fl(-0.95f * y1)),  pcm = (int16_t)(gain * y)
+          // runs out of registers: two dependent FP32 ops per step.
+          const uint32_t *in = dem + ((t & 1) * nw + lane) * T::DEM_WORDS;
+          float x[32];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const u32x4 v = lds_u4(in + 4 * i);
+            x[4 * i] = u2f(v.x); x[4 * i + 1] = u2f(v.y); x[4 * i + 2] = u2f(v.z); x[4 * i + 3] = u2f(v.w);
+          }
+          int o[32];
+          const float x_in = x1;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float d = fadd(x[i], fmul(-1.0f, i == 0 ? x_in : x[i == 0 ? 0 : i - 1]));
+            const float y = fsub(d, fmul(a1, y1));
+            if (i < r) {
+              y1 = y;
+              x1 = x[i];
+            }
+            o[i] = f2i16_wrap(fmul(gain, y));
+          }
+          uint32_t *out = pcm_s + lane * T::PCM_WORDS;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            sts_u4(out + 4 * i, u32x4{pack_i16x2(o[8 * i], o[8 * i + 1]), pack_i16x2(o[8 * i + 2], o[8 * i + 3]),
+                                     pack_i16x2(o[8 * i + 4], o[8 * i + 5]), pack_i16x2(o[8 * i + 6], o[8 * i + 7])});
+        }
+        __syncwarp();
+        // PCM rows out: 64 bytes per channel per tile, two samples per lane per store
+        for (int idx = lane; idx < n_words; idx += 32) {
+          const int c = idx >> 4, wd = idx & 15;
+          const uint32_t chc = p.chan_ids[list0 + c];
+          int16_t *dst = p.pcm + (uint64_t)chc * p.pcm_stride + (uint64_t)t * 32 + 2 * wd;
+          const uint32_t v = pcm_s[c * T::PCM_WORDS + wd];
+          if (2 * wd + 1 < r) *reinterpret_cast<uint32_t *>(dst) = v;
+          else if (2 * wd < r) *dst = (int16_t)(v & 0xffffu);
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+    }
+    if (active) {
+      iir[0] = x1;
+      iir[1] = y1;
+    }
+  }
+}
+
+}  // namespace sdr
+#endif  // SDR_DEVICE_BUILD
