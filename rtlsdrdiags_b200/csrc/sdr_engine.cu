@@ -82,7 +82,7 @@ int fail(sdr_engine *e, int code, const char *what, cudaError_t ce = cudaSuccess
 int state_bytes(int kind) {
   switch (kind) {
     case SDR_KIND_AM: return AmSsbTile<false>::STATE_BYTES;
-    case SDR_KIND_FM: return FmPipe::STATE_BYTES;
+    case SDR_KIND_FM: return FmTile::STATE_BYTES;
     case SDR_KIND_WBFM: return WbFmPipe::STATE_BYTES;
     case SDR_KIND_SSB: return AmSsbTile<true>::STATE_BYTES;
   }
@@ -240,6 +240,35 @@ int launch_amssb_tile(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_st
   SDR_CK(e, cudaFuncSetAttribute(amssb_tile_kernel<SSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const uint32_t grid = (n_list + G - 1) / G;
   amssb_tile_kernel<SSB><<<grid, 32 * (G + 1), smem, e->stream>>>(p);
+  SDR_CK(e, cudaGetLastError());
+  e->launches++;
+  return SDR_OK;
+}
+
+int launch_fm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples, int fmt) {
+  const int kind = SDR_KIND_FM;
+  const uint32_t n_list = (uint32_t)e->list[kind].size();
+  if (n_list == 0) return SDR_OK;
+  uint32_t G = e->shape[kind].G ? e->shape[kind].G : 4;  // worker warps per CTA; they never synchronise
+  if (G > 4) G = 4;
+  const int smem = (int)G * 2 * TILE_BYTES;
+  LaunchParams p;
+  p.iq = iq;
+  p.ch_stride = ch_stride;
+  p.n_samples = n_samples;
+  p.fmt = fmt;
+  p.chan_ids = e->d_list[kind];
+  p.n_list = n_list;
+  p.G = G;
+  p.state = e->d_state[kind];
+  p.state_stride = (uint32_t)FmTile::STATE_BYTES;
+  p.scale = e->d_scale[kind];
+  p.lsb = e->d_lsb;
+  p.pcm = e->d_pcm;
+  p.pcm_stride = e->pcm_stride;
+  p.lut = e->d_lut_fm;
+  const uint32_t grid = (n_list + G - 1) / G;
+  fm_tile_kernel<<<grid, 32 * G, smem, e->stream>>>(p);
   SDR_CK(e, cudaGetLastError());
   e->launches++;
   return SDR_OK;
@@ -470,7 +499,7 @@ int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_str
   const uint32_t n_samples = (uint32_t)(bytes / 2);
   if ((rc = launch_amssb_tile<false>(e, SDR_KIND_AM, dev_iq, dev_stride, n_samples, fmt))) return rc;
   if ((rc = launch_amssb_tile<true>(e, SDR_KIND_SSB, dev_iq, dev_stride, n_samples, fmt))) return rc;
-  if ((rc = launch_kind<FmPipe>(e, SDR_KIND_FM, dev_iq, dev_stride, n_samples, fmt))) return rc;
+  if ((rc = launch_fm_tile(e, dev_iq, dev_stride, n_samples, fmt))) return rc;
   if ((rc = launch_kind<WbFmPipe>(e, SDR_KIND_WBFM, dev_iq, dev_stride, n_samples, fmt))) return rc;
   e->last_samples = (uint32_t)(bytes / 64);
   return SDR_OK;

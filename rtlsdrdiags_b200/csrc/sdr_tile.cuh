@@ -182,13 +182,17 @@ struct AmSsbTile {
     }
 
     // the last 32 lanes of the stream become the next tile's "previous" registers
-    pv.a7 = roll_prev(cu.a7, pv.a7, r, lane); pv.b7 = roll_prev(cu.b7, pv.b7, r, lane);
-    pv.s1a0 = roll_prev(cu.s1a0, pv.s1a0, r, lane); pv.s1a1 = roll_prev(cu.s1a1, pv.s1a1, r, lane);
-    pv.s1b0 = roll_prev(cu.s1b0, pv.s1b0, r, lane); pv.s1b1 = roll_prev(cu.s1b1, pv.s1b1, r, lane);
-    pv.p = roll_prev(cu.p, pv.p, r, lane);
-    if constexpr (SSB) {
-      pv.y3a = roll_prev(cu.y3a, pv.y3a, r, lane);
-      pv.y3b = roll_prev(cu.y3b, pv.y3b, r, lane);
+    if (r == 32) {
+      pv = cu;
+    } else {
+      pv.a7 = roll_prev(cu.a7, pv.a7, r, lane); pv.b7 = roll_prev(cu.b7, pv.b7, r, lane);
+      pv.s1a0 = roll_prev(cu.s1a0, pv.s1a0, r, lane); pv.s1a1 = roll_prev(cu.s1a1, pv.s1a1, r, lane);
+      pv.s1b0 = roll_prev(cu.s1b0, pv.s1b0, r, lane); pv.s1b1 = roll_prev(cu.s1b1, pv.s1b1, r, lane);
+      pv.p = roll_prev(cu.p, pv.p, r, lane);
+      if constexpr (SSB) {
+        pv.y3a = roll_prev(cu.y3a, pv.y3a, r, lane);
+        pv.y3b = roll_prev(cu.y3b, pv.y3b, r, lane);
+      }
     }
     return out;
   }
@@ -333,6 +337,194 @@ __global__ void __launch_bounds__(512, 1) amssb_tile_kernel(const __grid_constan
       iir[0] = x1;
       iir[1] = y1;
     }
+  }
+}
+
+
+// ---------------------------------------------------------------------------
+// Narrow-band FM (FmDemodulator.cc): no recurrence anywhere, so a worker warp runs
+// the whole chain for its channel and stores PCM itself; the CTA never synchronises.
+// ---------------------------------------------------------------------------
+struct FmCarry {
+  uint32_t a[7], b[7];  // the lane's rotation groups 1..7 (I' and Q' words): 28 samples of tuner history
+  float th[4];          // theta of the lane's last four 64 kS/s samples
+  uint32_t dw[4];       // the lane's eight discriminator outputs (int16 x 2 per word)
+  uint32_t ew;          // the lane's two 16 kS/s samples (int16 x 2)
+};
+
+struct FmTile {
+  static constexpr int NREG = 23;
+  // state blob: NREG words per lane, then two sticky clamp-path flags
+  static constexpr int STATE_BYTES = NREG * 128 + 16;
+
+  __device__ __forceinline__ static void load_carry(FmCarry &c, const uint32_t *blob, int lane) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { c.a[i] = blob[i * 32 + lane]; c.b[i] = blob[(7 + i) * 32 + lane]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { c.th[i] = u2f(blob[(14 + i) * 32 + lane]); c.dw[i] = blob[(18 + i) * 32 + lane]; }
+    c.ew = blob[22 * 32 + lane];
+  }
+  __device__ __forceinline__ static void store_carry(const FmCarry &c, uint32_t *blob, int lane) {
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { blob[i * 32 + lane] = c.a[i]; blob[(7 + i) * 32 + lane] = c.b[i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { blob[(14 + i) * 32 + lane] = f2u(c.th[i]); blob[(18 + i) * 32 + lane] = c.dw[i]; }
+    blob[22 * 32 + lane] = c.ew;
+  }
+
+  template <int M>
+  __device__ __forceinline__ static int tuner_one(const uint32_t (&ext)[15]) {
+    const uint32_t w[8] = {ext[M], ext[M + 1], ext[M + 2], ext[M + 3], ext[M + 4], ext[M + 5], ext[M + 6], ext[M + 7]};
+    return (int)(int16_t)(fir_s8<taps::FM_TUNER, 31, 8>(w) >> 15);
+  }
+  template <int M>
+  __device__ __forceinline__ static void tuner_all(const uint32_t (&ea)[15], const uint32_t (&eb)[15], const float *lut,
+                                                   float (&th)[8]) {
+    if constexpr (M < 8) {
+      const int yi = tuner_one<M>(ea), yq = tuner_one<M>(eb);
+      // theta = (float)atan2((double)q, (double)i), FmDemodulator.cc:476 (table, see sdr_engine.cu)
+      th[M] = ld_lut(lut + (yq - FM_LUT_MIN) * FM_LUT_DIM + (yi - FM_LUT_MIN));
+      tuner_all<M + 1>(ea, eb, lut, th);
+    }
+  }
+  template <int J>
+  __device__ __forceinline__ static void gather_e(uint32_t (&e)[20], uint32_t cur, uint32_t prev, int lane) {
+    if constexpr (J <= 19) {
+      e[19 - J] = shfl_prev(cur, prev, J, lane);
+      gather_e<J + 1>(e, cur, prev, lane);
+    }
+  }
+
+  // One tile. big_a / big_b: sticky "clamp reachable" flags of the previous tile
+  // (in) and of this tile (out). Returns the lane's PCM sample.
+  __device__ __forceinline__ static int tile(const uint32_t (&w)[16], int fmt, float k, const float *lut, FmCarry &pv,
+                                             int lane, int r, bool &big_a, bool &big_b) {
+    FmCarry cu;
+    uint32_t a[8], b[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) front_end_group(fmt, w[2 * g], w[2 * g + 1], a[g], b[g]);
+#pragma unroll
+    for (int i = 0; i < 7; ++i) { cu.a[i] = a[i + 1]; cu.b[i] = b[i + 1]; }
+
+    // tuner decimators: 32 taps, 4:1. Output m uses rotation groups m-7 .. m.
+    uint32_t ea[15], eb[15];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) {
+      ea[i] = shfl_prev(cu.a[i], pv.a[i], 1, lane);
+      eb[i] = shfl_prev(cu.b[i], pv.b[i], 1, lane);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ea[7 + i] = a[i]; eb[7 + i] = b[i]; }
+    float th[8];
+    tuner_all<0>(ea, eb, lut, th);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cu.th[i] = th[4 + i];
+
+    // discriminator: taps {0,0,1,0,-1,0,0} -> theta[n-2] - theta[n-4]; wrap; * k; (int16_t)
+    float te[12];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) te[i] = shfl_prev(cu.th[i], pv.th[i], 1, lane);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) te[4 + i] = th[i];
+    int d[8];
+    bool big = false;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      d[m] = f2i16_wrap(fmul(k, wrap_pi(fsub(te[m + 2], te[m]))));
+      big |= iabs(d[m]) > taps::FM_POST::SAFE;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) cu.dw[i] = pack_i16x2(d[2 * i], d[2 * i + 1]);
+    const bool cur_a = __any_sync(FULL, big && lane < r);
+    const bool exact_a = cur_a || big_a;
+
+    // post-demodulation decimator: 12 taps, 4:1 on int16
+    uint32_t de[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      de[i] = shfl_prev(cu.dw[i], pv.dw[i], 1, lane);
+      de[4 + i] = cu.dw[i];
+    }
+    int e0, e1;
+    {
+      const uint32_t w0[6] = {de[0], de[1], de[2], de[3], de[4], de[5]};
+      const uint32_t w1[6] = {de[2], de[3], de[4], de[5], de[6], de[7]};
+      e0 = (int)(int16_t)(fir_s16<taps::FM_POST, 11, 6>(w0, exact_a) >> 15);
+      e1 = (int)(int16_t)(fir_s16<taps::FM_POST, 11, 6>(w1, exact_a) >> 15);
+    }
+    cu.ew = pack_i16x2(e0, e1);
+    const bool cur_b =
+        __any_sync(FULL, (iabs(e0) > taps::AUDIO40::SAFE || iabs(e1) > taps::AUDIO40::SAFE) && lane < r);
+    const bool exact_b = cur_b || big_b;
+
+    // audio decimator: 40 taps, 2:1: the lane's two samples and the 19 lanes below
+    uint32_t ee[20];
+    ee[19] = cu.ew;
+    gather_e<1>(ee, cu.ew, pv.ew, lane);
+    const int pcm = (int)(int16_t)(fir_s16<taps::AUDIO40, 39, 20>(ee, exact_b) >> 15);
+
+    big_a = cur_a || (r < 32 && big_a);
+    big_b = cur_b || (r < 32 && big_b);
+    if (r == 32) {
+      pv = cu;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 7; ++i) {
+        pv.a[i] = roll_prev(cu.a[i], pv.a[i], r, lane);
+        pv.b[i] = roll_prev(cu.b[i], pv.b[i], r, lane);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        pv.th[i] = roll_prev(cu.th[i], pv.th[i], r, lane);
+        pv.dw[i] = roll_prev(cu.dw[i], pv.dw[i], r, lane);
+      }
+      pv.ew = roll_prev(cu.ew, pv.ew, r, lane);
+    }
+    return pcm;
+  }
+};
+
+// every warp is a worker; blockDim = 32 * workers
+__global__ void __launch_bounds__(128, 4) fm_tile_kernel(const __grid_constant__ LaunchParams p) {
+  extern __shared__ uint4 smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nw = (int)(blockDim.x >> 5);
+  const uint32_t li = blockIdx.x * (uint32_t)nw + warp;
+  if (li >= p.n_list) return;
+  char *slots = reinterpret_cast<char *>(smem_raw) + warp * 2 * TILE_BYTES;
+  const uint32_t ch = p.chan_ids[li];
+  const uint8_t *src = p.iq + (uint64_t)ch * p.ch_stride;
+  uint32_t *blob = reinterpret_cast<uint32_t *>(p.state + (uint64_t)ch * p.state_stride);
+  FmCarry pv;
+  FmTile::load_carry(pv, blob, lane);
+  bool big_a = blob[FmTile::NREG * 32] != 0, big_b = blob[FmTile::NREG * 32 + 1] != 0;
+  const float k = p.scale[ch];
+  const int fmt = p.fmt;
+  const uint32_t n_tiles = (p.n_samples + TILE - 1) / TILE;
+  int16_t *out = p.pcm + (uint64_t)ch * p.pcm_stride;
+
+  tile_fill(slots, src, lane, (int)min((uint32_t)TILE, p.n_samples) >> 3);
+  cp_async_commit();
+  for (uint32_t t = 0; t < n_tiles; ++t) {
+    if (t + 1 < n_tiles) {
+      const uint32_t s1 = (t + 1) * TILE;
+      tile_fill(slots + ((t + 1) & 1) * TILE_BYTES, src + (uint64_t)s1 * 2, lane,
+                (int)min((uint32_t)TILE, p.n_samples - s1) >> 3);
+    }
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    uint32_t w[16];
+    tile_read(slots + (t & 1) * TILE_BYTES, lane, w);
+    __syncwarp();  // slot t&1 may be refilled (tile t+2) once every lane has read it
+    const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
+    const int pcm = FmTile::tile(w, fmt, k, p.lut, pv, lane, r, big_a, big_b);
+    if (lane < r) out[(uint64_t)t * 32 + lane] = (int16_t)pcm;
+  }
+  FmTile::store_carry(pv, blob, lane);
+  if (lane == 0) {
+    blob[FmTile::NREG * 32] = big_a;
+    blob[FmTile::NREG * 32 + 1] = big_b;
   }
 }
 
