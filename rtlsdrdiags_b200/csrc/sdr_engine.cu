@@ -83,7 +83,7 @@ int state_bytes(int kind) {
   switch (kind) {
     case SDR_KIND_AM: return AmSsbTile<false>::STATE_BYTES;
     case SDR_KIND_FM: return FmTile::STATE_BYTES;
-    case SDR_KIND_WBFM: return WbFmPipe::STATE_BYTES;
+    case SDR_KIND_WBFM: return WbTile::STATE_BYTES;
     case SDR_KIND_SSB: return AmSsbTile<true>::STATE_BYTES;
   }
   return -1;
@@ -269,6 +269,41 @@ int launch_fm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_
   p.lut = e->d_lut_fm;
   const uint32_t grid = (n_list + G - 1) / G;
   fm_tile_kernel<<<grid, 32 * G, smem, e->stream>>>(p);
+  SDR_CK(e, cudaGetLastError());
+  e->launches++;
+  return SDR_OK;
+}
+
+int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples, int fmt) {
+  using T = WbTile;
+  const int kind = SDR_KIND_WBFM;
+  const uint32_t n_list = (uint32_t)e->list[kind].size();
+  if (n_list == 0) return SDR_OK;
+  // one CTA per SM (the rings fill shared memory): spread the channels evenly over the waves
+  const long slots = e->n_sm;
+  const long W = ((long)n_list + slots * T::MAX_WORKERS - 1) / (slots * T::MAX_WORKERS);
+  uint32_t G = (uint32_t)(((long)n_list + slots * W - 1) / (slots * W));
+  if (e->shape[kind].G) G = e->shape[kind].G;
+  if (G > (uint32_t)T::MAX_WORKERS) G = T::MAX_WORKERS;
+  const int smem = T::smem_bytes((int)G);
+  LaunchParams p;
+  p.iq = iq;
+  p.ch_stride = ch_stride;
+  p.n_samples = n_samples;
+  p.fmt = fmt;
+  p.chan_ids = e->d_list[kind];
+  p.n_list = n_list;
+  p.G = G;
+  p.state = e->d_state[kind];
+  p.state_stride = (uint32_t)T::STATE_BYTES;
+  p.scale = e->d_scale[kind];
+  p.lsb = e->d_lsb;
+  p.pcm = e->d_pcm;
+  p.pcm_stride = e->pcm_stride;
+  p.lut = e->d_lut_wbfm;
+  SDR_CK(e, cudaFuncSetAttribute(wbfm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const uint32_t grid = (n_list + G - 1) / G;
+  wbfm_tile_kernel<<<grid, 32 * (G + 1), smem, e->stream>>>(p);
   SDR_CK(e, cudaGetLastError());
   e->launches++;
   return SDR_OK;
@@ -500,7 +535,7 @@ int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_str
   if ((rc = launch_amssb_tile<false>(e, SDR_KIND_AM, dev_iq, dev_stride, n_samples, fmt))) return rc;
   if ((rc = launch_amssb_tile<true>(e, SDR_KIND_SSB, dev_iq, dev_stride, n_samples, fmt))) return rc;
   if ((rc = launch_fm_tile(e, dev_iq, dev_stride, n_samples, fmt))) return rc;
-  if ((rc = launch_kind<WbFmPipe>(e, SDR_KIND_WBFM, dev_iq, dev_stride, n_samples, fmt))) return rc;
+  if ((rc = launch_wbfm_tile(e, dev_iq, dev_stride, n_samples, fmt))) return rc;
   e->last_samples = (uint32_t)(bytes / 64);
   return SDR_OK;
 }

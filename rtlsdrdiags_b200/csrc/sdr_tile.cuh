@@ -528,5 +528,343 @@ __global__ void __launch_bounds__(128, 4) fm_tile_kernel(const __grid_constant__
   }
 }
 
+// ---------------------------------------------------------------------------
+// Wide-band FM (WbFmDemodulator.cc). Three stages pipelined over tile rounds:
+//   round k, worker warp of a channel : C(k-2) then A(k)
+//   round k, recurrence warp          : B(k-1), lane == channel
+// A: front end, 16-tap pre-filter at 256 kS/s -> (int8) -> atan2 table -> first
+//    difference, wrap, * k -> numerator of the de-emphasis filter: u[n], 1024 floats
+//    into ring slot k&1 of the channel.
+// B: y[n] = fl(u[n] - fl(a1 * y[n-1])), d[n] = (int16_t)y[n], written over the
+//    consumed part of the same slot.
+// C: d -> 8-tap 4:1 -> 12-tap 4:1 -> 40-tap 2:1 -> PCM, read from slot (k-2)&1 = k&1
+//    before A(k) overwrites it.
+// One CTA barrier per round.
+// ---------------------------------------------------------------------------
+struct WbCarry {
+  uint32_t a[4], b[4];  // the lane's rotation groups 4..7: 16 samples of pre-filter history
+  float th31;           // theta of the lane's last sample
+  float v31;            // k * dtheta of the lane's last sample
+  uint32_t dw[2];       // the lane's last four de-emphasised samples (int16 x 2 per word)
+  uint32_t e1w[4];      // the lane's eight decimator-1 outputs
+  uint32_t ew;          // the lane's two decimator-2 outputs
+};
+
+struct WbTile {
+  static constexpr int NREG_A = 10, NREG_C = 7, NREG = NREG_A + NREG_C;
+  // blob: NREG words per lane; tail: y[n-1], v[n-1] of the de-emphasis IIR (NOT cleared
+  // by a reset, WbFmDemodulator.cc:304-320), clamp flag
+  static constexpr int STATE_BYTES = NREG * 128 + 16;
+  static constexpr int MAX_WORKERS = 21;
+  static constexpr int RING_BYTES = 2 * 4096 + 16;  // two slots + pad: row stride == 16 (mod 128)
+  __host__ __device__ static constexpr int smem_bytes(int nw) { return nw * (TILE_BYTES + RING_BYTES) + 64; }
+
+  // u[n] of row (= lane) `row`, 16-byte chunk j (four samples): rows are XOR-swizzled so
+  // that a quarter-warp writing chunk j of eight consecutive rows hits distinct banks
+  __device__ __forceinline__ static int u_off(int row, int j) { return 128 * row + 16 * (j ^ (row & 7)); }
+
+  // ---- A ----
+  template <int N>
+  __device__ __forceinline__ static int pre_one(const uint32_t (&ext)[12]) {
+    return fir_s8<taps::WB_PRE, 16 + N, 12>(ext) >> 15;
+  }
+  template <int N0>
+  __device__ __forceinline__ static void theta4(const uint32_t (&ea)[12], const uint32_t (&eb)[12], const float *lut,
+                                                float (&th)[4]) {
+    // (int8_t) truncation, then table[(uint8)(q+128)][(uint8)(i+128)] (WbFmDemodulator.cc:393-397, 458-462)
+    const int i0 = (pre_one<N0>(ea) + 128) & 255, q0 = (pre_one<N0>(eb) + 128) & 255;
+    const int i1 = (pre_one<N0 + 1>(ea) + 128) & 255, q1 = (pre_one<N0 + 1>(eb) + 128) & 255;
+    const int i2 = (pre_one<N0 + 2>(ea) + 128) & 255, q2 = (pre_one<N0 + 2>(eb) + 128) & 255;
+    const int i3 = (pre_one<N0 + 3>(ea) + 128) & 255, q3 = (pre_one<N0 + 3>(eb) + 128) & 255;
+    th[0] = ld_lut(lut + q0 * 256 + i0);
+    th[1] = ld_lut(lut + q1 * 256 + i1);
+    th[2] = ld_lut(lut + q2 * 256 + i2);
+    th[3] = ld_lut(lut + q3 * 256 + i3);
+  }
+  // four samples: returns the chunk of u, advances (th_prev, v_prev)
+  template <int N0>
+  __device__ __forceinline__ static u32x4 u4(const uint32_t (&ea)[12], const uint32_t (&eb)[12], const float *lut,
+                                             float k, float &th_prev, float &v_prev) {
+    const float b0 = (float)(0.0253863), b1 = (float)(0.0253863);
+    float th[4];
+    theta4<N0>(ea, eb, lut, th);
+    float u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float v = fmul(k, wrap_pi(fsub(th[i], th_prev)));
+      u[i] = fadd(fmul(b0, v), fmul(b1, v_prev));
+      th_prev = th[i];
+      v_prev = v;
+    }
+    return u32x4{f2u(u[0]), f2u(u[1]), f2u(u[2]), f2u(u[3])};
+  }
+  template <int J>
+  __device__ __forceinline__ static void u_all(const uint32_t (&ea)[12], const uint32_t (&eb)[12], const float *lut,
+                                               float k, float &th_prev, float &v_prev, char *slot, int lane) {
+    if constexpr (J < 8) {
+      sts_u4(slot + u_off(lane, J), u4<4 * J>(ea, eb, lut, k, th_prev, v_prev));
+      u_all<J + 1>(ea, eb, lut, k, th_prev, v_prev, slot, lane);
+    }
+  }
+
+  // A(k): w = the lane's 64 input bytes; writes the lane's 32 u values into `slot`.
+  // v_boundary: v[n-1] at the head of the tile (carried; scaled with the gain it was made with).
+  __device__ __forceinline__ static void part_a(const uint32_t (&w)[16], int fmt, float k, const float *lut, WbCarry &pv,
+                                                float &v_boundary, char *slot, int lane, int r) {
+    uint32_t a[8], b[8];
+#pragma unroll
+    for (int g = 0; g < 8; ++g) front_end_group(fmt, w[2 * g], w[2 * g + 1], a[g], b[g]);
+    uint32_t ea[12], eb[12];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ea[i] = shfl_prev(a[4 + i], pv.a[i], 1, lane);
+      eb[i] = shfl_prev(b[4 + i], pv.b[i], 1, lane);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ea[4 + i] = a[i]; eb[4 + i] = b[i]; }
+
+    // theta and v of the sample just before this lane's: the lane's own last sample
+    // needs its last two thetas only, so every lane can produce (th31, v31) up front
+    float th30_31[2];
+    {
+      const int i0 = (pre_one<30>(ea) + 128) & 255, q0 = (pre_one<30>(eb) + 128) & 255;
+      const int i1 = (pre_one<31>(ea) + 128) & 255, q1 = (pre_one<31>(eb) + 128) & 255;
+      th30_31[0] = ld_lut(lut + q0 * 256 + i0);
+      th30_31[1] = ld_lut(lut + q1 * 256 + i1);
+    }
+    const float my_th31 = th30_31[1];
+    const float my_v31 = fmul(k, wrap_pi(fsub(th30_31[1], th30_31[0])));
+    float th_prev = shfl_prev(my_th31, pv.th31, 1, lane);
+    float v_prev = __shfl_up_sync(FULL, my_v31, 1);
+    if (lane == 0) v_prev = v_boundary;
+    u_all<0>(ea, eb, lut, k, th_prev, v_prev, slot, lane);
+
+    // carry: last valid lane's values feed the next tile
+    v_boundary = __shfl_sync(FULL, my_v31, r - 1);
+    if (r == 32) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { pv.a[i] = a[4 + i]; pv.b[i] = b[4 + i]; }
+      pv.th31 = my_th31;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        pv.a[i] = roll_prev(a[4 + i], pv.a[i], r, lane);
+        pv.b[i] = roll_prev(b[4 + i], pv.b[i], r, lane);
+      }
+      pv.th31 = roll_prev(my_th31, pv.th31, r, lane);
+    }
+  }
+
+  // ---- C ----
+  template <int M>
+  __device__ __forceinline__ static int dec1_one(const uint32_t (&ext)[18]) {
+    const uint32_t w[4] = {ext[2 * M], ext[2 * M + 1], ext[2 * M + 2], ext[2 * M + 3]};
+    static_assert(taps::WB_DEC1::SAFE >= 32768, "decimator 1 must be clamp-free");
+    return (int)(int16_t)(fir_s16_fast<taps::WB_DEC1, 7, 4>(w) >> 15);
+  }
+  // C(j): dW = the lane's 32 de-emphasised samples; returns the lane's PCM sample
+  __device__ __forceinline__ static int part_c(const uint32_t (&dW)[16], WbCarry &pv, int lane, int r, bool &big_b) {
+    // decimator 1: 8 taps, 4:1; output m uses d[4m-4 .. 4m+3]
+    uint32_t ext[18];
+    ext[0] = shfl_prev(dW[14], pv.dw[0], 1, lane);
+    ext[1] = shfl_prev(dW[15], pv.dw[1], 1, lane);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ext[2 + i] = dW[i];
+    uint32_t e1w[4];
+    e1w[0] = pack_i16x2(dec1_one<0>(ext), dec1_one<1>(ext));
+    e1w[1] = pack_i16x2(dec1_one<2>(ext), dec1_one<3>(ext));
+    e1w[2] = pack_i16x2(dec1_one<4>(ext), dec1_one<5>(ext));
+    e1w[3] = pack_i16x2(dec1_one<6>(ext), dec1_one<7>(ext));
+    // decimator 2: 12 taps, 4:1, clamp-free (decimator 1 output <= 29126 <= FM_POST::SAFE)
+    uint32_t de[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      de[i] = shfl_prev(e1w[i], pv.e1w[i], 1, lane);
+      de[4 + i] = e1w[i];
+    }
+    const uint32_t w0[6] = {de[0], de[1], de[2], de[3], de[4], de[5]};
+    const uint32_t w1[6] = {de[2], de[3], de[4], de[5], de[6], de[7]};
+    const int e0 = (int)(int16_t)(fir_s16_fast<taps::FM_POST, 11, 6>(w0) >> 15);
+    const int e1 = (int)(int16_t)(fir_s16_fast<taps::FM_POST, 11, 6>(w1) >> 15);
+    const uint32_t ew = pack_i16x2(e0, e1);
+    const bool cur_b =
+        __any_sync(FULL, (iabs(e0) > taps::AUDIO40::SAFE || iabs(e1) > taps::AUDIO40::SAFE) && lane < r);
+    const bool exact_b = cur_b || big_b;
+    // audio decimator: 40 taps, 2:1
+    uint32_t ee[20];
+    ee[19] = ew;
+    FmTile::gather_e<1>(ee, ew, pv.ew, lane);
+    const int pcm = (int)(int16_t)(fir_s16<taps::AUDIO40, 39, 20>(ee, exact_b) >> 15);
+    big_b = cur_b || (r < 32 && big_b);
+    if (r == 32) {
+      pv.dw[0] = dW[14]; pv.dw[1] = dW[15];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pv.e1w[i] = e1w[i];
+      pv.ew = ew;
+    } else {
+      pv.dw[0] = roll_prev(dW[14], pv.dw[0], r, lane);
+      pv.dw[1] = roll_prev(dW[15], pv.dw[1], r, lane);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pv.e1w[i] = roll_prev(e1w[i], pv.e1w[i], r, lane);
+      pv.ew = roll_prev(ew, pv.ew, r, lane);
+    }
+    return pcm;
+  }
+
+  __device__ __forceinline__ static void load_carry(WbCarry &c, const uint32_t *blob, int lane) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { c.a[i] = blob[i * 32 + lane]; c.b[i] = blob[(4 + i) * 32 + lane]; }
+    c.th31 = u2f(blob[8 * 32 + lane]);
+    c.v31 = 0.f;
+    c.dw[0] = blob[10 * 32 + lane]; c.dw[1] = blob[11 * 32 + lane];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c.e1w[i] = blob[(12 + i) * 32 + lane];
+    c.ew = blob[16 * 32 + lane];
+  }
+  __device__ __forceinline__ static void store_carry(const WbCarry &c, uint32_t *blob, int lane) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { blob[i * 32 + lane] = c.a[i]; blob[(4 + i) * 32 + lane] = c.b[i]; }
+    blob[8 * 32 + lane] = f2u(c.th31);
+    blob[9 * 32 + lane] = 0;
+    blob[10 * 32 + lane] = c.dw[0]; blob[11 * 32 + lane] = c.dw[1];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) blob[(12 + i) * 32 + lane] = c.e1w[i];
+    blob[16 * 32 + lane] = c.ew;
+  }
+};
+
+// two (int16_t)float conversions with x86 wrap semantics, packed
+__device__ __forceinline__ uint32_t f2i16x2_wrap(float v0, float v1) {
+  int r0 = f2i_rz(v0), r1 = f2i_rz(v1);
+  if (!(fabsf(v0) < 2147483648.0f)) r0 = 0;
+  if (!(fabsf(v1) < 2147483648.0f)) r1 = 0;
+  return __byte_perm((uint32_t)r0, (uint32_t)r1, 0x5410);
+}
+
+// blockDim = 32 * (workers + 1); warp 3 runs the recurrences (it shares its scheduler
+// with the fewest workers), the other warps are workers.
+__global__ void __launch_bounds__(704, 1) wbfm_tile_kernel(const __grid_constant__ LaunchParams p) {
+  using T = WbTile;
+  extern __shared__ uint4 smem_raw[];
+  char *smem = reinterpret_cast<char *>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nw = (int)(blockDim.x >> 5) - 1;
+  constexpr int IIR_WARP = 3;
+  const int nwarps = nw + 1;
+  const int iir_warp = nwarps > IIR_WARP ? IIR_WARP : nwarps - 1;
+  const uint32_t list0 = blockIdx.x * (uint32_t)nw;
+  const int n_here = (int)min((uint32_t)nw, p.n_list - list0);
+  const uint32_t n_tiles = (p.n_samples + TILE - 1) / TILE;
+  char *in_base = smem;                       // nw input slots of TILE_BYTES
+  char *ring_base = smem + nw * TILE_BYTES;   // nw rings of RING_BYTES
+
+  if (warp != iir_warp) {
+    // ------------------------------ worker ------------------------------
+    const int wi = warp < iir_warp ? warp : warp - 1;  // worker index = channel slot
+    const bool active = wi < n_here;
+    uint32_t ch = 0;
+    const uint8_t *src = nullptr;
+    uint32_t *blob = nullptr;
+    WbCarry pv;
+    float k = 0.f, v_boundary = 0.f;
+    bool big_b = false;
+    char *in_slot = in_base + wi * TILE_BYTES;
+    char *ring = ring_base + wi * T::RING_BYTES;
+    int16_t *out = nullptr;
+    if (active) {
+      ch = p.chan_ids[list0 + wi];
+      src = p.iq + (uint64_t)ch * p.ch_stride;
+      blob = reinterpret_cast<uint32_t *>(p.state + (uint64_t)ch * p.state_stride);
+      T::load_carry(pv, blob, lane);
+      v_boundary = u2f(blob[T::NREG * 32 + 1]);
+      big_b = blob[T::NREG * 32 + 2] != 0;
+      k = p.scale[ch];
+      out = p.pcm + (uint64_t)ch * p.pcm_stride;
+      tile_fill(in_slot, src, lane, (int)min((uint32_t)TILE, p.n_samples) >> 3);
+    }
+    cp_async_commit();
+    for (uint32_t kk = 0; kk < n_tiles + 2; ++kk) {
+      if (active) {
+        char *slot = ring + (kk & 1) * 4096;
+        if (kk >= 2) {
+          // C(kk-2): the recurrence warp left d[0..1023] (int16) at the head of this slot,
+          // 16-byte chunks swizzled like an input tile
+          const uint32_t t = kk - 2;
+          const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
+          uint32_t dW[16];
+          tile_read(slot, lane, dW);
+          const int pcm = T::part_c(dW, pv, lane, r, big_b);
+          if (lane < r) out[(uint64_t)t * 32 + lane] = (int16_t)pcm;
+          __syncwarp();  // every lane has read d before A overwrites the slot
+        }
+        if (kk < n_tiles) {
+          cp_async_wait<0>();
+          __syncwarp();
+          uint32_t w[16];
+          tile_read(in_slot, lane, w);
+          __syncwarp();
+          if (kk + 1 < n_tiles) {  // the single input slot is free again: fetch the next tile now
+            const uint32_t s1 = (kk + 1) * TILE;
+            tile_fill(in_slot, src + (uint64_t)s1 * 2, lane, (int)min((uint32_t)TILE, p.n_samples - s1) >> 3);
+          }
+          cp_async_commit();
+          const int r = (int)min((uint32_t)TILE, p.n_samples - kk * TILE) >> 5;
+          T::part_a(w, p.fmt, k, p.lut, pv, v_boundary, slot, lane, r);
+        }
+      }
+      __syncthreads();
+    }
+    if (active) {
+      T::store_carry(pv, blob, lane);
+      if (lane == 0) {
+        blob[T::NREG * 32 + 1] = f2u(v_boundary);
+        blob[T::NREG * 32 + 2] = big_b;
+      }
+    }
+  } else {
+    // ---------------------- recurrence warp: lane == channel ----------------------
+    const bool active = lane < n_here;
+    uint32_t *tail = nullptr;
+    float y1 = 0.f;
+    if (active) {
+      const uint32_t ch = p.chan_ids[list0 + lane];
+      tail = reinterpret_cast<uint32_t *>(p.state + (uint64_t)ch * p.state_stride) + T::NREG * 32;
+      y1 = u2f(tail[0]);
+    }
+    const float a1 = (float)(-0.9492274);
+    char *ring = ring_base + lane * T::RING_BYTES;
+    for (uint32_t kk = 0; kk < n_tiles + 2; ++kk) {
+      if (active && kk >= 1 && kk <= n_tiles) {
+        const uint32_t t = kk - 1;
+        const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
+        char *slot = ring + (t & 1) * 4096;
+        for (int row = 0; row < r; ++row) {
+          // the row's 32 inputs into registers, then 32 dependent steps, then 64 bytes of
+          // int16 back over rows that are already consumed
+          float u[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const u32x4 v = lds_u4(slot + T::u_off(row, j));
+            u[4 * j] = u2f(v.x); u[4 * j + 1] = u2f(v.y); u[4 * j + 2] = u2f(v.z); u[4 * j + 3] = u2f(v.w);
+          }
+          uint32_t o[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float ya = fsub(u[2 * i], fmul(a1, y1));
+            const float yb = fsub(u[2 * i + 1], fmul(a1, ya));
+            y1 = yb;
+            o[i] = f2i16x2_wrap(ya, yb);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts_u4(slot + 16 * tile_slot(4 * row + j), u32x4{o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]});
+        }
+      }
+      __syncthreads();
+    }
+    if (active) tail[0] = f2u(y1);
+  }
+}
+
 }  // namespace sdr
 #endif  // SDR_DEVICE_BUILD
