@@ -92,13 +92,18 @@ SDR_DEV int f2i16_wrap(float v) {
   return (int)(int16_t)(uint16_t)(uint32_t)r;
 }
 
-// while (d > M_PI) d -= 2*M_PI; in the reference the compare and subtraction are
-// double, the store rounds to float. For a float d, d > M_PI  <=>  d >= (float)M_PI.
+// while (d > M_PI) d -= 2*M_PI; while (d < -M_PI) d += 2*M_PI; in the reference the
+// compares and the additions are double, the store rounds to float
+// (FmDemodulator.cc:486-494). For a float d, d > M_PI  <=>  d >= (float)M_PI. d is a
+// difference of two atan2 values, |d| <= 2 pi, so each loop runs at most once; written
+// as two predicated steps (no divergent branch) because in a warp some lane wraps on
+// almost every sample.
 SDR_DEV float wrap_pi(float d) {
   const float PI_F = 3.14159274101257324f;
-  for (int it = 0; it < 8 && d >= PI_F; ++it) d = dadd_to_f(d, -6.283185307179586);
-  for (int it = 0; it < 8 && d <= -PI_F; ++it) d = dadd_to_f(d, 6.283185307179586);
-  return d;
+  // adding 0.0 in double and rounding back returns d itself, so one FP64 add serves
+  // all three cases
+  const double off = d >= PI_F ? -6.283185307179586 : (d <= -PI_F ? 6.283185307179586 : 0.0);
+  return dadd_to_f(d, off);
 }
 
 // ---------------------------------------------------------------------------

@@ -564,30 +564,34 @@ struct WbTile {
   __device__ __forceinline__ static int u_off(int row, int j) { return 128 * row + 16 * (j ^ (row & 7)); }
 
   // ---- A ----
+  // The pre-filter runs with every tap doubled (|2 h| <= 31866 still fits int16) and the
+  // rounding constant doubled: acc' = 2 acc exactly, so (acc >> 15) & 255 -- the int8
+  // truncation of WbFmDemodulator.cc:393-397 -- is simply byte 2 of acc'.
+  struct Pre2 {
+    static constexpr int N = taps::WB_PRE::N;
+    SDR_HD static constexpr int tap(int k) { return 2 * taps::WB_PRE::tap(k); }
+  };
+  // table index of sample N: byte 0 = (uint8)(i + 128), byte 1 = (uint8)(q + 128)
   template <int N>
-  __device__ __forceinline__ static int pre_one(const uint32_t (&ext)[12]) {
-    return fir_s8<taps::WB_PRE, 16 + N, 12>(ext) >> 15;
+  __device__ __forceinline__ static uint32_t lut_index(const uint32_t (&ea)[12], const uint32_t (&eb)[12]) {
+    const uint32_t ai = (uint32_t)fir_s8<Pre2, 16 + N, 12>(ea, 1 << 15);
+    const uint32_t aq = (uint32_t)fir_s8<Pre2, 16 + N, 12>(eb, 1 << 15);
+    return (__byte_perm(ai, aq, 0x7762) & 0xffffu) ^ 0x8080u;
   }
   template <int N0>
   __device__ __forceinline__ static void theta4(const uint32_t (&ea)[12], const uint32_t (&eb)[12], const float *lut,
                                                 float (&th)[4]) {
-    // (int8_t) truncation, then table[(uint8)(q+128)][(uint8)(i+128)] (WbFmDemodulator.cc:393-397, 458-462)
-    const int i0 = (pre_one<N0>(ea) + 128) & 255, q0 = (pre_one<N0>(eb) + 128) & 255;
-    const int i1 = (pre_one<N0 + 1>(ea) + 128) & 255, q1 = (pre_one<N0 + 1>(eb) + 128) & 255;
-    const int i2 = (pre_one<N0 + 2>(ea) + 128) & 255, q2 = (pre_one<N0 + 2>(eb) + 128) & 255;
-    const int i3 = (pre_one<N0 + 3>(ea) + 128) & 255, q3 = (pre_one<N0 + 3>(eb) + 128) & 255;
-    th[0] = ld_lut(lut + q0 * 256 + i0);
-    th[1] = ld_lut(lut + q1 * 256 + i1);
-    th[2] = ld_lut(lut + q2 * 256 + i2);
-    th[3] = ld_lut(lut + q3 * 256 + i3);
+    // theta = table[(uint8)(q+128)][(uint8)(i+128)] (WbFmDemodulator.cc:458-462)
+    const uint32_t x0 = lut_index<N0>(ea, eb), x1 = lut_index<N0 + 1>(ea, eb);
+    const uint32_t x2 = lut_index<N0 + 2>(ea, eb), x3 = lut_index<N0 + 3>(ea, eb);
+    th[0] = ld_lut(lut + x0);
+    th[1] = ld_lut(lut + x1);
+    th[2] = ld_lut(lut + x2);
+    th[3] = ld_lut(lut + x3);
   }
-  // four samples: returns the chunk of u, advances (th_prev, v_prev)
-  template <int N0>
-  __device__ __forceinline__ static u32x4 u4(const uint32_t (&ea)[12], const uint32_t (&eb)[12], const float *lut,
-                                             float k, float &th_prev, float &v_prev) {
+  // four samples from their thetas: returns the chunk of u, advances (th_prev, v_prev)
+  __device__ __forceinline__ static u32x4 u4(const float (&th)[4], float k, float &th_prev, float &v_prev) {
     const float b0 = (float)(0.0253863), b1 = (float)(0.0253863);
-    float th[4];
-    theta4<N0>(ea, eb, lut, th);
     float u[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -599,11 +603,13 @@ struct WbTile {
     return u32x4{f2u(u[0]), f2u(u[1]), f2u(u[2]), f2u(u[3])};
   }
   template <int J>
-  __device__ __forceinline__ static void u_all(const uint32_t (&ea)[12], const uint32_t (&eb)[12], const float *lut,
-                                               float k, float &th_prev, float &v_prev, char *slot, int lane) {
-    if constexpr (J < 8) {
-      sts_u4(slot + u_off(lane, J), u4<4 * J>(ea, eb, lut, k, th_prev, v_prev));
-      u_all<J + 1>(ea, eb, lut, k, th_prev, v_prev, slot, lane);
+  __device__ __forceinline__ static void u_chunks(const uint32_t (&ea)[12], const uint32_t (&eb)[12], const float *lut,
+                                                  float k, float &th_prev, float &v_prev, char *slot, int lane) {
+    if constexpr (J < 7) {
+      float th[4];
+      theta4<4 * J>(ea, eb, lut, th);
+      sts_u4(slot + u_off(lane, J), u4(th, k, th_prev, v_prev));
+      u_chunks<J + 1>(ea, eb, lut, k, th_prev, v_prev, slot, lane);
     }
   }
 
@@ -623,21 +629,17 @@ struct WbTile {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { ea[4 + i] = a[i]; eb[4 + i] = b[i]; }
 
-    // theta and v of the sample just before this lane's: the lane's own last sample
-    // needs its last two thetas only, so every lane can produce (th31, v31) up front
-    float th30_31[2];
-    {
-      const int i0 = (pre_one<30>(ea) + 128) & 255, q0 = (pre_one<30>(eb) + 128) & 255;
-      const int i1 = (pre_one<31>(ea) + 128) & 255, q1 = (pre_one<31>(eb) + 128) & 255;
-      th30_31[0] = ld_lut(lut + q0 * 256 + i0);
-      th30_31[1] = ld_lut(lut + q1 * 256 + i1);
-    }
-    const float my_th31 = th30_31[1];
-    const float my_v31 = fmul(k, wrap_pi(fsub(th30_31[1], th30_31[0])));
+    // The lane's LAST four samples first: theta[31] and v[31] = k * wrap(theta[31] - theta[30])
+    // depend on this lane's data only, and the lane above needs them before it can start.
+    float th_last[4];
+    theta4<28>(ea, eb, lut, th_last);
+    const float my_th31 = th_last[3];
+    const float my_v31 = fmul(k, wrap_pi(fsub(th_last[3], th_last[2])));
     float th_prev = shfl_prev(my_th31, pv.th31, 1, lane);
     float v_prev = __shfl_up_sync(FULL, my_v31, 1);
     if (lane == 0) v_prev = v_boundary;
-    u_all<0>(ea, eb, lut, k, th_prev, v_prev, slot, lane);
+    u_chunks<0>(ea, eb, lut, k, th_prev, v_prev, slot, lane);
+    sts_u4(slot + u_off(lane, 7), u4(th_last, k, th_prev, v_prev));
 
     // carry: last valid lane's values feed the next tile
     v_boundary = __shfl_sync(FULL, my_v31, r - 1);
@@ -833,6 +835,11 @@ __global__ void __launch_bounds__(704, 1) wbfm_tile_kernel(const __grid_constant
     }
     const float a1 = (float)(-0.9492274);
     char *ring = ring_base + lane * T::RING_BYTES;
+    // |y| <= max(|y[-1]|, |u|max / (1 - |a1|)) < 3.2 |k|: with |k| < 1e8 and |y[-1]| < 1e9 no
+    // value can reach 2^31, where cvt.rzi (saturating) and x86 cvttss2si (wrapping) differ
+    bool small = true;
+    if (active) small = fabsf(p.scale[p.chan_ids[list0 + lane]]) < 1e8f && fabsf(y1) < 1e9f;
+    const bool no_patch = __all_sync(FULL, small);
     for (uint32_t kk = 0; kk < n_tiles + 2; ++kk) {
       if (active && kk >= 1 && kk <= n_tiles) {
         const uint32_t t = kk - 1;
@@ -848,12 +855,22 @@ __global__ void __launch_bounds__(704, 1) wbfm_tile_kernel(const __grid_constant
             u[4 * j] = u2f(v.x); u[4 * j + 1] = u2f(v.y); u[4 * j + 2] = u2f(v.z); u[4 * j + 3] = u2f(v.w);
           }
           uint32_t o[16];
+          if (no_patch) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float ya = fsub(u[2 * i], fmul(a1, y1));
-            const float yb = fsub(u[2 * i + 1], fmul(a1, ya));
-            y1 = yb;
-            o[i] = f2i16x2_wrap(ya, yb);
+            for (int i = 0; i < 16; ++i) {
+              const float ya = fsub(u[2 * i], fmul(a1, y1));
+              const float yb = fsub(u[2 * i + 1], fmul(a1, ya));
+              y1 = yb;
+              o[i] = __byte_perm((uint32_t)f2i_rz(ya), (uint32_t)f2i_rz(yb), 0x5410);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float ya = fsub(u[2 * i], fmul(a1, y1));
+              const float yb = fsub(u[2 * i + 1], fmul(a1, ya));
+              y1 = yb;
+              o[i] = f2i16x2_wrap(ya, yb);
+            }
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
