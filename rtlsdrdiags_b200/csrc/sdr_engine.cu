@@ -88,15 +88,6 @@ int state_bytes(int kind) {
   }
   return -1;
 }
-int stride_bytes(int kind) {
-  switch (kind) {
-    case SDR_KIND_AM: return AmPipe::STRIDE;
-    case SDR_KIND_FM: return FmPipe::STRIDE;
-    case SDR_KIND_WBFM: return WbFmPipe::STRIDE;
-    case SDR_KIND_SSB: return SsbPipe::STRIDE;
-  }
-  return -1;
-}
 int kind_of_mode(int mode) {
   switch (mode) {
     case SDR_MODE_AM: return SDR_KIND_AM;
@@ -128,68 +119,6 @@ float scale_of(int kind, float gain, int scaling) {
   volatile float k = gain / (kind == SDR_KIND_FM ? 15000.0f : 75000.0f);
   k = k * 32767.0f;
   return k;
-}
-
-// Channels per CTA (G), threads per CTA (NT): pick the number of co-resident
-// CTAs per SM (R) and of waves (W) that wastes the fewest channel slots; prefer
-// more co-resident CTAs so one CTA's sequential phase overlaps another's FIRs.
-Shape choose_shape(const sdr_engine *e, int kind, uint32_t n_list) {
-  Shape best;
-  double best_score = -1;
-  const int stride = stride_bytes(kind);
-  for (int R = 1; R <= 4; ++R) {
-    long gmax = ((long)e->smem_optin / R - HDR_BYTES - 1024) / stride;
-    if (gmax > MAX_G) gmax = MAX_G;
-    if (gmax < 1) continue;
-    const long slots = (long)e->n_sm * R;
-    const long W = ((long)n_list + slots * gmax - 1) / (slots * gmax);
-    const long G = ((long)n_list + slots * W - 1) / (slots * W);
-    const long ctas = ((long)n_list + G - 1) / G;
-    const long waves = (ctas + slots - 1) / slots;
-    const double eff = (double)n_list / (double)(waves * slots * G);
-    const double score = eff + (R == 2 ? 0.02 : 0.0) - (R > 2 ? 0.01 * (R - 2) : 0.0);
-    if (score > best_score) {
-      best_score = score;
-      best.G = (uint32_t)G;
-      best.NT = (uint32_t)(1024 / R);
-    }
-  }
-  if (best.G == 0) { best.G = 1; best.NT = 256; }
-  return best;
-}
-
-template <class M>
-int launch_kind(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples,
-                int fmt) {
-  const uint32_t n_list = (uint32_t)e->list[kind].size();
-  if (n_list == 0) return SDR_OK;
-  Shape s = choose_shape(e, kind, n_list);
-  if (e->shape[kind].G) s.G = e->shape[kind].G;
-  if (e->shape[kind].NT) s.NT = e->shape[kind].NT;
-  if (s.G > MAX_G) s.G = MAX_G;
-  const int smem = smem_bytes<M>((int)s.G);
-  if (smem > e->smem_optin) return fail(e, SDR_E_ARG, "launch shape needs more shared memory than an SM has");
-  LaunchParams p;
-  p.iq = iq;
-  p.ch_stride = ch_stride;
-  p.n_samples = n_samples;
-  p.fmt = fmt;
-  p.chan_ids = e->d_list[kind];
-  p.n_list = n_list;
-  p.G = s.G;
-  p.state = e->d_state[kind];
-  p.state_stride = (uint32_t)M::STATE_BYTES;
-  p.scale = e->d_scale[kind];
-  p.lsb = e->d_lsb;
-  p.pcm = e->d_pcm;
-  p.pcm_stride = e->pcm_stride;
-  p.lut = kind == SDR_KIND_FM ? e->d_lut_fm : e->d_lut_wbfm;
-  SDR_CK(e, cudaFuncSetAttribute(demod_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const uint32_t grid = (n_list + s.G - 1) / s.G;
-  demod_kernel<M><<<grid, s.NT, smem, e->stream>>>(p);
-  SDR_CK(e, cudaGetLastError());
-  e->launches++;
-  return SDR_OK;
 }
 
 // Warp-tile kernels: G = worker warps (= channels) per CTA, one more warp runs the
@@ -237,6 +166,7 @@ int launch_amssb_tile(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_st
   p.pcm = e->d_pcm;
   p.pcm_stride = e->pcm_stride;
   p.lut = nullptr;
+  p.aux = 0;
   SDR_CK(e, cudaFuncSetAttribute(amssb_tile_kernel<SSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const uint32_t grid = (n_list + G - 1) / G;
   amssb_tile_kernel<SSB><<<grid, 32 * (G + 1), smem, e->stream>>>(p);
@@ -267,6 +197,7 @@ int launch_fm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_
   p.pcm = e->d_pcm;
   p.pcm_stride = e->pcm_stride;
   p.lut = e->d_lut_fm;
+  p.aux = 0;
   const uint32_t grid = (n_list + G - 1) / G;
   fm_tile_kernel<<<grid, 32 * G, smem, e->stream>>>(p);
   SDR_CK(e, cudaGetLastError());
@@ -283,6 +214,8 @@ int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint3
   const long slots = e->n_sm;
   const long W = ((long)n_list + slots * T::MAX_WORKERS - 1) / (slots * T::MAX_WORKERS);
   uint32_t G = (uint32_t)(((long)n_list + slots * W - 1) / (slots * W));
+  static const int g_env = getenv("SDR_WB_G") ? atoi(getenv("SDR_WB_G")) : 0;  // tuning override
+  if (g_env) G = (uint32_t)g_env;
   if (e->shape[kind].G) G = e->shape[kind].G;
   if (G > (uint32_t)T::MAX_WORKERS) G = T::MAX_WORKERS;
   const int smem = T::smem_bytes((int)G);
@@ -301,9 +234,12 @@ int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint3
   p.pcm = e->d_pcm;
   p.pcm_stride = e->pcm_stride;
   p.lut = e->d_lut_wbfm;
+  // workers allowed on the recurrence warp's scheduler (tunable: SDR_WB_S3)
+  static const int s3_env = getenv("SDR_WB_S3") ? atoi(getenv("SDR_WB_S3")) : 4;
+  p.aux = (uint32_t)s3_env;
   SDR_CK(e, cudaFuncSetAttribute(wbfm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const uint32_t grid = (n_list + G - 1) / G;
-  wbfm_tile_kernel<<<grid, 32 * (G + 1), smem, e->stream>>>(p);
+  wbfm_tile_kernel<<<grid, 32 * T::warps_for((int)G, s3_env), smem, e->stream>>>(p);
   SDR_CK(e, cudaGetLastError());
   e->launches++;
   return SDR_OK;

@@ -535,10 +535,10 @@ __global__ void __launch_bounds__(128, 4) fm_tile_kernel(const __grid_constant__
 // A: front end, 16-tap pre-filter at 256 kS/s -> (int8) -> atan2 table -> first
 //    difference, wrap, * k -> numerator of the de-emphasis filter: u[n], 1024 floats
 //    into ring slot k&1 of the channel.
-// B: y[n] = fl(u[n] - fl(a1 * y[n-1])), d[n] = (int16_t)y[n], written over the
-//    consumed part of the same slot.
-// C: d -> 8-tap 4:1 -> 12-tap 4:1 -> 40-tap 2:1 -> PCM, read from slot (k-2)&1 = k&1
-//    before A(k) overwrites it.
+// B: y[n] = fl(u[n] - fl(a1 * y[n-1])), written back in place. Nothing else: the warp's
+//    dependent FMUL->FSUB chain is the critical path of a round.
+// C: d[n] = (int16_t)y[n] -> 8-tap 4:1 -> 12-tap 4:1 -> 40-tap 2:1 -> PCM, read from slot
+//    (k-2)&1 = k&1 before A(k) overwrites it.
 // One CTA barrier per round.
 // ---------------------------------------------------------------------------
 struct WbCarry {
@@ -555,7 +555,25 @@ struct WbTile {
   // blob: NREG words per lane; tail: y[n-1], v[n-1] of the de-emphasis IIR (NOT cleared
   // by a reset, WbFmDemodulator.cc:304-320), clamp flag
   static constexpr int STATE_BYTES = NREG * 128 + 16;
-  static constexpr int MAX_WORKERS = 21;
+  static constexpr int MAX_WORKERS = 19;
+  // Warp w issues from scheduler w & 3. The recurrence warp (warp 3) carries the round's
+  // critical path, a dependent FMUL->FSUB chain; how many workers may share its scheduler is
+  // a launch parameter (s3). Measured on B200: once the warp does nothing but the chain,
+  // sharing with up to four workers costs nothing (profiles/r01v2_wbfm_sweep.txt).
+  // s3 = how many workers may share scheduler 3 with the recurrence warp
+  __host__ __device__ static constexpr bool is_worker(int warp, int s3) {
+    return (warp & 3) != 3 || (warp != 3 && (warp >> 2) <= s3);
+  }
+  __host__ __device__ static constexpr int worker_index(int warp, int s3) {
+    int n = 0;
+    for (int w = 0; w < warp; ++w) n += is_worker(w, s3) ? 1 : 0;
+    return n;
+  }
+  __host__ __device__ static constexpr int warps_for(int workers, int s3) {
+    int n = 4;
+    while (worker_index(n, s3) < workers) ++n;
+    return n;
+  }
   static constexpr int RING_BYTES = 2 * 4096 + 16;  // two slots + pad: row stride == 16 (mod 128)
   __host__ __device__ static constexpr int smem_bytes(int nw) { return nw * (TILE_BYTES + RING_BYTES) + 64; }
 
@@ -743,33 +761,34 @@ __device__ __forceinline__ uint32_t f2i16x2_wrap(float v0, float v1) {
   return __byte_perm((uint32_t)r0, (uint32_t)r1, 0x5410);
 }
 
-// blockDim = 32 * (workers + 1); warp 3 runs the recurrences (it shares its scheduler
-// with the fewest workers), the other warps are workers.
-__global__ void __launch_bounds__(704, 1) wbfm_tile_kernel(const __grid_constant__ LaunchParams p) {
+// blockDim = 32 * WbTile::warps_for(p.G): warp 3 runs the recurrences, warps with
+// (w & 3) != 3 are workers, the remaining warps only keep the barrier count.
+__global__ void __launch_bounds__(768, 1) wbfm_tile_kernel(const __grid_constant__ LaunchParams p) {
   using T = WbTile;
   extern __shared__ uint4 smem_raw[];
   char *smem = reinterpret_cast<char *>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nw = (int)(blockDim.x >> 5) - 1;
-  constexpr int IIR_WARP = 3;
-  const int nwarps = nw + 1;
-  const int iir_warp = nwarps > IIR_WARP ? IIR_WARP : nwarps - 1;
+  const int nw = (int)p.G;
+  const int iir_warp = 3;
+  const int s3 = (int)p.aux;
   const uint32_t list0 = blockIdx.x * (uint32_t)nw;
   const int n_here = (int)min((uint32_t)nw, p.n_list - list0);
   const uint32_t n_tiles = (p.n_samples + TILE - 1) / TILE;
   char *in_base = smem;                       // nw input slots of TILE_BYTES
   char *ring_base = smem + nw * TILE_BYTES;   // nw rings of RING_BYTES
 
-  if (warp != iir_warp) {
+  if (warp != iir_warp && !T::is_worker(warp, s3)) {
+    for (uint32_t kk = 0; kk < n_tiles + 2; ++kk) __syncthreads();
+  } else if (warp != iir_warp) {
     // ------------------------------ worker ------------------------------
-    const int wi = warp < iir_warp ? warp : warp - 1;  // worker index = channel slot
+    const int wi = T::worker_index(warp, s3);  // = channel slot
     const bool active = wi < n_here;
     uint32_t ch = 0;
     const uint8_t *src = nullptr;
     uint32_t *blob = nullptr;
     WbCarry pv;
     float k = 0.f, v_boundary = 0.f;
-    bool big_b = false;
+    bool big_b = false, no_patch = false;
     char *in_slot = in_base + wi * TILE_BYTES;
     char *ring = ring_base + wi * T::RING_BYTES;
     int16_t *out = nullptr;
@@ -781,6 +800,9 @@ __global__ void __launch_bounds__(704, 1) wbfm_tile_kernel(const __grid_constant
       v_boundary = u2f(blob[T::NREG * 32 + 1]);
       big_b = blob[T::NREG * 32 + 2] != 0;
       k = p.scale[ch];
+      // |y| <= max(|y[-1]|, |u|max / (1 - |a1|)) < 3.2 |k|: with |k| < 1e8 and |y[-1]| < 1e9 no
+      // value can reach 2^31, where cvt.rzi (saturating) and x86 cvttss2si (wrapping) differ
+      no_patch = fabsf(k) < 1e8f && fabsf(u2f(blob[T::NREG * 32])) < 1e9f;
       out = p.pcm + (uint64_t)ch * p.pcm_stride;
       tile_fill(in_slot, src, lane, (int)min((uint32_t)TILE, p.n_samples) >> 3);
     }
@@ -789,12 +811,21 @@ __global__ void __launch_bounds__(704, 1) wbfm_tile_kernel(const __grid_constant
       if (active) {
         char *slot = ring + (kk & 1) * 4096;
         if (kk >= 2) {
-          // C(kk-2): the recurrence warp left d[0..1023] (int16) at the head of this slot,
-          // 16-byte chunks swizzled like an input tile
+          // C(kk-2): the recurrence warp left y[0..1023] where u was; (int16_t)y of the lane's row
           const uint32_t t = kk - 2;
           const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
           uint32_t dW[16];
-          tile_read(slot, lane, dW);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const u32x4 v = lds_u4(slot + T::u_off(lane, j));
+            if (no_patch) {
+              dW[2 * j] = __byte_perm((uint32_t)f2i_rz(u2f(v.x)), (uint32_t)f2i_rz(u2f(v.y)), 0x5410);
+              dW[2 * j + 1] = __byte_perm((uint32_t)f2i_rz(u2f(v.z)), (uint32_t)f2i_rz(u2f(v.w)), 0x5410);
+            } else {
+              dW[2 * j] = f2i16x2_wrap(u2f(v.x), u2f(v.y));
+              dW[2 * j + 1] = f2i16x2_wrap(u2f(v.z), u2f(v.w));
+            }
+          }
           const int pcm = T::part_c(dW, pv, lane, r, big_b);
           if (lane < r) out[(uint64_t)t * 32 + lane] = (int16_t)pcm;
           __syncwarp();  // every lane has read d before A overwrites the slot
@@ -835,46 +866,23 @@ __global__ void __launch_bounds__(704, 1) wbfm_tile_kernel(const __grid_constant
     }
     const float a1 = (float)(-0.9492274);
     char *ring = ring_base + lane * T::RING_BYTES;
-    // |y| <= max(|y[-1]|, |u|max / (1 - |a1|)) < 3.2 |k|: with |k| < 1e8 and |y[-1]| < 1e9 no
-    // value can reach 2^31, where cvt.rzi (saturating) and x86 cvttss2si (wrapping) differ
-    bool small = true;
-    if (active) small = fabsf(p.scale[p.chan_ids[list0 + lane]]) < 1e8f && fabsf(y1) < 1e9f;
-    const bool no_patch = __all_sync(FULL, small);
     for (uint32_t kk = 0; kk < n_tiles + 2; ++kk) {
       if (active && kk >= 1 && kk <= n_tiles) {
         const uint32_t t = kk - 1;
         const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
         char *slot = ring + (t & 1) * 4096;
         for (int row = 0; row < r; ++row) {
-          // the row's 32 inputs into registers, then 32 dependent steps, then 64 bytes of
-          // int16 back over rows that are already consumed
-          float u[32];
+          u32x4 v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = lds_u4(slot + T::u_off(row, j));
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const u32x4 v = lds_u4(slot + T::u_off(row, j));
-            u[4 * j] = u2f(v.x); u[4 * j + 1] = u2f(v.y); u[4 * j + 2] = u2f(v.z); u[4 * j + 3] = u2f(v.w);
+            const float y0 = fsub(u2f(v[j].x), fmul(a1, y1));
+            const float y2 = fsub(u2f(v[j].y), fmul(a1, y0));
+            const float y3 = fsub(u2f(v[j].z), fmul(a1, y2));
+            y1 = fsub(u2f(v[j].w), fmul(a1, y3));
+            sts_u4(slot + T::u_off(row, j), u32x4{f2u(y0), f2u(y2), f2u(y3), f2u(y1)});
           }
-          uint32_t o[16];
-          if (no_patch) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float ya = fsub(u[2 * i], fmul(a1, y1));
-              const float yb = fsub(u[2 * i + 1], fmul(a1, ya));
-              y1 = yb;
-              o[i] = __byte_perm((uint32_t)f2i_rz(ya), (uint32_t)f2i_rz(yb), 0x5410);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float ya = fsub(u[2 * i], fmul(a1, y1));
-              const float yb = fsub(u[2 * i + 1], fmul(a1, ya));
-              y1 = yb;
-              o[i] = f2i16x2_wrap(ya, yb);
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            sts_u4(slot + 16 * tile_slot(4 * row + j), u32x4{o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]});
         }
       }
       __syncthreads();

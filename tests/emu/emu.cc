@@ -1,16 +1,17 @@
 // TEST HARNESS -- serial emulation of the CUDA pipelines on the host.
 //
-// Compiles rtlsdrdiags_b200/csrc/sdr_device.cuh with -DSDR_EMU: every phase of a
-// CTA is run for tid = 0..NT-1 in turn, a phase boundary stands in for
-// __syncthreads(). It exists so the kernels' indexing, history and state logic
-// can be checked against the oracle on the CPU-only build box. It is not a
+// Compiles the arithmetic building blocks of the product kernels
+// (rtlsdrdiags_b200/csrc/sdr_device.cuh) together with the phase-structured test kernels
+// (sdr_phase.cuh) with -DSDR_EMU: every phase of a CTA is run for tid = 0..NT-1 in turn, a
+// phase boundary stands in for __syncthreads(). It exists so the front end, the FIR cores,
+// the wrap and conversion helpers can be checked against the oracle on the CPU-only build box. It is not a
 // fallback: nothing in rtlsdrdiags_b200/ builds, links or loads it.
 #include <stdint.h>
 #include <string.h>
 
 #include <vector>
 
-#include "sdr_config.h"
+#include "emu_config.h"
 
 namespace {
 using namespace sdr;
@@ -85,7 +86,7 @@ int emu_run(int kind, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples,
   p.iq = iq; p.ch_stride = ch_stride; p.n_samples = n_samples; p.fmt = fmt;
   p.chan_ids = chan_ids; p.n_list = n_list; p.G = G; p.state = state;
   p.state_stride = state_stride; p.scale = scale; p.lsb = lsb; p.pcm = pcm;
-  p.pcm_stride = pcm_stride; p.lut = lut;
+  p.pcm_stride = pcm_stride; p.lut = lut; p.aux = 0;
   switch (kind) {
     case sdr::KIND_AM: emu_launch<sdr::AmPipe>(p, NT); return 0;
     case sdr::KIND_FM: emu_launch<sdr::FmPipe>(p, NT); return 0;
