@@ -66,6 +66,14 @@ __device__ __forceinline__ void tile_read(const char *slot_base, int lane, uint3
   }
 }
 
+// two (int16_t)float conversions with x86 wrap semantics, packed
+__device__ __forceinline__ uint32_t f2i16x2_wrap(float v0, float v1) {
+  int r0 = f2i_rz(v0), r1 = f2i_rz(v1);
+  if (!(fabsf(v0) < 2147483648.0f)) r0 = 0;
+  if (!(fabsf(v1) < 2147483648.0f)) r1 = 0;
+  return __byte_perm((uint32_t)r0, (uint32_t)r1, 0x5410);
+}
+
 // ---------------------------------------------------------------------------
 // AM / SSB
 // ---------------------------------------------------------------------------
@@ -75,13 +83,14 @@ struct AmSsbCarry {
   uint32_t a7, b7;            // last rotation group of the lane: I' and Q' words
   uint32_t s1a0, s1a1, s1b0, s1b1;  // the lane's eight stage-1 outputs per arm (int8 x 4)
   uint32_t p;                 // stage-2 outputs: I pair in bytes 0-1, Q pair in bytes 2-3
+  float dem;                  // the lane's demodulated value (AM magnitude / SSB phased sum)
   int y3a, y3b;               // SSB: stage-3 outputs (delay line and Hilbert history)
 };
 
 template <bool SSB>
 struct AmSsbTile {
-  static constexpr int NREG = SSB ? 9 : 7;
-  // state blob: NREG words per lane, then x[n-1], y[n-1] of the DC-removal IIR
+  static constexpr int NREG = SSB ? 10 : 8;
+  // state blob: NREG words per lane, then (unused), y[n-1] of the DC-removal IIR
   static constexpr int STATE_BYTES = NREG * 128 + 16;
   static constexpr int MAX_WORKERS = 15;
   // shared memory per CTA for `nw` workers
@@ -89,9 +98,9 @@ struct AmSsbTile {
   // rows read or written 128 bits at a time with lane == channel: a row stride of
   // 16 (mod 128) bytes keeps every quarter-warp on distinct banks
   static constexpr int DEM_WORDS = 36;                    // per worker per parity: 32 values + pad
-  static constexpr int PCM_WORDS = 20;                    // per worker: 32 int16 (16 words) + pad
+  static constexpr int PCM_WORDS = 20;                    // per worker per parity: 32 int16 + pad
   __host__ __device__ static constexpr int smem_bytes(int nw) {
-    return nw * IN_BYTES + 2 * nw * DEM_WORDS * 4 + nw * PCM_WORDS * 4 + 64;
+    return nw * IN_BYTES + 2 * nw * DEM_WORDS * 4 + 2 * nw * PCM_WORDS * 4 + 64;
   }
 
   __device__ __forceinline__ static void load_carry(AmSsbCarry<SSB> &c, const uint32_t *blob, int lane) {
@@ -99,7 +108,8 @@ struct AmSsbTile {
     c.s1a0 = blob[2 * 32 + lane]; c.s1a1 = blob[3 * 32 + lane];
     c.s1b0 = blob[4 * 32 + lane]; c.s1b1 = blob[5 * 32 + lane];
     c.p = blob[6 * 32 + lane];
-    if constexpr (SSB) { c.y3a = (int)blob[7 * 32 + lane]; c.y3b = (int)blob[8 * 32 + lane]; }
+    c.dem = u2f(blob[7 * 32 + lane]);
+    if constexpr (SSB) { c.y3a = (int)blob[8 * 32 + lane]; c.y3b = (int)blob[9 * 32 + lane]; }
     else { c.y3a = 0; c.y3b = 0; }
   }
   __device__ __forceinline__ static void store_carry(const AmSsbCarry<SSB> &c, uint32_t *blob, int lane) {
@@ -107,13 +117,14 @@ struct AmSsbTile {
     blob[2 * 32 + lane] = c.s1a0; blob[3 * 32 + lane] = c.s1a1;
     blob[4 * 32 + lane] = c.s1b0; blob[5 * 32 + lane] = c.s1b1;
     blob[6 * 32 + lane] = c.p;
-    if constexpr (SSB) { blob[7 * 32 + lane] = (uint32_t)c.y3a; blob[8 * 32 + lane] = (uint32_t)c.y3b; }
+    blob[7 * 32 + lane] = f2u(c.dem);
+    if constexpr (SSB) { blob[8 * 32 + lane] = (uint32_t)c.y3a; blob[9 * 32 + lane] = (uint32_t)c.y3b; }
   }
 
   // One tile of one channel. `w` = the lane's 64 input bytes. Returns what the
-  // recurrence warp consumes for this lane's PCM sample: AM the magnitude estimate
-  // (as float bits), SSB the phased sum (float bits). Updates the carry to this
-  // tile's registers rolled by r valid lanes.
+  // recurrence warp consumes for this lane's PCM sample: the numerator of the DC-removal
+  // filter, fl(x[n] - x[n-1]) (float bits), where x is the AM magnitude estimate or the
+  // SSB phased sum. Updates the carry to this tile's registers rolled by r valid lanes.
   __device__ __forceinline__ static uint32_t tile(const uint32_t (&w)[16], int fmt, bool lsb, AmSsbCarry<SSB> &pv, int lane, int r) {
     AmSsbCarry<SSB> cu;
     uint32_t a[8], b[8];
@@ -162,12 +173,11 @@ struct AmSsbTile {
     cu.y3a = (int)(int16_t)(acc_i >> 15);
     cu.y3b = (int)(int16_t)(acc_q >> 15);
 
-    uint32_t out;
     if constexpr (!SSB) {
       // magnitude estimate, tie -> q branch (AmDemodulator.cc:441-458)
       const int im = (int)(int16_t)iabs(cu.y3a), qm = (int)(int16_t)iabs(cu.y3b);
       const int mag = (int)(int16_t)(im > qm ? im + (qm >> 1) : qm + (im >> 1));
-      out = f2u(i2f(mag));
+      cu.dem = i2f(mag);
     } else {
       // phasing network (SsbDemodulator.cc:569-590): delay line {0 x15, -32768}, Hilbert 31 taps
       const int x15 = shfl_prev(cu.y3a, pv.y3a, 15, lane);
@@ -178,8 +188,10 @@ struct AmSsbTile {
       int h = (1 << 14) + taps::SSB_HILBERT::tap(0) * cu.y3b;
       hilbert<2>(h, cu.y3b, pv.y3b, lane);
       const int q_shifted = (int)(int16_t)(h >> 15);
-      out = f2u(i2f(lsb ? i_delayed - q_shifted : i_delayed + q_shifted));
+      cu.dem = i2f(lsb ? i_delayed - q_shifted : i_delayed + q_shifted);
     }
+    // numerator of the DC-removal IIR, b = {1, -1}: fl(1*x[n] + (-1)*x[n-1]) (IirFilter.cc:164)
+    const uint32_t out = f2u(fadd(cu.dem, fmul(-1.0f, shfl_prev(cu.dem, pv.dem, 1, lane))));
 
     // the last 32 lanes of the stream become the next tile's "previous" registers
     if (r == 32) {
@@ -189,6 +201,7 @@ struct AmSsbTile {
       pv.s1a0 = roll_prev(cu.s1a0, pv.s1a0, r, lane); pv.s1a1 = roll_prev(cu.s1a1, pv.s1a1, r, lane);
       pv.s1b0 = roll_prev(cu.s1b0, pv.s1b0, r, lane); pv.s1b1 = roll_prev(cu.s1b1, pv.s1b1, r, lane);
       pv.p = roll_prev(cu.p, pv.p, r, lane);
+      pv.dem = roll_prev(cu.dem, pv.dem, r, lane);
       if constexpr (SSB) {
         pv.y3a = roll_prev(cu.y3a, pv.y3a, r, lane);
         pv.y3b = roll_prev(cu.y3b, pv.y3b, r, lane);
@@ -226,7 +239,7 @@ __global__ void __launch_bounds__(512, 1) amssb_tile_kernel(const __grid_constan
   const int nw = (int)(blockDim.x >> 5) - 1;  // workers in this CTA
   char *in_base = smem;
   uint32_t *dem = reinterpret_cast<uint32_t *>(smem + nw * T::IN_BYTES);
-  uint32_t *pcm_s = dem + 2 * nw * T::DEM_WORDS;
+  uint32_t *pcm_s = dem + 2 * nw * T::DEM_WORDS;  // [2 parities][nw][PCM_WORDS]
 
   const uint32_t list0 = blockIdx.x * (uint32_t)nw;
   const int n_here = (int)min((uint32_t)nw, p.n_list - list0);  // channels this CTA owns
@@ -250,7 +263,16 @@ __global__ void __launch_bounds__(512, 1) amssb_tile_kernel(const __grid_constan
       tile_fill(slots, src, lane, valid0);
     }
     cp_async_commit();
-    for (uint32_t k = 0; k <= n_tiles; ++k) {
+    int16_t *out = active ? p.pcm + (uint64_t)ch * p.pcm_stride : nullptr;
+    // round k: tile k is computed here, the recurrence warp turns tile k-1 into PCM, and
+    // this warp stores the PCM of tile k-2 (64 bytes, coalesced)
+    for (uint32_t k = 0; k < n_tiles + 2; ++k) {
+      if (active && k >= 2) {
+        const uint32_t t = k - 2;
+        const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
+        const int16_t *row = reinterpret_cast<const int16_t *>(pcm_s + ((t & 1) * nw + warp) * T::PCM_WORDS);
+        if (lane < r) out[(uint64_t)t * 32 + lane] = row[lane];
+      }
       if (active && k < n_tiles) {
         if (k + 1 < n_tiles) {
           const uint32_t s1 = (k + 1) * TILE;
@@ -273,70 +295,49 @@ __global__ void __launch_bounds__(512, 1) amssb_tile_kernel(const __grid_constan
   } else {
     // ---------------------- recurrence warp: lane == channel ----------------------
     const bool active = lane < n_here;
-    uint32_t ch = 0;
-    float x1 = 0.f, y1 = 0.f, gain = 0.f;
+    float y1 = 0.f, gain = 0.f;
     float *iir = nullptr;
     if (active) {
-      ch = p.chan_ids[list0 + lane];
+      const uint32_t ch = p.chan_ids[list0 + lane];
       iir = reinterpret_cast<float *>(p.state + (uint64_t)ch * p.state_stride + T::NREG * 128);
-      x1 = iir[0];
       y1 = iir[1];
       gain = p.scale[ch];
     }
-    // PCM row of the channel that word `lane + 32 it` of the CTA's PCM block belongs to
-    const int n_words = n_here * 16;
+    // |y| <= max(|y[-1]|, 20 |d|max) and |d| <= 2^17: with |gain| < 500 and |y[-1]| < 2e6 no
+    // gain * y can reach 2^31, where cvt.rzi saturates but x86 cvttss2si wraps
+    const bool no_patch = __all_sync(FULL, !active || (fabsf(gain) < 500.f && fabsf(y1) < 2e6f));
     const float a1 = (float)(-0.95);
-    for (uint32_t k = 0; k <= n_tiles; ++k) {
-      if (k >= 1) {
+    for (uint32_t k = 0; k < n_tiles + 2; ++k) {
+      if (active && k >= 1 && k <= n_tiles) {
         const uint32_t t = k - 1;
         const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
-        if (active) {
-          // all 32 inputs first (eight 128-bit loads), then the dependent chain
-          //   y = fl(fl(x - x1) - fl(-0.95f * y1)),  pcm = (int16_t)(gain * y)
-          // runs out of registers: two dependent FP32 ops per step.
-          const uint32_t *in = dem + ((t & 1) * nw + lane) * T::DEM_WORDS;
-          float x[32];
+        // all 32 numerators first (eight 128-bit loads), then the dependent chain
+        //   y = fl(d - fl(-0.95f * y1)),  pcm = (int16_t)(gain * y)      (IirFilter.cc:161-176)
+        // runs out of registers: two dependent FP32 ops per step.
+        const uint32_t *in = dem + ((t & 1) * nw + lane) * T::DEM_WORDS;
+        float d[32];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const u32x4 v = lds_u4(in + 4 * i);
-            x[4 * i] = u2f(v.x); x[4 * i + 1] = u2f(v.y); x[4 * i + 2] = u2f(v.z); x[4 * i + 3] = u2f(v.w);
-          }
-          int o[32];
-          const float x_in = x1;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float d = fadd(x[i], fmul(-1.0f, i == 0 ? x_in : x[i == 0 ? 0 : i - 1]));
-            const float y = fsub(d, fmul(a1, y1));
-            if (i < r) {
-              y1 = y;
-              x1 = x[i];
-            }
-            o[i] = f2i16_wrap(fmul(gain, y));
-          }
-          uint32_t *out = pcm_s + lane * T::PCM_WORDS;
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            sts_u4(out + 4 * i, u32x4{pack_i16x2(o[8 * i], o[8 * i + 1]), pack_i16x2(o[8 * i + 2], o[8 * i + 3]),
-                                     pack_i16x2(o[8 * i + 4], o[8 * i + 5]), pack_i16x2(o[8 * i + 6], o[8 * i + 7])});
+        for (int i = 0; i < 8; ++i) {
+          const u32x4 v = lds_u4(in + 4 * i);
+          d[4 * i] = u2f(v.x); d[4 * i + 1] = u2f(v.y); d[4 * i + 2] = u2f(v.z); d[4 * i + 3] = u2f(v.w);
         }
-        __syncwarp();
-        // PCM rows out: 64 bytes per channel per tile, two samples per lane per store
-        for (int idx = lane; idx < n_words; idx += 32) {
-          const int c = idx >> 4, wd = idx & 15;
-          const uint32_t chc = p.chan_ids[list0 + c];
-          int16_t *dst = p.pcm + (uint64_t)chc * p.pcm_stride + (uint64_t)t * 32 + 2 * wd;
-          const uint32_t v = pcm_s[c * T::PCM_WORDS + wd];
-          if (2 * wd + 1 < r) *reinterpret_cast<uint32_t *>(dst) = v;
-          else if (2 * wd < r) *dst = (int16_t)(v & 0xffffu);
+        uint32_t o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float ya = fsub(d[2 * i], fmul(a1, y1));
+          if (2 * i < r) y1 = ya;
+          const float yb = fsub(d[2 * i + 1], fmul(a1, y1));
+          if (2 * i + 1 < r) y1 = yb;
+          o[i] = no_patch ? __byte_perm((uint32_t)f2i_rz(fmul(gain, ya)), (uint32_t)f2i_rz(fmul(gain, yb)), 0x5410)
+                          : f2i16x2_wrap(fmul(gain, ya), fmul(gain, yb));
         }
-        __syncwarp();
+        uint32_t *row = pcm_s + ((t & 1) * nw + lane) * T::PCM_WORDS;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sts_u4(row + 4 * i, u32x4{o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]});
       }
       __syncthreads();
     }
-    if (active) {
-      iir[0] = x1;
-      iir[1] = y1;
-    }
+    if (active) iir[1] = y1;
   }
 }
 
@@ -752,14 +753,6 @@ struct WbTile {
     blob[16 * 32 + lane] = c.ew;
   }
 };
-
-// two (int16_t)float conversions with x86 wrap semantics, packed
-__device__ __forceinline__ uint32_t f2i16x2_wrap(float v0, float v1) {
-  int r0 = f2i_rz(v0), r1 = f2i_rz(v1);
-  if (!(fabsf(v0) < 2147483648.0f)) r0 = 0;
-  if (!(fabsf(v1) < 2147483648.0f)) r1 = 0;
-  return __byte_perm((uint32_t)r0, (uint32_t)r1, 0x5410);
-}
 
 // blockDim = 32 * WbTile::warps_for(p.G): warp 3 runs the recurrences, warps with
 // (w & 3) != 3 are workers, the remaining warps only keep the barrier count.
