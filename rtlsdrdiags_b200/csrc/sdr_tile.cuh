@@ -229,7 +229,8 @@ struct AmSsbTile {
   }
 };
 
-// blockDim = 32 * (workers + 1); the last warp runs the recurrences.
+// blockDim = 32 * (workers + 1); the last warp runs the recurrences. Both roles share one
+// round loop, so every thread of the CTA meets the same barrier instruction.
 template <bool SSB>
 __global__ void __launch_bounds__(512, 1) amssb_tile_kernel(const __grid_constant__ LaunchParams p) {
   using T = AmSsbTile<SSB>;
@@ -237,7 +238,6 @@ __global__ void __launch_bounds__(512, 1) amssb_tile_kernel(const __grid_constan
   char *smem = reinterpret_cast<char *>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nw = (int)(blockDim.x >> 5) - 1;  // workers in this CTA
-  char *in_base = smem;
   uint32_t *dem = reinterpret_cast<uint32_t *>(smem + nw * T::IN_BYTES);
   uint32_t *pcm_s = dem + 2 * nw * T::DEM_WORDS;  // [2 parities][nw][PCM_WORDS]
 
@@ -245,28 +245,45 @@ __global__ void __launch_bounds__(512, 1) amssb_tile_kernel(const __grid_constan
   const int n_here = (int)min((uint32_t)nw, p.n_list - list0);  // channels this CTA owns
   const uint32_t n_tiles = (p.n_samples + TILE - 1) / TILE;
   const int fmt = p.fmt;
+  const bool is_worker = warp < nw;
+  // a worker's channel is its warp index, a recurrence lane's channel its lane index
+  const int slot_id = is_worker ? warp : lane;
+  const bool active = slot_id < n_here;
+  const uint32_t ch = active ? p.chan_ids[list0 + slot_id] : 0;
+  uint32_t *blob = reinterpret_cast<uint32_t *>(p.state + (uint64_t)ch * p.state_stride);
 
-  if (warp < nw) {
-    // ------------------------------ worker ------------------------------
-    const bool active = warp < n_here;
-    uint32_t ch = 0;
-    const uint8_t *src = nullptr;
-    AmSsbCarry<SSB> pv;
-    bool lsb = false;
-    char *slots = in_base + warp * T::IN_BYTES;
+  // ---- worker state ----
+  AmSsbCarry<SSB> pv;
+  const uint8_t *src = p.iq + (uint64_t)ch * p.ch_stride;
+  int16_t *out = p.pcm + (uint64_t)ch * p.pcm_stride;
+  char *slots = smem + (is_worker ? warp : 0) * T::IN_BYTES;
+  bool lsb = false;
+  // ---- recurrence state ----
+  float y1 = 0.f, gain = 0.f;
+  bool no_patch = true;
+  const float a1 = (float)(-0.95);
+
+  if (is_worker) {
     if (active) {
-      ch = p.chan_ids[list0 + warp];
-      src = p.iq + (uint64_t)ch * p.ch_stride;
-      T::load_carry(pv, reinterpret_cast<const uint32_t *>(p.state + (uint64_t)ch * p.state_stride), lane);
+      T::load_carry(pv, blob, lane);
       if (SSB) lsb = p.lsb[ch] != 0;
-      const int valid0 = (int)min((uint32_t)TILE, p.n_samples) >> 3;  // 16-byte chunks in tile 0
-      tile_fill(slots, src, lane, valid0);
+      tile_fill(slots, src, lane, (int)min((uint32_t)TILE, p.n_samples) >> 3);
     }
     cp_async_commit();
-    int16_t *out = active ? p.pcm + (uint64_t)ch * p.pcm_stride : nullptr;
-    // round k: tile k is computed here, the recurrence warp turns tile k-1 into PCM, and
-    // this warp stores the PCM of tile k-2 (64 bytes, coalesced)
-    for (uint32_t k = 0; k < n_tiles + 2; ++k) {
+  } else {
+    if (active) {
+      y1 = u2f(blob[T::NREG * 32 + 1]);
+      gain = p.scale[ch];
+    }
+    // |y| <= max(|y[-1]|, 20 |d|max) and |d| <= 2^17: with |gain| < 500 and |y[-1]| < 2e6 no
+    // gain * y can reach 2^31, where cvt.rzi saturates but x86 cvttss2si wraps
+    no_patch = __all_sync(FULL, !active || (fabsf(gain) < 500.f && fabsf(y1) < 2e6f));
+  }
+
+  // round k: the workers compute tile k and store the PCM of tile k-2 (64 bytes,
+  // coalesced); the recurrence warp turns tile k-1 into PCM.
+  for (uint32_t k = 0; k < n_tiles + 2; ++k) {
+    if (is_worker) {
       if (active && k >= 2) {
         const uint32_t t = k - 2;
         const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
@@ -276,8 +293,8 @@ __global__ void __launch_bounds__(512, 1) amssb_tile_kernel(const __grid_constan
       if (active && k < n_tiles) {
         if (k + 1 < n_tiles) {
           const uint32_t s1 = (k + 1) * TILE;
-          const int valid = (int)min((uint32_t)TILE, p.n_samples - s1) >> 3;
-          tile_fill(slots + ((k + 1) & 1) * TILE_BYTES, src + (uint64_t)s1 * 2, lane, valid);
+          tile_fill(slots + ((k + 1) & 1) * TILE_BYTES, src + (uint64_t)s1 * 2, lane,
+                    (int)min((uint32_t)TILE, p.n_samples - s1) >> 3);
         }
         cp_async_commit();
         cp_async_wait<1>();
@@ -289,55 +306,39 @@ __global__ void __launch_bounds__(512, 1) amssb_tile_kernel(const __grid_constan
         dem[((k & 1) * nw + warp) * T::DEM_WORDS + lane] = v;
         __syncwarp();  // every lane has read slot k&1 before tile k+2 is copied into it
       }
-      __syncthreads();
-    }
-    if (active) T::store_carry(pv, reinterpret_cast<uint32_t *>(p.state + (uint64_t)ch * p.state_stride), lane);
-  } else {
-    // ---------------------- recurrence warp: lane == channel ----------------------
-    const bool active = lane < n_here;
-    float y1 = 0.f, gain = 0.f;
-    float *iir = nullptr;
-    if (active) {
-      const uint32_t ch = p.chan_ids[list0 + lane];
-      iir = reinterpret_cast<float *>(p.state + (uint64_t)ch * p.state_stride + T::NREG * 128);
-      y1 = iir[1];
-      gain = p.scale[ch];
-    }
-    // |y| <= max(|y[-1]|, 20 |d|max) and |d| <= 2^17: with |gain| < 500 and |y[-1]| < 2e6 no
-    // gain * y can reach 2^31, where cvt.rzi saturates but x86 cvttss2si wraps
-    const bool no_patch = __all_sync(FULL, !active || (fabsf(gain) < 500.f && fabsf(y1) < 2e6f));
-    const float a1 = (float)(-0.95);
-    for (uint32_t k = 0; k < n_tiles + 2; ++k) {
-      if (active && k >= 1 && k <= n_tiles) {
-        const uint32_t t = k - 1;
-        const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
-        // all 32 numerators first (eight 128-bit loads), then the dependent chain
-        //   y = fl(d - fl(-0.95f * y1)),  pcm = (int16_t)(gain * y)      (IirFilter.cc:161-176)
-        // runs out of registers: two dependent FP32 ops per step.
-        const uint32_t *in = dem + ((t & 1) * nw + lane) * T::DEM_WORDS;
-        float d[32];
+    } else if (active && k >= 1 && k <= n_tiles) {
+      const uint32_t t = k - 1;
+      const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
+      // all 32 numerators first (eight 128-bit loads), then the dependent chain
+      //   y = fl(d - fl(-0.95f * y1)),  pcm = (int16_t)(gain * y)      (IirFilter.cc:161-176)
+      // runs out of registers: two dependent FP32 ops per step.
+      const uint32_t *in = dem + ((t & 1) * nw + lane) * T::DEM_WORDS;
+      float d[32];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const u32x4 v = lds_u4(in + 4 * i);
-          d[4 * i] = u2f(v.x); d[4 * i + 1] = u2f(v.y); d[4 * i + 2] = u2f(v.z); d[4 * i + 3] = u2f(v.w);
-        }
-        uint32_t o[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float ya = fsub(d[2 * i], fmul(a1, y1));
-          if (2 * i < r) y1 = ya;
-          const float yb = fsub(d[2 * i + 1], fmul(a1, y1));
-          if (2 * i + 1 < r) y1 = yb;
-          o[i] = no_patch ? __byte_perm((uint32_t)f2i_rz(fmul(gain, ya)), (uint32_t)f2i_rz(fmul(gain, yb)), 0x5410)
-                          : f2i16x2_wrap(fmul(gain, ya), fmul(gain, yb));
-        }
-        uint32_t *row = pcm_s + ((t & 1) * nw + lane) * T::PCM_WORDS;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) sts_u4(row + 4 * i, u32x4{o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]});
+      for (int i = 0; i < 8; ++i) {
+        const u32x4 v = lds_u4(in + 4 * i);
+        d[4 * i] = u2f(v.x); d[4 * i + 1] = u2f(v.y); d[4 * i + 2] = u2f(v.z); d[4 * i + 3] = u2f(v.w);
       }
-      __syncthreads();
+      uint32_t o[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float ya = fsub(d[2 * i], fmul(a1, y1));
+        if (2 * i < r) y1 = ya;
+        const float yb = fsub(d[2 * i + 1], fmul(a1, y1));
+        if (2 * i + 1 < r) y1 = yb;
+        o[i] = no_patch ? __byte_perm((uint32_t)f2i_rz(fmul(gain, ya)), (uint32_t)f2i_rz(fmul(gain, yb)), 0x5410)
+                        : f2i16x2_wrap(fmul(gain, ya), fmul(gain, yb));
+      }
+      uint32_t *row = pcm_s + ((t & 1) * nw + lane) * T::PCM_WORDS;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) sts_u4(row + 4 * i, u32x4{o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]});
     }
-    if (active) iir[1] = y1;
+    __syncthreads();
+  }
+
+  if (active) {
+    if (is_worker) T::store_carry(pv, blob, lane);
+    else blob[T::NREG * 32 + 1] = f2u(y1);
   }
 }
 
@@ -754,41 +755,42 @@ struct WbTile {
   }
 };
 
-// blockDim = 32 * WbTile::warps_for(p.G): warp 3 runs the recurrences, warps with
-// (w & 3) != 3 are workers, the remaining warps only keep the barrier count.
+// blockDim = 32 * WbTile::warps_for(p.G, s3): warp 3 runs the recurrences, the warps
+// WbTile::is_worker() names are workers, the rest only keep the barrier count. All roles
+// share one round loop, so every thread of the CTA meets the same barrier instruction.
 __global__ void __launch_bounds__(768, 1) wbfm_tile_kernel(const __grid_constant__ LaunchParams p) {
   using T = WbTile;
   extern __shared__ uint4 smem_raw[];
   char *smem = reinterpret_cast<char *>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nw = (int)p.G;
-  const int iir_warp = 3;
   const int s3 = (int)p.aux;
+  const bool is_iir = warp == 3;
+  const bool is_worker = !is_iir && T::is_worker(warp, s3);
   const uint32_t list0 = blockIdx.x * (uint32_t)nw;
   const int n_here = (int)min((uint32_t)nw, p.n_list - list0);
   const uint32_t n_tiles = (p.n_samples + TILE - 1) / TILE;
-  char *in_base = smem;                       // nw input slots of TILE_BYTES
-  char *ring_base = smem + nw * TILE_BYTES;   // nw rings of RING_BYTES
+  char *ring_base = smem + nw * TILE_BYTES;   // after nw input slots: nw rings of RING_BYTES
 
-  if (warp != iir_warp && !T::is_worker(warp, s3)) {
-    for (uint32_t kk = 0; kk < n_tiles + 2; ++kk) __syncthreads();
-  } else if (warp != iir_warp) {
-    // ------------------------------ worker ------------------------------
-    const int wi = T::worker_index(warp, s3);  // = channel slot
-    const bool active = wi < n_here;
-    uint32_t ch = 0;
-    const uint8_t *src = nullptr;
-    uint32_t *blob = nullptr;
-    WbCarry pv;
-    float k = 0.f, v_boundary = 0.f;
-    bool big_b = false, no_patch = false;
-    char *in_slot = in_base + wi * TILE_BYTES;
-    char *ring = ring_base + wi * T::RING_BYTES;
-    int16_t *out = nullptr;
+  const int slot_id = is_iir ? lane : T::worker_index(warp, s3);  // channel slot in this CTA
+  const bool active = (is_iir || is_worker) && slot_id < n_here;
+  const uint32_t ch = active ? p.chan_ids[list0 + slot_id] : 0;
+  uint32_t *blob = reinterpret_cast<uint32_t *>(p.state + (uint64_t)ch * p.state_stride);
+  char *ring = ring_base + (active ? slot_id : 0) * T::RING_BYTES;
+
+  // ---- worker state ----
+  WbCarry pv;
+  const uint8_t *src = p.iq + (uint64_t)ch * p.ch_stride;
+  int16_t *out = p.pcm + (uint64_t)ch * p.pcm_stride;
+  char *in_slot = smem + (active && is_worker ? slot_id : 0) * TILE_BYTES;
+  float k = 0.f, v_boundary = 0.f;
+  bool big_b = false, no_patch = false;
+  // ---- recurrence state ----
+  float y1 = 0.f;
+  const float a1 = (float)(-0.9492274);
+
+  if (is_worker) {
     if (active) {
-      ch = p.chan_ids[list0 + wi];
-      src = p.iq + (uint64_t)ch * p.ch_stride;
-      blob = reinterpret_cast<uint32_t *>(p.state + (uint64_t)ch * p.state_stride);
       T::load_carry(pv, blob, lane);
       v_boundary = u2f(blob[T::NREG * 32 + 1]);
       big_b = blob[T::NREG * 32 + 2] != 0;
@@ -796,91 +798,82 @@ __global__ void __launch_bounds__(768, 1) wbfm_tile_kernel(const __grid_constant
       // |y| <= max(|y[-1]|, |u|max / (1 - |a1|)) < 3.2 |k|: with |k| < 1e8 and |y[-1]| < 1e9 no
       // value can reach 2^31, where cvt.rzi (saturating) and x86 cvttss2si (wrapping) differ
       no_patch = fabsf(k) < 1e8f && fabsf(u2f(blob[T::NREG * 32])) < 1e9f;
-      out = p.pcm + (uint64_t)ch * p.pcm_stride;
       tile_fill(in_slot, src, lane, (int)min((uint32_t)TILE, p.n_samples) >> 3);
     }
     cp_async_commit();
-    for (uint32_t kk = 0; kk < n_tiles + 2; ++kk) {
-      if (active) {
-        char *slot = ring + (kk & 1) * 4096;
-        if (kk >= 2) {
-          // C(kk-2): the recurrence warp left y[0..1023] where u was; (int16_t)y of the lane's row
-          const uint32_t t = kk - 2;
-          const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
-          uint32_t dW[16];
+  } else if (is_iir && active) {
+    y1 = u2f(blob[T::NREG * 32]);
+  }
+
+  for (uint32_t kk = 0; kk < n_tiles + 2; ++kk) {
+    if (is_worker && active) {
+      char *slot = ring + (kk & 1) * 4096;
+      if (kk >= 2) {
+        // C(kk-2): the recurrence warp left y[0..1023] where u was; (int16_t)y of the lane's row
+        const uint32_t t = kk - 2;
+        const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
+        uint32_t dW[16];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const u32x4 v = lds_u4(slot + T::u_off(lane, j));
-            if (no_patch) {
-              dW[2 * j] = __byte_perm((uint32_t)f2i_rz(u2f(v.x)), (uint32_t)f2i_rz(u2f(v.y)), 0x5410);
-              dW[2 * j + 1] = __byte_perm((uint32_t)f2i_rz(u2f(v.z)), (uint32_t)f2i_rz(u2f(v.w)), 0x5410);
-            } else {
-              dW[2 * j] = f2i16x2_wrap(u2f(v.x), u2f(v.y));
-              dW[2 * j + 1] = f2i16x2_wrap(u2f(v.z), u2f(v.w));
-            }
+        for (int j = 0; j < 8; ++j) {
+          const u32x4 v = lds_u4(slot + T::u_off(lane, j));
+          if (no_patch) {
+            dW[2 * j] = __byte_perm((uint32_t)f2i_rz(u2f(v.x)), (uint32_t)f2i_rz(u2f(v.y)), 0x5410);
+            dW[2 * j + 1] = __byte_perm((uint32_t)f2i_rz(u2f(v.z)), (uint32_t)f2i_rz(u2f(v.w)), 0x5410);
+          } else {
+            dW[2 * j] = f2i16x2_wrap(u2f(v.x), u2f(v.y));
+            dW[2 * j + 1] = f2i16x2_wrap(u2f(v.z), u2f(v.w));
           }
-          const int pcm = T::part_c(dW, pv, lane, r, big_b);
-          if (lane < r) out[(uint64_t)t * 32 + lane] = (int16_t)pcm;
-          __syncwarp();  // every lane has read d before A overwrites the slot
         }
-        if (kk < n_tiles) {
-          cp_async_wait<0>();
-          __syncwarp();
-          uint32_t w[16];
-          tile_read(in_slot, lane, w);
-          __syncwarp();
-          if (kk + 1 < n_tiles) {  // the single input slot is free again: fetch the next tile now
-            const uint32_t s1 = (kk + 1) * TILE;
-            tile_fill(in_slot, src + (uint64_t)s1 * 2, lane, (int)min((uint32_t)TILE, p.n_samples - s1) >> 3);
-          }
-          cp_async_commit();
-          const int r = (int)min((uint32_t)TILE, p.n_samples - kk * TILE) >> 5;
-          T::part_a(w, p.fmt, k, p.lut, pv, v_boundary, slot, lane, r);
+        const int pcm = T::part_c(dW, pv, lane, r, big_b);
+        if (lane < r) out[(uint64_t)t * 32 + lane] = (int16_t)pcm;
+        __syncwarp();  // every lane has read y before A overwrites the slot
+      }
+      if (kk < n_tiles) {
+        cp_async_wait<0>();
+        __syncwarp();
+        uint32_t w[16];
+        tile_read(in_slot, lane, w);
+        __syncwarp();
+        if (kk + 1 < n_tiles) {  // the single input slot is free again: fetch the next tile now
+          const uint32_t s1 = (kk + 1) * TILE;
+          tile_fill(in_slot, src + (uint64_t)s1 * 2, lane, (int)min((uint32_t)TILE, p.n_samples - s1) >> 3);
+        }
+        cp_async_commit();
+        const int r = (int)min((uint32_t)TILE, p.n_samples - kk * TILE) >> 5;
+        T::part_a(w, p.fmt, k, p.lut, pv, v_boundary, slot, lane, r);
+      }
+    } else if (is_iir && active && kk >= 1 && kk <= n_tiles) {
+      // B(kk-1): y[n] = fl(u[n] - fl(a1 * y[n-1])) in place, lane == channel (IirFilter.cc:161-176)
+      const uint32_t t = kk - 1;
+      const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
+      char *slot = ring + (t & 1) * 4096;
+      for (int row = 0; row < r; ++row) {
+        u32x4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = lds_u4(slot + T::u_off(row, j));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float y0 = fsub(u2f(v[j].x), fmul(a1, y1));
+          const float y2 = fsub(u2f(v[j].y), fmul(a1, y0));
+          const float y3 = fsub(u2f(v[j].z), fmul(a1, y2));
+          y1 = fsub(u2f(v[j].w), fmul(a1, y3));
+          sts_u4(slot + T::u_off(row, j), u32x4{f2u(y0), f2u(y2), f2u(y3), f2u(y1)});
         }
       }
-      __syncthreads();
     }
-    if (active) {
+    __syncthreads();
+  }
+
+  if (active) {
+    if (is_worker) {
       T::store_carry(pv, blob, lane);
       if (lane == 0) {
         blob[T::NREG * 32 + 1] = f2u(v_boundary);
         blob[T::NREG * 32 + 2] = big_b;
       }
+    } else {
+      blob[T::NREG * 32] = f2u(y1);
     }
-  } else {
-    // ---------------------- recurrence warp: lane == channel ----------------------
-    const bool active = lane < n_here;
-    uint32_t *tail = nullptr;
-    float y1 = 0.f;
-    if (active) {
-      const uint32_t ch = p.chan_ids[list0 + lane];
-      tail = reinterpret_cast<uint32_t *>(p.state + (uint64_t)ch * p.state_stride) + T::NREG * 32;
-      y1 = u2f(tail[0]);
-    }
-    const float a1 = (float)(-0.9492274);
-    char *ring = ring_base + lane * T::RING_BYTES;
-    for (uint32_t kk = 0; kk < n_tiles + 2; ++kk) {
-      if (active && kk >= 1 && kk <= n_tiles) {
-        const uint32_t t = kk - 1;
-        const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
-        char *slot = ring + (t & 1) * 4096;
-        for (int row = 0; row < r; ++row) {
-          u32x4 v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = lds_u4(slot + T::u_off(row, j));
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float y0 = fsub(u2f(v[j].x), fmul(a1, y1));
-            const float y2 = fsub(u2f(v[j].y), fmul(a1, y0));
-            const float y3 = fsub(u2f(v[j].z), fmul(a1, y2));
-            y1 = fsub(u2f(v[j].w), fmul(a1, y3));
-            sts_u4(slot + T::u_off(row, j), u32x4{f2u(y0), f2u(y2), f2u(y3), f2u(y1)});
-          }
-        }
-      }
-      __syncthreads();
-    }
-    if (active) tail[0] = f2u(y1);
   }
 }
 
