@@ -31,6 +31,9 @@ sys.path.insert(0, ROOT)
 ALGO_BYTES_PER_SAMPLE = 2.0 + 2.0 / 32.0  # 2 B of IQ read + one int16 PCM sample per 32
 BLOCK_BYTES = 32768
 METRIC = "aggregate_iq_msamples_per_s"
+KERNELS = {"am": "amssb_tile_kernel<false>", "ssb": "amssb_tile_kernel<true>", "fm": "fm_tile_kernel",
+           "wbfm": "wbfm_tile_kernel",
+           "mixed": "amssb_tile_kernel<false> + amssb_tile_kernel<true> + fm_tile_kernel + wbfm_tile_kernel"}
 
 
 def parse_args():
@@ -357,7 +360,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE,
-                         "kernel_ms": round(kernel_ms, 4), "kernel": "demod_kernel<%s>" % args.workload},
+                         "kernel_ms": round(kernel_ms, 4), "kernel": KERNELS[args.workload]},
             "cpu_baseline": cpu,
             "other_workloads": extras,
         }
