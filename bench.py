@@ -175,6 +175,7 @@ def bench_one(torch, R, synth, workload, channels, n_blocks, steps, warmup, sign
         a.record(stream)
         for _ in range(n):
             eng.accept_iq_device(iq)
+        eng.join()  # the end event must cover the engine's second stream too
         b.record(stream)
         return a, b
 

@@ -100,6 +100,11 @@ int sdr_get_pcm(sdr_engine *e, int16_t *pcm, uint32_t *counts);
 /* Device-resident PCM of the last call: [n_channels][*stride] int16. */
 int sdr_pcm_device(sdr_engine *e, int16_t **pcm, uint64_t *stride);
 int sdr_sync(sdr_engine *e);
+/* The engine runs part of its work on a second, internal stream. sdr_join makes the
+ * engine's (or the caller's, see sdr_set_stream) stream wait for it without blocking the
+ * host, so that an event recorded on that stream afterwards covers everything queued so
+ * far. sdr_get_pcm and sdr_sync imply it. */
+int sdr_join(sdr_engine *e);
 
 /* Launch shape of one demodulator kind: channels per CTA (1..32) and threads
  * per CTA (multiple of 32). 0 = let the engine choose. For tuning and tests. */

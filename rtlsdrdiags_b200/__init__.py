@@ -23,7 +23,7 @@ BLOCK_BYTES = 32768  # the reference's IQ block: 16384 complex samples = 64 ms -
 # every symbol include/sdr_b200.h declares
 ABI_SYMBOLS = ["sdr_engine_create", "sdr_engine_destroy", "sdr_set_stream", "sdr_set_scaling",
                "sdr_set_mode", "sdr_set_modes", "sdr_set_gain", "sdr_set_gain_all", "sdr_reset",
-               "sdr_accept_iq", "sdr_get_pcm", "sdr_pcm_device", "sdr_sync", "sdr_set_launch_shape",
+               "sdr_accept_iq", "sdr_get_pcm", "sdr_pcm_device", "sdr_sync", "sdr_join", "sdr_set_launch_shape",
                "sdr_launch_count", "sdr_state_bytes", "sdr_last_error", "sdr_version"]
 
 
@@ -59,6 +59,7 @@ def load_library(build_if_missing=True):
     L.sdr_get_pcm.argtypes = [vp, vp, vp]
     L.sdr_pcm_device.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     L.sdr_sync.argtypes = [vp]
+    L.sdr_join.argtypes = [vp]
     L.sdr_set_launch_shape.argtypes = [vp, i32, u32, u32]
     L.sdr_launch_count.argtypes = [vp]
     L.sdr_launch_count.restype = u64
@@ -165,6 +166,10 @@ class Engine:
 
     def sync(self):
         self._ck(self.L.sdr_sync(self.h))
+
+    def join(self):
+        """Make the engine's stream wait for its internal second stream (no host blocking)."""
+        self._ck(self.L.sdr_join(self.h))
 
     @property
     def launch_count(self):

@@ -43,7 +43,9 @@ struct LaunchParams {
   int16_t *pcm;              // [n_channels][pcm_stride]
   uint64_t pcm_stride;       // int16 elements between channels
   const float *lut;          // atan2 table of this mode (FM 280x280, WBFM 256x256)
-  uint32_t aux;              // kernel-specific tuning word
+  uint32_t aux;              // kernel-specific word (WBFM: scheduler sharing; AM/SSB: time segments)
+  float *scratch;            // AM/SSB: IIR numerators between the FIR and the recurrence kernel,
+                             // [tile][list index][32 lanes]
 };
 
 // ---------------------------------------------------------------------------

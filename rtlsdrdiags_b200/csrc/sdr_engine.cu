@@ -7,8 +7,8 @@
 //   * per-channel mode / gain / sideband tables, mirrored on the host,
 //   * per-kind channel lists (channels bucketed by mode so every CTA is
 //     mode-uniform), the two atan2 tables, an IQ staging buffer and the PCM buffer.
-// sdr_accept_iq queues at most four kernel launches (one per demodulator kind
-// that has channels) on one stream. No CPU path exists.
+// sdr_accept_iq queues one launch per demodulator kind that has channels (AM and SSB: a FIR
+// kernel plus a recurrence kernel on a second stream). No CPU path exists.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -38,6 +38,13 @@ struct sdr_engine {
   int n_sm = 148;
   int smem_optin = 227 * 1024;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  // AM/SSB: the recurrence kernels run on rec_stream, one call behind the FIR kernels on
+  // `stream`; the numerators travel through scratch[kind][call parity]
+  cudaStream_t rec_stream = nullptr;
+  cudaEvent_t ev_fir[2] = {}, ev_rec[2] = {};
+  float *d_scratch[5][2] = {};
+  uint64_t seq = 0;        // sdr_accept_iq calls so far
+  bool rec_pending = false;  // work on rec_stream that `stream` has not waited for yet
   int scaling = SDR_SCALING_RADIODIAGS;
 
   // host mirrors (index 1..4 = kind)
@@ -121,36 +128,34 @@ float scale_of(int kind, float gain, int scaling) {
   return k;
 }
 
-// Warp-tile kernels: G = worker warps (= channels) per CTA, one more warp runs the
-// recurrences. Pick the CTA size that leaves the fewest idle channel slots per wave.
-uint32_t choose_workers(const sdr_engine *e, uint32_t n_list, int max_workers) {
-  uint32_t best = 1;
-  double best_eff = -1;
-  for (int R = 1; R <= 2; ++R) {
-    const long gmax = R == 1 ? max_workers : max_workers / 2;
-    const long slots = (long)e->n_sm * R;
-    const long W = ((long)n_list + slots * gmax - 1) / (slots * gmax);
-    const long G = ((long)n_list + slots * W - 1) / (slots * W);
-    const long ctas = ((long)n_list + G - 1) / G;
-    const long waves = (ctas + slots - 1) / slots;
-    const double eff = (double)n_list / (double)(waves * slots * G);
-    if (eff > best_eff + 1e-9) {
-      best_eff = eff;
-      best = (uint32_t)G;
-    }
+// main stream waits for everything queued on rec_stream
+int join_streams(sdr_engine *e) {
+  if (e->rec_pending) {
+    SDR_CK(e, cudaStreamWaitEvent(e->stream, e->ev_rec[(e->seq + 1) & 1], 0));
+    e->rec_pending = false;
   }
-  return best;
+  return SDR_OK;
 }
 
+// AM / SSB: FIR kernel on the engine's stream, recurrence kernel on rec_stream.
 template <bool SSB>
-int launch_amssb_tile(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples, int fmt) {
+int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples, int fmt) {
   using T = AmSsbTile<SSB>;
   const uint32_t n_list = (uint32_t)e->list[kind].size();
   if (n_list == 0) return SDR_OK;
-  uint32_t G = choose_workers(e, n_list, T::MAX_WORKERS);
-  if (e->shape[kind].G) G = e->shape[kind].G;
-  if (G > (uint32_t)T::MAX_WORKERS) G = T::MAX_WORKERS;
-  const int smem = T::smem_bytes((int)G);
+  const int par = (int)(e->seq & 1);
+  const uint32_t n_tiles = (n_samples + TILE - 1) / TILE;
+  if (!e->d_scratch[kind][par]) {
+    const size_t max_tiles = (size_t)((e->max_bytes / 2 + TILE - 1) / TILE);
+    SDR_CK(e, cudaMalloc(&e->d_scratch[kind][par], (size_t)e->n * max_tiles * 32 * sizeof(float)));
+  }
+  // time segments per channel: aim at ~18 worker warps per SM, keep segments >= 8 tiles
+  static const int nseg_env = getenv("SDR_AM_NSEG") ? atoi(getenv("SDR_AM_NSEG")) : 0;
+  uint32_t nseg = (uint32_t)((18L * e->n_sm + n_list - 1) / n_list);
+  if (nseg_env > 0) nseg = (uint32_t)nseg_env;
+  if (nseg > 8) nseg = 8;
+  while (nseg > 1 && (n_tiles + nseg - 1) / nseg < 8) --nseg;
+  if (nseg < 1) nseg = 1;
   LaunchParams p;
   p.iq = iq;
   p.ch_stride = ch_stride;
@@ -158,7 +163,7 @@ int launch_amssb_tile(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_st
   p.fmt = fmt;
   p.chan_ids = e->d_list[kind];
   p.n_list = n_list;
-  p.G = G;
+  p.G = 4;
   p.state = e->d_state[kind];
   p.state_stride = (uint32_t)T::STATE_BYTES;
   p.scale = e->d_scale[kind];
@@ -166,10 +171,32 @@ int launch_amssb_tile(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_st
   p.pcm = e->d_pcm;
   p.pcm_stride = e->pcm_stride;
   p.lut = nullptr;
-  p.aux = 0;
-  SDR_CK(e, cudaFuncSetAttribute(amssb_tile_kernel<SSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  const uint32_t grid = (n_list + G - 1) / G;
-  amssb_tile_kernel<SSB><<<grid, 32 * (G + 1), smem, e->stream>>>(p);
+  p.aux = nseg;
+  p.scratch = e->d_scratch[kind][par];
+  const uint64_t warps = (uint64_t)n_list * nseg;
+  amssb_fir_kernel<SSB><<<(uint32_t)((warps + 3) / 4), 128, 4 * 2 * TILE_BYTES, e->stream>>>(p);
+  SDR_CK(e, cudaGetLastError());
+  e->launches++;
+  return SDR_OK;
+}
+
+int launch_dc_block(sdr_engine *e, int kind, uint32_t n_samples) {
+  const uint32_t n_list = (uint32_t)e->list[kind].size();
+  if (n_list == 0) return SDR_OK;
+  const int par = (int)(e->seq & 1);
+  const int nreg = kind == SDR_KIND_SSB ? AmSsbTile<true>::NREG : AmSsbTile<false>::NREG;
+  LaunchParams p = {};
+  p.n_samples = n_samples;
+  p.chan_ids = e->d_list[kind];
+  p.n_list = n_list;
+  p.state = e->d_state[kind];
+  p.state_stride = (uint32_t)state_bytes(kind);
+  p.scale = e->d_scale[kind];
+  p.pcm = e->d_pcm;
+  p.pcm_stride = e->pcm_stride;
+  p.aux = (uint32_t)nreg * 128;  // byte offset of the IIR tail in the state blob
+  p.scratch = e->d_scratch[kind][par];
+  dc_block_kernel<<<(n_list + 31) / 32, 32, 0, e->rec_stream>>>(p);
   SDR_CK(e, cudaGetLastError());
   e->launches++;
   return SDR_OK;
@@ -198,6 +225,7 @@ int launch_fm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_
   p.pcm_stride = e->pcm_stride;
   p.lut = e->d_lut_fm;
   p.aux = 0;
+  p.scratch = nullptr;
   const uint32_t grid = (n_list + G - 1) / G;
   fm_tile_kernel<<<grid, 32 * G, smem, e->stream>>>(p);
   SDR_CK(e, cudaGetLastError());
@@ -237,6 +265,7 @@ int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint3
   // workers allowed on the recurrence warp's scheduler (tunable: SDR_WB_S3)
   static const int s3_env = getenv("SDR_WB_S3") ? atoi(getenv("SDR_WB_S3")) : 4;
   p.aux = (uint32_t)s3_env;
+  p.scratch = nullptr;
   SDR_CK(e, cudaFuncSetAttribute(wbfm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const uint32_t grid = (n_list + G - 1) / G;
   wbfm_tile_kernel<<<grid, 32 * T::warps_for((int)G, s3_env), smem, e->stream>>>(p);
@@ -246,6 +275,12 @@ int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint3
 }
 
 int upload_tables(sdr_engine *e) {
+  bool dirty = e->lists_dirty || e->lsb_dirty;
+  for (int k = 1; k <= 4; ++k) dirty = dirty || e->scale_dirty[k];
+  if (dirty) {  // a recurrence kernel may still be reading the tables
+    int rc = join_streams(e);
+    if (rc) return rc;
+  }
   if (e->lists_dirty) {
     for (int k = 1; k <= 4; ++k) e->list[k].clear();
     for (uint32_t ch = 0; ch < e->n; ++ch) {
@@ -313,6 +348,11 @@ int sdr_engine_create(uint32_t n_channels, int device, uint64_t max_bytes_per_ch
   SDR_CK_CREATE(cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device));
   SDR_CK_CREATE(cudaDeviceGetAttribute(&e->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   SDR_CK_CREATE(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+  SDR_CK_CREATE(cudaStreamCreateWithFlags(&e->rec_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    SDR_CK_CREATE(cudaEventCreateWithFlags(&e->ev_fir[i], cudaEventDisableTiming));
+    SDR_CK_CREATE(cudaEventCreateWithFlags(&e->ev_rec[i], cudaEventDisableTiming));
+  }
   e->stream = e->own_stream;
 
   e->mode.assign(n_channels, SDR_MODE_NONE);  // IqDataProcessor.cc:38
@@ -327,7 +367,7 @@ int sdr_engine_create(uint32_t n_channels, int device, uint64_t max_bytes_per_ch
     SDR_CK_CREATE(cudaMalloc(&e->d_list[k], (size_t)n_channels * 4));
   }
   SDR_CK_CREATE(cudaMalloc(&e->d_lsb, n_channels));
-  e->pcm_stride = (max_bytes_per_channel / 64 + 1) & ~1ull;
+  e->pcm_stride = (max_bytes_per_channel / 64 + 7) & ~7ull;  // rows stay 16-byte aligned
   SDR_CK_CREATE(cudaMalloc(&e->d_pcm, (size_t)n_channels * e->pcm_stride * 2));
   SDR_CK_CREATE(cudaMemsetAsync(e->d_pcm, 0, (size_t)n_channels * e->pcm_stride * 2, e->stream));
 
@@ -360,7 +400,17 @@ int sdr_engine_destroy(sdr_engine *e) {
   if (!e) return SDR_E_ARG;
   cudaSetDevice(e->device);
   if (e->own_stream) cudaStreamSynchronize(e->own_stream);
+  if (e->rec_stream) {
+    cudaStreamSynchronize(e->rec_stream);
+    cudaStreamDestroy(e->rec_stream);
+  }
+  for (int i = 0; i < 2; ++i) {
+    if (e->ev_fir[i]) cudaEventDestroy(e->ev_fir[i]);
+    if (e->ev_rec[i]) cudaEventDestroy(e->ev_rec[i]);
+  }
   for (int k = 1; k <= 4; ++k) {
+    cudaFree(e->d_scratch[k][0]);
+    cudaFree(e->d_scratch[k][1]);
     cudaFree(e->d_state[k]);
     cudaFree(e->d_scale[k]);
     cudaFree(e->d_list[k]);
@@ -378,6 +428,8 @@ int sdr_engine_destroy(sdr_engine *e) {
 int sdr_set_stream(sdr_engine *e, void *cuda_stream) {
   if (!e) return SDR_E_ARG;
   SDR_CK(e, cudaStreamSynchronize(e->stream));
+  SDR_CK(e, cudaStreamSynchronize(e->rec_stream));
+  e->rec_pending = false;
   e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
   return SDR_OK;
 }
@@ -431,6 +483,10 @@ int sdr_set_gain_all(sdr_engine *e, int kind, float gain) {
 int sdr_reset(sdr_engine *e, uint32_t ch, int kind) {
   if (!e || ch >= e->n || kind < SDR_KIND_AM || kind > SDR_KIND_SSB) return SDR_E_ARG;
   SDR_CK(e, cudaSetDevice(e->device));
+  {
+    int rc = join_streams(e);  // a recurrence kernel may still be updating this blob
+    if (rc) return rc;
+  }
   size_t sb = (size_t)state_bytes(kind), n = sb;
   // WbFmDemodulator::resetDemodulator leaves the de-emphasis IIR alone
   // (WbFmDemodulator.cc:304-320); its state is the last 16 bytes of the blob.
@@ -468,10 +524,24 @@ int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_str
   }
   const int fmt = (flags & SDR_IQ_S8_ROTATED) ? FMT_S8_ROTATED : FMT_U8_OFFSET_ROTATE;
   const uint32_t n_samples = (uint32_t)(bytes / 2);
-  if ((rc = launch_amssb_tile<false>(e, SDR_KIND_AM, dev_iq, dev_stride, n_samples, fmt))) return rc;
-  if ((rc = launch_amssb_tile<true>(e, SDR_KIND_SSB, dev_iq, dev_stride, n_samples, fmt))) return rc;
+  const bool have_rec = !e->list[SDR_KIND_AM].empty() || !e->list[SDR_KIND_SSB].empty();
+  const int par = (int)(e->seq & 1);
+  // scratch[par] was last read by the recurrence kernels of the call before the previous one
+  if (have_rec) SDR_CK(e, cudaStreamWaitEvent(e->stream, e->ev_rec[par], 0));
+  if ((rc = launch_amssb<false>(e, SDR_KIND_AM, dev_iq, dev_stride, n_samples, fmt))) return rc;
+  if ((rc = launch_amssb<true>(e, SDR_KIND_SSB, dev_iq, dev_stride, n_samples, fmt))) return rc;
+  if (have_rec) {
+    SDR_CK(e, cudaEventRecord(e->ev_fir[par], e->stream));
+    SDR_CK(e, cudaStreamWaitEvent(e->rec_stream, e->ev_fir[par], 0));
+    if ((rc = launch_dc_block(e, SDR_KIND_AM, n_samples))) return rc;
+    if ((rc = launch_dc_block(e, SDR_KIND_SSB, n_samples))) return rc;
+  }
+  // always recorded, so ev_rec[par] of the latest call orders after everything on rec_stream
+  SDR_CK(e, cudaEventRecord(e->ev_rec[par], e->rec_stream));
+  e->rec_pending = true;
   if ((rc = launch_fm_tile(e, dev_iq, dev_stride, n_samples, fmt))) return rc;
   if ((rc = launch_wbfm_tile(e, dev_iq, dev_stride, n_samples, fmt))) return rc;
+  e->seq++;
   e->last_samples = (uint32_t)(bytes / 64);
   return SDR_OK;
 }
@@ -479,6 +549,10 @@ int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_str
 int sdr_get_pcm(sdr_engine *e, int16_t *pcm, uint32_t *counts) {
   if (!e) return SDR_E_ARG;
   SDR_CK(e, cudaSetDevice(e->device));
+  {
+    int rc = join_streams(e);
+    if (rc) return rc;
+  }
   if (pcm && e->last_samples)
     SDR_CK(e, cudaMemcpy2DAsync(pcm, (size_t)e->last_samples * 2, e->d_pcm, e->pcm_stride * 2,
                                 (size_t)e->last_samples * 2, e->n, cudaMemcpyDeviceToHost, e->stream));
@@ -495,8 +569,15 @@ int sdr_pcm_device(sdr_engine *e, int16_t **pcm, uint64_t *stride) {
   return SDR_OK;
 }
 
+int sdr_join(sdr_engine *e) {
+  if (!e) return SDR_E_ARG;
+  return join_streams(e);
+}
+
 int sdr_sync(sdr_engine *e) {
   if (!e) return SDR_E_ARG;
+  int rc = join_streams(e);
+  if (rc) return rc;
   SDR_CK(e, cudaStreamSynchronize(e->stream));
   return SDR_OK;
 }

@@ -14,9 +14,11 @@
 // one is in flight while the current one is computed and both the global reads
 // and the per-lane 64-byte shared reads are conflict free.
 //
-// The strictly sequential recurrences (DC-removal IIR; IirFilter.cc:161-176) run
-// in one extra warp per CTA with lane == channel, one tile behind the workers; a
-// single CTA barrier per tile round hands the 32 values per channel over.
+// The strictly sequential recurrences (IirFilter.cc:161-176) run with lane == channel:
+// for AM/SSB in a second, tiny kernel over the numerators the FIR kernel leaves in HBM/L2
+// (it overlaps the next call's FIR kernel on another stream); for WBFM, whose recurrence
+// runs at the full 256 kS/s, in one extra warp per CTA one tile behind the workers, with a
+// single CTA barrier per tile round.
 #pragma once
 #include "sdr_device.cuh"
 
@@ -92,16 +94,7 @@ struct AmSsbTile {
   static constexpr int NREG = SSB ? 10 : 8;
   // state blob: NREG words per lane, then (unused), y[n-1] of the DC-removal IIR
   static constexpr int STATE_BYTES = NREG * 128 + 16;
-  static constexpr int MAX_WORKERS = 15;
-  // shared memory per CTA for `nw` workers
-  static constexpr int IN_BYTES = 2 * TILE_BYTES;         // per worker: double-buffered input
-  // rows read or written 128 bits at a time with lane == channel: a row stride of
-  // 16 (mod 128) bytes keeps every quarter-warp on distinct banks
-  static constexpr int DEM_WORDS = 36;                    // per worker per parity: 32 values + pad
-  static constexpr int PCM_WORDS = 20;                    // per worker per parity: 32 int16 + pad
-  __host__ __device__ static constexpr int smem_bytes(int nw) {
-    return nw * IN_BYTES + 2 * nw * DEM_WORDS * 4 + 2 * nw * PCM_WORDS * 4 + 64;
-  }
+  static constexpr int WARMUP_TILES = SSB ? 2 : 1;  // see amssb_fir_kernel
 
   __device__ __forceinline__ static void load_carry(AmSsbCarry<SSB> &c, const uint32_t *blob, int lane) {
     c.a7 = blob[0 * 32 + lane]; c.b7 = blob[1 * 32 + lane];
@@ -229,117 +222,132 @@ struct AmSsbTile {
   }
 };
 
-// blockDim = 32 * (workers + 1); the last warp runs the recurrences. Both roles share one
-// round loop, so every thread of the CTA meets the same barrier instruction.
+// AM / SSB run as two kernels.
+//
+// amssb_fir_kernel: barrier-free worker warps, one per (channel, time segment). Everything up
+// to the numerator of the DC-removal filter is finite-memory, so a channel's launch can be cut
+// into `nseg` segments that run concurrently: a segment that does not start at tile 0 first
+// runs WARMUP tiles from an all-zero carry and discards their outputs, after which every
+// register the next tile reads from the carry is exact (AM: the carry of tile t is a function
+// of tile t's own lanes >= 22; SSB: the Hilbert history of lane 2 reaches five lanes into
+// the tile before, hence two tiles). Small banks (1024 channels = 7 per SM) get their
+// parallelism from nseg, large banks use nseg = 1.
+//
+// dc_block_kernel: the sequential recurrence, lane == channel, over the numerators the FIR
+// kernel left in `scratch`. The engine launches it on a second stream, so it overlaps the
+// next call's FIR kernel.
 template <bool SSB>
-__global__ void __launch_bounds__(512, 1) amssb_tile_kernel(const __grid_constant__ LaunchParams p) {
+__global__ void __launch_bounds__(128, 4) amssb_fir_kernel(const __grid_constant__ LaunchParams p) {
   using T = AmSsbTile<SSB>;
+  constexpr uint32_t WARMUP = SSB ? 2 : 1;
   extern __shared__ uint4 smem_raw[];
-  char *smem = reinterpret_cast<char *>(smem_raw);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nw = (int)(blockDim.x >> 5) - 1;  // workers in this CTA
-  uint32_t *dem = reinterpret_cast<uint32_t *>(smem + nw * T::IN_BYTES);
-  uint32_t *pcm_s = dem + 2 * nw * T::DEM_WORDS;  // [2 parities][nw][PCM_WORDS]
-
-  const uint32_t list0 = blockIdx.x * (uint32_t)nw;
-  const int n_here = (int)min((uint32_t)nw, p.n_list - list0);  // channels this CTA owns
+  const uint32_t nseg = p.aux;
+  const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;
+  const uint32_t li = gw / nseg, seg = gw - li * nseg;
+  if (li >= p.n_list) return;
   const uint32_t n_tiles = (p.n_samples + TILE - 1) / TILE;
-  const int fmt = p.fmt;
-  const bool is_worker = warp < nw;
-  // a worker's channel is its warp index, a recurrence lane's channel its lane index
-  const int slot_id = is_worker ? warp : lane;
-  const bool active = slot_id < n_here;
-  const uint32_t ch = active ? p.chan_ids[list0 + slot_id] : 0;
-  uint32_t *blob = reinterpret_cast<uint32_t *>(p.state + (uint64_t)ch * p.state_stride);
+  const uint32_t per = (n_tiles + nseg - 1) / nseg;
+  const uint32_t t0 = seg * per, t1 = min(n_tiles, t0 + per);
+  if (t0 >= t1) return;
+  const uint32_t tw = seg == 0 ? 0 : t0 - WARMUP;  // the host guarantees per >= WARMUP
 
-  // ---- worker state ----
-  AmSsbCarry<SSB> pv;
+  char *slots = reinterpret_cast<char *>(smem_raw) + warp * 2 * TILE_BYTES;
+  const uint32_t ch = p.chan_ids[li];
   const uint8_t *src = p.iq + (uint64_t)ch * p.ch_stride;
-  int16_t *out = p.pcm + (uint64_t)ch * p.pcm_stride;
-  char *slots = smem + (is_worker ? warp : 0) * T::IN_BYTES;
-  bool lsb = false;
-  // ---- recurrence state ----
-  float y1 = 0.f, gain = 0.f;
-  bool no_patch = true;
-  const float a1 = (float)(-0.95);
+  uint32_t *blob = reinterpret_cast<uint32_t *>(p.state + (uint64_t)ch * p.state_stride);
+  AmSsbCarry<SSB> pv;
+  if (seg == 0) {
+    T::load_carry(pv, blob, lane);
+  } else {
+    pv.a7 = pv.b7 = pv.s1a0 = pv.s1a1 = pv.s1b0 = pv.s1b1 = pv.p = 0;
+    pv.dem = 0.f;
+    pv.y3a = pv.y3b = 0;
+  }
+  const bool lsb = SSB && p.lsb[ch] != 0;
+  const int fmt = p.fmt;
 
-  if (is_worker) {
-    if (active) {
-      T::load_carry(pv, blob, lane);
-      if (SSB) lsb = p.lsb[ch] != 0;
-      tile_fill(slots, src, lane, (int)min((uint32_t)TILE, p.n_samples) >> 3);
+  tile_fill(slots + (tw & 1) * TILE_BYTES, src + (uint64_t)tw * TILE_BYTES, lane,
+            (int)min((uint32_t)TILE, p.n_samples - tw * TILE) >> 3);
+  cp_async_commit();
+  for (uint32_t t = tw; t < t1; ++t) {
+    if (t + 1 < t1) {
+      const uint32_t s1 = (t + 1) * TILE;
+      tile_fill(slots + ((t + 1) & 1) * TILE_BYTES, src + (uint64_t)s1 * 2, lane,
+                (int)min((uint32_t)TILE, p.n_samples - s1) >> 3);
     }
     cp_async_commit();
-  } else {
-    if (active) {
-      y1 = u2f(blob[T::NREG * 32 + 1]);
-      gain = p.scale[ch];
-    }
-    // |y| <= max(|y[-1]|, 20 |d|max) and |d| <= 2^17: with |gain| < 500 and |y[-1]| < 2e6 no
-    // gain * y can reach 2^31, where cvt.rzi saturates but x86 cvttss2si wraps
-    no_patch = __all_sync(FULL, !active || (fabsf(gain) < 500.f && fabsf(y1) < 2e6f));
+    cp_async_wait<1>();
+    __syncwarp();
+    uint32_t w[16];
+    tile_read(slots + (t & 1) * TILE_BYTES, lane, w);
+    __syncwarp();  // slot t&1 may be refilled (tile t+2) once every lane has read it
+    const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
+    const uint32_t d = T::tile(w, fmt, lsb, pv, lane, r);
+    if (t >= t0 && lane < r) p.scratch[((uint64_t)t * p.n_list + li) * 32 + lane] = u2f(d);
   }
+  if (t1 == n_tiles) T::store_carry(pv, blob, lane);
+}
 
-  // round k: the workers compute tile k and store the PCM of tile k-2 (64 bytes,
-  // coalesced); the recurrence warp turns tile k-1 into PCM.
-  for (uint32_t k = 0; k < n_tiles + 2; ++k) {
-    if (is_worker) {
-      if (active && k >= 2) {
-        const uint32_t t = k - 2;
-        const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
-        const int16_t *row = reinterpret_cast<const int16_t *>(pcm_s + ((t & 1) * nw + warp) * T::PCM_WORDS);
-        if (lane < r) out[(uint64_t)t * 32 + lane] = row[lane];
-      }
-      if (active && k < n_tiles) {
-        if (k + 1 < n_tiles) {
-          const uint32_t s1 = (k + 1) * TILE;
-          tile_fill(slots + ((k + 1) & 1) * TILE_BYTES, src + (uint64_t)s1 * 2, lane,
-                    (int)min((uint32_t)TILE, p.n_samples - s1) >> 3);
-        }
-        cp_async_commit();
-        cp_async_wait<1>();
-        __syncwarp();
-        uint32_t w[16];
-        tile_read(slots + (k & 1) * TILE_BYTES, lane, w);
-        const int r = (int)min((uint32_t)TILE, p.n_samples - k * TILE) >> 5;  // valid lanes
-        const uint32_t v = T::tile(w, fmt, lsb, pv, lane, r);
-        dem[((k & 1) * nw + warp) * T::DEM_WORDS + lane] = v;
-        __syncwarp();  // every lane has read slot k&1 before tile k+2 is copied into it
-      }
-    } else if (active && k >= 1 && k <= n_tiles) {
-      const uint32_t t = k - 1;
-      const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
-      // all 32 numerators first (eight 128-bit loads), then the dependent chain
-      //   y = fl(d - fl(-0.95f * y1)),  pcm = (int16_t)(gain * y)      (IirFilter.cc:161-176)
-      // runs out of registers: two dependent FP32 ops per step.
-      const uint32_t *in = dem + ((t & 1) * nw + lane) * T::DEM_WORDS;
-      float d[32];
+// y[n] = fl(d[n] - fl(-0.95f * y[n-1])), pcm[n] = (int16_t)(gain * y[n])
+// (IirFilter.cc:161-176 with a = {-0.95}; AmDemodulator.cc:461-467, SsbDemodulator.cc:587-594).
+// One thread per channel; the next tile's 32 numerators are loaded while the current tile's
+// dependent chain (two FP32 ops per step) runs.
+__global__ void __launch_bounds__(128) dc_block_kernel(const __grid_constant__ LaunchParams p) {
+  const uint32_t li = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = li < p.n_list;
+  const uint32_t ch = active ? p.chan_ids[li] : 0;
+  float *tail = reinterpret_cast<float *>(p.state + (uint64_t)ch * p.state_stride + p.aux);
+  float y1 = active ? tail[1] : 0.f;
+  const float gain = active ? p.scale[ch] : 0.f;
+  // |y| <= max(|y[-1]|, 20 |d|max) and |d| <= 2^17: with |gain| < 500 and |y[-1]| < 2e6 no
+  // gain * y can reach 2^31, where cvt.rzi saturates but x86 cvttss2si wraps
+  const bool no_patch = __all_sync(FULL, !active || (fabsf(gain) < 500.f && fabsf(y1) < 2e6f));
+  const float a1 = (float)(-0.95);
+  const uint32_t n_tiles = (p.n_samples + TILE - 1) / TILE;
+  if (!active) return;
+  int16_t *out = p.pcm + (uint64_t)ch * p.pcm_stride;
+  const float *in = p.scratch + (uint64_t)li * 32;
+  const uint64_t tile_stride = (uint64_t)p.n_list * 32;
+
+  u32x4 nx[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const u32x4 v = lds_u4(in + 4 * i);
-        d[4 * i] = u2f(v.x); d[4 * i + 1] = u2f(v.y); d[4 * i + 2] = u2f(v.z); d[4 * i + 3] = u2f(v.w);
-      }
-      uint32_t o[16];
+  for (int j = 0; j < 8; ++j) nx[j] = ldg_u4(in + 4 * j);
+  for (uint32_t t = 0; t < n_tiles; ++t) {
+    float d[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      d[4 * j] = u2f(nx[j].x); d[4 * j + 1] = u2f(nx[j].y); d[4 * j + 2] = u2f(nx[j].z); d[4 * j + 3] = u2f(nx[j].w);
+    }
+    if (t + 1 < n_tiles) {
+      const float *nin = in + (uint64_t)(t + 1) * tile_stride;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) nx[j] = ldg_u4(nin + 4 * j);
+    }
+    const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
+    uint32_t o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float ya = fsub(d[2 * i], fmul(a1, y1));
+      if (2 * i < r) y1 = ya;
+      const float yb = fsub(d[2 * i + 1], fmul(a1, y1));
+      if (2 * i + 1 < r) y1 = yb;
+      o[i] = no_patch ? __byte_perm((uint32_t)f2i_rz(fmul(gain, ya)), (uint32_t)f2i_rz(fmul(gain, yb)), 0x5410)
+                      : f2i16x2_wrap(fmul(gain, ya), fmul(gain, yb));
+    }
+    int16_t *row = out + (uint64_t)t * 32;
+    if (r == 32) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) stg_u4(row + 8 * j, u32x4{o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]});
+    } else {
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
-        const float ya = fsub(d[2 * i], fmul(a1, y1));
-        if (2 * i < r) y1 = ya;
-        const float yb = fsub(d[2 * i + 1], fmul(a1, y1));
-        if (2 * i + 1 < r) y1 = yb;
-        o[i] = no_patch ? __byte_perm((uint32_t)f2i_rz(fmul(gain, ya)), (uint32_t)f2i_rz(fmul(gain, yb)), 0x5410)
-                        : f2i16x2_wrap(fmul(gain, ya), fmul(gain, yb));
+        if (2 * i < r) row[2 * i] = (int16_t)(o[i] & 0xffffu);
+        if (2 * i + 1 < r) row[2 * i + 1] = (int16_t)(o[i] >> 16);
       }
-      uint32_t *row = pcm_s + ((t & 1) * nw + lane) * T::PCM_WORDS;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) sts_u4(row + 4 * i, u32x4{o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]});
     }
-    __syncthreads();
   }
-
-  if (active) {
-    if (is_worker) T::store_carry(pv, blob, lane);
-    else blob[T::NREG * 32 + 1] = f2u(y1);
-  }
+  tail[1] = y1;
 }
 
 
