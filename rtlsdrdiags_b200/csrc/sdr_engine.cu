@@ -196,7 +196,8 @@ int launch_dc_block(sdr_engine *e, int kind, uint32_t n_samples) {
   p.pcm_stride = e->pcm_stride;
   p.aux = (uint32_t)nreg * 128;  // byte offset of the IIR tail in the state blob
   p.scratch = e->d_scratch[kind][par];
-  dc_block_kernel<<<(n_list + 31) / 32, 32, 0, e->rec_stream>>>(p);
+  SDR_CK(e, cudaFuncSetAttribute(dc_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM_BYTES));
+  dc_block_kernel<<<(n_list + 31) / 32, 32 * (1 + DC_HELPERS), DC_SMEM_BYTES, e->rec_stream>>>(p);
   SDR_CK(e, cudaGetLastError());
   e->launches++;
   return SDR_OK;
