@@ -349,7 +349,13 @@ int sdr_engine_create(uint32_t n_channels, int device, uint64_t max_bytes_per_ch
   SDR_CK_CREATE(cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device));
   SDR_CK_CREATE(cudaDeviceGetAttribute(&e->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
   SDR_CK_CREATE(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
-  SDR_CK_CREATE(cudaStreamCreateWithFlags(&e->rec_stream, cudaStreamNonBlocking));
+  {
+    // the recurrence kernels are small and latency bound: highest priority, so their CTAs are
+    // placed before the next call's FIR kernel floods the SMs
+    int prio_lo = 0, prio_hi = 0;
+    SDR_CK_CREATE(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    SDR_CK_CREATE(cudaStreamCreateWithPriority(&e->rec_stream, cudaStreamNonBlocking, prio_hi));
+  }
   for (int i = 0; i < 2; ++i) {
     SDR_CK_CREATE(cudaEventCreateWithFlags(&e->ev_fir[i], cudaEventDisableTiming));
     SDR_CK_CREATE(cudaEventCreateWithFlags(&e->ev_rec[i], cudaEventDisableTiming));

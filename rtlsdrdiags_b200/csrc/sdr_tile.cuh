@@ -89,6 +89,21 @@ struct AmSsbCarry {
   int y3a, y3b;               // SSB: stage-3 outputs (delay line and Hilbert history)
 };
 
+// A filter with every tap doubled: with the rounding constant doubled too, acc' = 2 acc
+// exactly, so acc >> 15 is acc' >> 16 and an int8 result is simply byte 2 of acc' -- four
+// results pack with three PRMTs instead of four shifts and three logic ops.
+template <class F>
+struct Doubled {
+  static constexpr int N = F::N;
+  SDR_HD static constexpr int tap(int k) { return 2 * F::tap(k); }
+};
+static_assert(2 * 6419 < 32768 && 2 * 5914 < 32768, "doubled AM stage-1/2 taps must fit int16");
+// bytes 2 of four accumulators -> one word of four int8
+__device__ __forceinline__ uint32_t pack_b2x4(int a0, int a1, int a2, int a3) {
+  return __byte_perm(__byte_perm((uint32_t)a0, (uint32_t)a1, 0x7762), __byte_perm((uint32_t)a2, (uint32_t)a3, 0x7762),
+                     0x5410);
+}
+
 template <bool SSB>
 struct AmSsbTile {
   static constexpr int NREG = SSB ? 10 : 8;
@@ -133,13 +148,13 @@ struct AmSsbTile {
     for (int m = 0; m < 8; ++m) {
       const uint32_t wa[2] = {m == 0 ? am1 : a[m == 0 ? 0 : m - 1], a[m]};
       const uint32_t wb[2] = {m == 0 ? bm1 : b[m == 0 ? 0 : m - 1], b[m]};
-      ya[m] = fir_s8<taps::AM1, 7, 2>(wa) >> 15;
-      yb[m] = fir_s8<taps::AM1, 7, 2>(wb) >> 15;
+      ya[m] = fir_s8<Doubled<taps::AM1>, 7, 2>(wa, 1 << 15);  // the int8 result is byte 2
+      yb[m] = fir_s8<Doubled<taps::AM1>, 7, 2>(wb, 1 << 15);
     }
-    cu.s1a0 = pack_i8x4(ya[0], ya[1], ya[2], ya[3]);
-    cu.s1a1 = pack_i8x4(ya[4], ya[5], ya[6], ya[7]);
-    cu.s1b0 = pack_i8x4(yb[0], yb[1], yb[2], yb[3]);
-    cu.s1b1 = pack_i8x4(yb[4], yb[5], yb[6], yb[7]);
+    cu.s1a0 = pack_b2x4(ya[0], ya[1], ya[2], ya[3]);
+    cu.s1a1 = pack_b2x4(ya[4], ya[5], ya[6], ya[7]);
+    cu.s1b0 = pack_b2x4(yb[0], yb[1], yb[2], yb[3]);
+    cu.s1b1 = pack_b2x4(yb[4], yb[5], yb[6], yb[7]);
 
     // stage 2: 12 taps, 4:1
     const uint32_t pa0 = shfl_prev(cu.s1a0, pv.s1a0, 1, lane), pa1 = shfl_prev(cu.s1a1, pv.s1a1, 1, lane);
@@ -147,13 +162,13 @@ struct AmSsbTile {
     int za0, za1, zb0, zb1;
     {
       const uint32_t w0[3] = {pa0, pa1, cu.s1a0}, w1[3] = {pa1, cu.s1a0, cu.s1a1};
-      za0 = fir_s8<taps::AM2, 11, 3>(w0) >> 15;
-      za1 = fir_s8<taps::AM2, 11, 3>(w1) >> 15;
+      za0 = fir_s8<Doubled<taps::AM2>, 11, 3>(w0, 1 << 15);
+      za1 = fir_s8<Doubled<taps::AM2>, 11, 3>(w1, 1 << 15);
       const uint32_t v0[3] = {pb0, pb1, cu.s1b0}, v1[3] = {pb1, cu.s1b0, cu.s1b1};
-      zb0 = fir_s8<taps::AM2, 11, 3>(v0) >> 15;
-      zb1 = fir_s8<taps::AM2, 11, 3>(v1) >> 15;
+      zb0 = fir_s8<Doubled<taps::AM2>, 11, 3>(v0, 1 << 15);
+      zb1 = fir_s8<Doubled<taps::AM2>, 11, 3>(v1, 1 << 15);
     }
-    cu.p = pack_i8x4(za0, za1, zb0, zb1);
+    cu.p = pack_b2x4(za0, za1, zb0, zb1);
 
     // stage 3: 16 taps, 2:1. Window word i holds stage-2 samples at positions 2i, 2i+1
     // (I in bytes 0-1, Q in bytes 2-3); position pos meets tap 15 - pos.
@@ -267,15 +282,17 @@ __global__ void __launch_bounds__(128, 4) amssb_fir_kernel(const __grid_constant
   const bool lsb = SSB && p.lsb[ch] != 0;
   const int fmt = p.fmt;
 
-  tile_fill(slots + (tw & 1) * TILE_BYTES, src + (uint64_t)tw * TILE_BYTES, lane,
-            (int)min((uint32_t)TILE, p.n_samples - tw * TILE) >> 3);
+  // running pointers: the input tile to prefetch next and the scratch row to write
+  const uint8_t *gnext = src + (uint64_t)tw * TILE_BYTES;
+  float *sp = p.scratch + ((uint64_t)t0 * p.n_list + li) * 32 + lane;
+  const uint64_t sp_step = (uint64_t)p.n_list * 32;
+  tile_fill(slots + (tw & 1) * TILE_BYTES, gnext, lane, (int)min((uint32_t)TILE, p.n_samples - tw * TILE) >> 3);
   cp_async_commit();
   for (uint32_t t = tw; t < t1; ++t) {
-    if (t + 1 < t1) {
-      const uint32_t s1 = (t + 1) * TILE;
-      tile_fill(slots + ((t + 1) & 1) * TILE_BYTES, src + (uint64_t)s1 * 2, lane,
-                (int)min((uint32_t)TILE, p.n_samples - s1) >> 3);
-    }
+    gnext += TILE_BYTES;
+    if (t + 1 < t1)
+      tile_fill(slots + ((t + 1) & 1) * TILE_BYTES, gnext, lane,
+                (int)min((uint32_t)TILE, p.n_samples - (t + 1) * TILE) >> 3);
     cp_async_commit();
     cp_async_wait<1>();
     __syncwarp();
@@ -284,7 +301,10 @@ __global__ void __launch_bounds__(128, 4) amssb_fir_kernel(const __grid_constant
     __syncwarp();  // slot t&1 may be refilled (tile t+2) once every lane has read it
     const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
     const uint32_t d = T::tile(w, fmt, lsb, pv, lane, r);
-    if (t >= t0 && lane < r) p.scratch[((uint64_t)t * p.n_list + li) * 32 + lane] = u2f(d);
+    if (t >= t0) {
+      if (lane < r) *sp = u2f(d);
+      sp += sp_step;
+    }
   }
   if (t1 == n_tiles) T::store_carry(pv, blob, lane);
 }
