@@ -252,7 +252,7 @@ struct AmSsbTile {
 // kernel left in `scratch`. The engine launches it on a second stream, so it overlaps the
 // next call's FIR kernel.
 template <bool SSB>
-__global__ void __launch_bounds__(128, 4) amssb_fir_kernel(const __grid_constant__ LaunchParams p) {
+__global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant__ LaunchParams p) {
   using T = AmSsbTile<SSB>;
   constexpr uint32_t WARMUP = SSB ? 2 : 1;
   extern __shared__ uint4 smem_raw[];
