@@ -76,6 +76,9 @@ def oracle():
     L.sdro_chain_accept_u8.argtypes = [_vp, _pu8, _u32, _pi16, _u32]
     L.sdro_chain_accept_s8.restype = _u32
     L.sdro_chain_accept_s8.argtypes = [_vp, _i32, _pi8, _u32, _pi16, _u32]
+    L.sdro_chain_set_threshold.argtypes = [_vp, C.c_int32]
+    L.sdro_chain_set_rx_gain.argtypes = [_vp, _u32]
+    L.sdro_chain_signal.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
     L.sdro_q15_taps.restype = _i32
     L.sdro_q15_taps.argtypes = [_i32, _pi16]
     L.sdro_atan2f.restype = _f32
@@ -131,6 +134,9 @@ def ref(tree="radiodiags"):
         L.ref_iqp_reset.argtypes = [_vp, _i32]
         L.ref_iqp_accept.restype = _u32
         L.ref_iqp_accept.argtypes = [_vp, _pu8, _u32, _pi16, _u32]
+        L.ref_iqp_set_threshold.argtypes = [_vp, C.c_int32]
+        L.ref_set_rx_gain.argtypes = [C.c_int32]
+        L.ref_iqp_signal.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
         L.ref_bank_run.restype = C.c_double
         L.ref_bank_run.argtypes = [_pu8, _u32, _pu8, C.c_uint64, _u32, _pi16, _u32]
     _refs[tree] = L
@@ -158,6 +164,17 @@ class OracleChain:
 
     def reset(self, kind):
         self.L.sdro_chain_reset(self.h, kind)
+
+    def set_threshold(self, dbfs):
+        self.L.sdro_chain_set_threshold(self.h, int(dbfs))
+
+    def set_rx_gain(self, gain_db):
+        self.L.sdro_chain_set_rx_gain(self.h, int(gain_db))
+
+    def signal(self):
+        a, m = C.c_int(), C.c_uint32()
+        self.L.sdro_chain_signal(self.h, C.byref(a), C.byref(m))
+        return bool(a.value), int(m.value)
 
     def accept_u8(self, iq):
         buf = np.array(iq, dtype=np.uint8, copy=True)
@@ -194,6 +211,18 @@ class RefChain:
 
     def reset(self, kind):
         self.L.ref_iqp_reset(self.h, kind)
+
+    def set_threshold(self, dbfs):
+        self.L.ref_iqp_set_threshold(self.h, int(dbfs))
+
+    def set_rx_gain(self, gain_db):
+        """Process-wide in the reference: affects every RefChain."""
+        self.L.ref_set_rx_gain(int(gain_db))
+
+    def signal(self):
+        a, m = C.c_int(), C.c_uint32()
+        self.L.ref_iqp_signal(self.h, C.byref(a), C.byref(m))
+        return bool(a.value), int(m.value)
 
     def accept_u8(self, iq, block=32768):
         buf = np.array(iq, dtype=np.uint8, copy=True)

@@ -189,7 +189,11 @@ struct Chain {
   FmDemodulator *fm;
   WbFmDemodulator *wbfm;
   SsbDemodulator *ssb;
+  int signal_present;        // last value the signal-state callback delivered
+  uint32_t signal_magnitude; // last value the signal-magnitude callback delivered
 };
+void onSignalState(bool signalPresent, void *contextPtr) { ((Chain *)contextPtr)->signal_present = signalPresent; }
+void onSignalMagnitude(uint32_t magnitude, void *contextPtr) { ((Chain *)contextPtr)->signal_magnitude = magnitude; }
 Chain *chainNew() {
   // Mirrors the wiring in radioDiags/src_diags/Radio.cc:150-181.
   static char host[] = "127.0.0.1";
@@ -203,6 +207,12 @@ Chain *chainNew() {
   c->iqp->setFmDemodulator(c->fm);
   c->iqp->setWbFmDemodulator(c->wbfm);
   c->iqp->setSsbDemodulator(c->ssb);
+  c->signal_present = -1;
+  c->signal_magnitude = 0;
+  c->iqp->registerSignalStateCallback(onSignalState, c);
+  c->iqp->enableSignalNotification();
+  c->iqp->registerSignalMagnitudeCallback(onSignalMagnitude, c);
+  c->iqp->enableSignalMagnitudeNotification();
   return c;
 }
 void chainFree(Chain *c) {
@@ -237,6 +247,13 @@ void ref_iqp_reset(void *h, int kind) {
     case KIND_WBFM: c->wbfm->resetDemodulator(); break;
     case KIND_SSB: c->ssb->resetDemodulator(); break;
   }
+}
+void ref_iqp_set_threshold(void *h, int32_t threshold) { ((Chain *)h)->iqp->setSignalDetectThreshold(threshold); }
+// the tuner gain is a process-wide global in the reference (Radio.cc owns it)
+void ref_set_rx_gain(int32_t gain_db) { radio_adjustableReceiveGainInDb = gain_db; }
+void ref_iqp_signal(void *h, int *present, uint32_t *magnitude) {
+  *present = ((Chain *)h)->signal_present;
+  *magnitude = ((Chain *)h)->signal_magnitude;
 }
 // buf is u8 offset-binary IQ and IS modified in place (IqDataProcessor.cc:735).
 uint32_t ref_iqp_accept(void *h, uint8_t *buf, uint32_t nbytes, int16_t *pcm, uint32_t cap) {

@@ -509,6 +509,56 @@ static void wbfm_accept(wbfm_t *d, int variant, int8_t *buf, uint32_t nbytes, pc
 /* ------------------------------------------------------------------ */
 /* IqDataProcessor front end + mode switch                               */
 /* ------------------------------------------------------------------ */
+/* ------------------------------------------------------------------ */
+/* Squelch: SignalDetector.cc:205-273, DbfsCalculator.cc:43-147,         */
+/* SignalTracker.cc:104-145, Squelch.cc:227-273                          */
+/* ------------------------------------------------------------------ */
+typedef struct {
+  int32_t threshold;   /* dBFS; IqDataProcessor.cc:41 starts at -200 = always open */
+  uint32_t gain_db;    /* radio_adjustableReceiveGainInDb, owned by Radio.cc */
+  int tracking;        /* SignalTracker state: 0 NoSignal, 1 Tracking */
+  uint32_t magnitude;  /* mean magnitude of the last block */
+  int allowed;         /* gate decision of the last block */
+  int32_t db_table[257];
+} squelch_t;
+
+static void squelch_init(squelch_t *q) {
+  memset(q, 0, sizeof(*q));
+  q->threshold = -200;
+  /* DbfsCalculator(7): full scale 127 -> 42 dB; table of (int32_t)(20*log10f(i)) */
+  for (int i = 1; i <= 256; i++) {
+    float db = 20 * log10f((float)i);
+    q->db_table[i] = (int32_t)db;
+  }
+  q->db_table[0] = q->db_table[1];
+}
+
+/* buf: signed (already offset-corrected) IQ. Returns signalAllowed. */
+static int squelch_run(squelch_t *q, const int8_t *buf, uint32_t nbytes) {
+  uint32_t sum = 0, n = nbytes / 2;
+  for (uint32_t i = 0; i < nbytes; i += 2) {
+    uint8_t im = (uint8_t)abs((int)buf[i]), qm = (uint8_t)abs((int)buf[i + 1]);
+    uint8_t m = (im > qm) ? (uint8_t)(im + (qm >> 1)) : (uint8_t)(qm + (im >> 1));
+    sum += m;
+  }
+  uint32_t mag = n ? sum / n : 0;
+  q->magnitude = mag;
+  uint32_t idx = mag > 127u ? 127u : mag; /* clip to full scale; <= 256 so no halving loop */
+  int32_t db = q->db_table[idx] + 0 - (int32_t)42u;
+  db -= q->gain_db;
+  int present = db >= q->threshold;
+  int allowed;
+  if (!q->tracking) { /* NoSignal */
+    allowed = present;   /* START_OF_SIGNAL -> allowed, NOISE -> not */
+    q->tracking = present;
+  } else {              /* Tracking: SIGNAL_PRESENT or END_OF_SIGNAL (squelch tail) */
+    allowed = 1;
+    q->tracking = present;
+  }
+  q->allowed = allowed;
+  return allowed;
+}
+
 struct sdro_chain {
   int variant;
   int mode;
@@ -516,6 +566,7 @@ struct sdro_chain {
   fm_t fm;
   wbfm_t wbfm;
   ssb_t ssb;
+  squelch_t sq;
 };
 
 sdro_chain *sdro_chain_new(int variant) {
@@ -526,6 +577,7 @@ sdro_chain *sdro_chain_new(int variant) {
   fm_init(&c->fm);
   wbfm_init(&c->wbfm, variant);
   ssb_init(&c->ssb);
+  squelch_init(&c->sq);
   return c;
 }
 void sdro_chain_free(sdro_chain *c) { free(c); }
@@ -586,8 +638,20 @@ uint32_t sdro_chain_accept_u8(sdro_chain *c, uint8_t *ubuf, uint32_t nbytes, int
     x = buf[i + 4]; y = buf[i + 5]; buf[i + 4] = neg_i8(x); buf[i + 5] = neg_i8(y);
     x = buf[i + 6]; y = buf[i + 7]; buf[i + 6] = y; buf[i + 7] = neg_i8(x);
   }
-  dispatch(c, c->mode, buf, nbytes, &s);
+  /* IqDataProcessor.cc:764-765, 793: the squelch sees the converted block; a closed
+   * squelch skips the demodulator altogether (its state does not advance) */
+  if (squelch_run(&c->sq, buf, nbytes)) dispatch(c, c->mode, buf, nbytes, &s);
   return s.count;
+}
+
+/* IqDataProcessor::setSignalDetectThreshold (IqDataProcessor.cc:284-295) */
+void sdro_chain_set_threshold(sdro_chain *c, int32_t threshold) { c->sq.threshold = threshold; }
+/* radio_adjustableReceiveGainInDb (IqDataProcessor.cc:8, 765) */
+void sdro_chain_set_rx_gain(sdro_chain *c, uint32_t gain_db) { c->sq.gain_db = gain_db; }
+/* what the signal-state and signal-magnitude callbacks deliver (IqDataProcessor.cc:771-790) */
+void sdro_chain_signal(const sdro_chain *c, int *allowed, uint32_t *magnitude) {
+  if (allowed) *allowed = c->sq.allowed;
+  if (magnitude) *magnitude = c->sq.magnitude;
 }
 
 uint32_t sdro_chain_accept_s8(sdro_chain *c, int mode, int8_t *buf, uint32_t nbytes, int16_t *pcm,

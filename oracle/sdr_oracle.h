@@ -66,6 +66,12 @@ uint32_t sdro_chain_accept_u8(sdro_chain *c, uint8_t *buf, uint32_t nbytes,
 uint32_t sdro_chain_accept_s8(sdro_chain *c, int mode, int8_t *buf, uint32_t nbytes,
                               int16_t *pcm, uint32_t cap);
 
+/* squelch: threshold in dBFS (default -200 = always open), tuner gain in dB, and the
+ * state / mean magnitude the reference hands to its signal callbacks after a block */
+void sdro_chain_set_threshold(sdro_chain *c, int32_t threshold);
+void sdro_chain_set_rx_gain(sdro_chain *c, uint32_t gain_db);
+void sdro_chain_signal(const sdro_chain *c, int *allowed, uint32_t *magnitude);
+
 /* quantised taps of every Q15 filter on the path, for table cross-checks.
  * id: 0 am1 1 am2 2 am3 3 fm_tuner 4 fm_post 5 audio40 6 wb_pre 7 wb_dec1
  *     8 ssb_delay 9 ssb_hilbert. Returns the tap count. */
