@@ -23,6 +23,11 @@
  *   XDemodulator::acceptIqData(int8_t*, n)                 sdr_accept_iq(.., SDR_IQ_S8_ROTATED)
  *     (e.g. FmDemodulator.cc:334-352)
  *   pcmCallbackPtr(int16_t*, n)  (radioApp.cc:103-111)     sdr_get_pcm / sdr_pcm_device
+ *   IqDataProcessor::setSignalDetectThreshold              sdr_set_squelch_threshold
+ *     (src_diags/IqDataProcessor.cc:284-295)
+ *   radio_adjustableReceiveGainInDb (IqDataProcessor.cc:8) sdr_set_receive_gain_db
+ *   signal-state / signal-magnitude callbacks              sdr_enable_signal_reports,
+ *     (src_diags/IqDataProcessor.cc:771-790)                sdr_get_signal
  *
  * All functions return 0 on success or a negative SDR_E_* code; none throws.
  * Calls on one engine must be serialised by the caller (the reference calls
@@ -82,6 +87,21 @@ int sdr_set_modes(sdr_engine *e, const uint8_t *modes /* [n_channels] */);
 int sdr_set_gain(sdr_engine *e, uint32_t channel, int kind, float gain);
 int sdr_set_gain_all(sdr_engine *e, int kind, float gain);
 int sdr_reset(sdr_engine *e, uint32_t channel, int kind);
+
+/* Squelch (IqDataProcessor's Squelch object, Squelch.cc:227-273). A channel's block is
+ * demodulated only if its mean magnitude, in dBFS minus the tuner gain, reaches the
+ * threshold, or did so on the previous block (one-block tail); a squelched channel
+ * produces no PCM (counts[ch] = 0) and its demodulator state does not advance. The
+ * default threshold of -200 dBFS never closes (IqDataProcessor.cc:41). The decision is
+ * per sdr_accept_iq call, as the reference's is per acceptIqData call. */
+int sdr_set_squelch_threshold(sdr_engine *e, uint32_t channel, int32_t threshold_dbfs);
+int sdr_set_receive_gain_db(sdr_engine *e, uint32_t channel, uint32_t gain_db);
+/* Compute the signal state and mean magnitude of every call even while no threshold can
+ * close (what enableSignalNotification / enableSignalMagnitudeNotification ask for). */
+int sdr_enable_signal_reports(sdr_engine *e, int on);
+/* Gate and mean magnitude of the last call, [n_channels] each; either may be NULL.
+ * Synchronises. Fails with SDR_E_ARG if the last call did not run the squelch. */
+int sdr_get_signal(sdr_engine *e, uint8_t *allowed, uint32_t *magnitude);
 
 /* One block for every channel: iq is [n_channels][channel_stride] bytes of
  * interleaved I,Q of which the first bytes_per_channel are consumed.

@@ -24,7 +24,8 @@ BLOCK_BYTES = 32768  # the reference's IQ block: 16384 complex samples = 64 ms -
 ABI_SYMBOLS = ["sdr_engine_create", "sdr_engine_destroy", "sdr_set_stream", "sdr_set_scaling",
                "sdr_set_mode", "sdr_set_modes", "sdr_set_gain", "sdr_set_gain_all", "sdr_reset",
                "sdr_accept_iq", "sdr_get_pcm", "sdr_pcm_device", "sdr_sync", "sdr_join", "sdr_set_launch_shape",
-               "sdr_launch_count", "sdr_state_bytes", "sdr_last_error", "sdr_version"]
+               "sdr_launch_count", "sdr_state_bytes", "sdr_last_error", "sdr_version", "sdr_set_squelch_threshold",
+               "sdr_set_receive_gain_db", "sdr_enable_signal_reports", "sdr_get_signal"]
 
 
 class SdrError(RuntimeError):
@@ -60,6 +61,10 @@ def load_library(build_if_missing=True):
     L.sdr_pcm_device.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
     L.sdr_sync.argtypes = [vp]
     L.sdr_join.argtypes = [vp]
+    L.sdr_set_squelch_threshold.argtypes = [vp, u32, C.c_int32]
+    L.sdr_set_receive_gain_db.argtypes = [vp, u32, u32]
+    L.sdr_enable_signal_reports.argtypes = [vp, i32]
+    L.sdr_get_signal.argtypes = [vp, vp, vp]
     L.sdr_set_launch_shape.argtypes = [vp, i32, u32, u32]
     L.sdr_launch_count.argtypes = [vp]
     L.sdr_launch_count.restype = u64
@@ -122,6 +127,22 @@ class Engine:
 
     def reset(self, channel, kind):
         self._ck(self.L.sdr_reset(self.h, channel, kind))
+
+    def set_squelch_threshold(self, channel, dbfs):
+        self._ck(self.L.sdr_set_squelch_threshold(self.h, channel, int(dbfs)))
+
+    def set_receive_gain_db(self, channel, gain_db):
+        self._ck(self.L.sdr_set_receive_gain_db(self.h, channel, int(gain_db)))
+
+    def enable_signal_reports(self, on=True):
+        self._ck(self.L.sdr_enable_signal_reports(self.h, int(bool(on))))
+
+    def get_signal(self):
+        """(allowed [n] bool, magnitude [n] uint32) of the last accept. Synchronises."""
+        a = np.empty(self.n, dtype=np.uint8)
+        m = np.empty(self.n, dtype=np.uint32)
+        self._ck(self.L.sdr_get_signal(self.h, a.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p)))
+        return a.astype(bool), m
 
     def set_launch_shape(self, kind, channels_per_cta=0, threads=0):
         self._ck(self.L.sdr_set_launch_shape(self.h, kind, channels_per_cta, threads))

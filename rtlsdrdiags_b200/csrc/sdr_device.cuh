@@ -46,6 +46,7 @@ struct LaunchParams {
   uint32_t aux;              // kernel-specific word (WBFM: scheduler sharing; AM/SSB: time segments)
   float *scratch;            // AM/SSB: IIR numerators between the FIR and the recurrence kernel,
                              // [tile][list index][32 lanes]
+  const uint8_t *allowed;    // [n_channels] squelch gate of this call, or nullptr = all open
 };
 
 // ---------------------------------------------------------------------------

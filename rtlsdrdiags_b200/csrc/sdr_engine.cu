@@ -63,6 +63,16 @@ struct sdr_engine {
   int16_t *d_pcm = nullptr;
   uint64_t pcm_stride = 0;
 
+  // squelch (IqDataProcessor's Squelch object, one per channel)
+  std::vector<int32_t> threshold;   // dBFS, -200 = the reference's always-open default
+  std::vector<uint32_t> rx_gain_db; // radio_adjustableReceiveGainInDb per radio
+  bool squelch_dirty = false, squelch_armed = false, signal_reports = false;
+  int32_t *d_threshold = nullptr;
+  uint32_t *d_rx_gain = nullptr, *d_magnitude = nullptr;
+  uint8_t *d_tracking = nullptr, *d_allowed[2] = {};
+  int32_t *d_db_table = nullptr;
+  bool last_gated = false;  // the last accept ran the squelch kernel with the gate in force
+
   Shape shape[5];
   uint32_t last_samples = 0;  // PCM samples per channel of the last accept
   uint64_t launches = 0;
@@ -173,6 +183,7 @@ int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride,
   p.lut = nullptr;
   p.aux = nseg;
   p.scratch = e->d_scratch[kind][par];
+  p.allowed = e->last_gated ? e->d_allowed[par] : nullptr;
   const uint64_t warps = (uint64_t)n_list * nseg;
   amssb_fir_kernel<SSB><<<(uint32_t)((warps + 3) / 4), 128, 4 * 2 * TILE_BYTES, e->stream>>>(p);
   SDR_CK(e, cudaGetLastError());
@@ -196,6 +207,7 @@ int launch_dc_block(sdr_engine *e, int kind, uint32_t n_samples) {
   p.pcm_stride = e->pcm_stride;
   p.aux = (uint32_t)nreg * 128;  // byte offset of the IIR tail in the state blob
   p.scratch = e->d_scratch[kind][par];
+  p.allowed = e->last_gated ? e->d_allowed[par] : nullptr;
   SDR_CK(e, cudaFuncSetAttribute(dc_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM_BYTES));
   dc_block_kernel<<<(n_list + 31) / 32, 32 * (1 + DC_HELPERS), DC_SMEM_BYTES, e->rec_stream>>>(p);
   SDR_CK(e, cudaGetLastError());
@@ -227,6 +239,7 @@ int launch_fm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_
   p.lut = e->d_lut_fm;
   p.aux = 0;
   p.scratch = nullptr;
+  p.allowed = e->last_gated ? e->d_allowed[e->seq & 1] : nullptr;
   const uint32_t grid = (n_list + G - 1) / G;
   fm_tile_kernel<<<grid, 32 * G, smem, e->stream>>>(p);
   SDR_CK(e, cudaGetLastError());
@@ -267,11 +280,69 @@ int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint3
   static const int s3_env = getenv("SDR_WB_S3") ? atoi(getenv("SDR_WB_S3")) : 4;
   p.aux = (uint32_t)s3_env;
   p.scratch = nullptr;
+  p.allowed = e->last_gated ? e->d_allowed[e->seq & 1] : nullptr;
   SDR_CK(e, cudaFuncSetAttribute(wbfm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const uint32_t grid = (n_list + G - 1) / G;
   wbfm_tile_kernel<<<grid, 32 * T::warps_for((int)G, s3_env), smem, e->stream>>>(p);
   SDR_CK(e, cudaGetLastError());
   e->launches++;
+  return SDR_OK;
+}
+
+// Runs the squelch kernel when a threshold that can close is set (the gate is then in force)
+// or when signal reports are wanted. A channel whose threshold can never close
+// (threshold <= -42 - gain: even magnitude 0 passes, DbfsCalculator.cc) needs no kernel.
+int run_squelch(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint64_t bytes, int fmt) {
+  e->last_gated = false;
+  if (e->squelch_dirty) {
+    bool armed = e->squelch_armed;
+    for (uint32_t ch = 0; ch < e->n && !armed; ++ch)
+      armed = (int64_t)e->threshold[ch] > -42 - (int64_t)e->rx_gain_db[ch];
+    if ((armed || e->signal_reports) && !e->d_tracking) {
+      SDR_CK(e, cudaMalloc(&e->d_threshold, (size_t)e->n * 4));
+      SDR_CK(e, cudaMalloc(&e->d_rx_gain, (size_t)e->n * 4));
+      SDR_CK(e, cudaMalloc(&e->d_magnitude, (size_t)e->n * 4));
+      SDR_CK(e, cudaMalloc(&e->d_tracking, e->n));
+      SDR_CK(e, cudaMalloc(&e->d_allowed[0], e->n));
+      SDR_CK(e, cudaMalloc(&e->d_allowed[1], e->n));
+      SDR_CK(e, cudaMalloc(&e->d_db_table, 128 * 4));
+      // until now every block of every channel passed: the trackers are in `Tracking`
+      // (SignalTracker.cc:104-145) if any block was seen, else in `NoSignal`
+      SDR_CK(e, cudaMemsetAsync(e->d_tracking, e->seq > 0 ? 1 : 0, e->n, e->stream));
+      SDR_CK(e, cudaMemsetAsync(e->d_magnitude, 0, (size_t)e->n * 4, e->stream));
+      int32_t table[128];
+      for (int i = 1; i < 128; ++i) {  // DbfsCalculator.cc:60-68, host libm like the reference
+        float db = 20 * log10f((float)i);
+        table[i] = (int32_t)db;
+      }
+      table[0] = table[1];
+      SDR_CK(e, cudaMemcpyAsync(e->d_db_table, table, sizeof table, cudaMemcpyHostToDevice, e->stream));
+    }
+    if (e->d_tracking) {
+      int rc = join_streams(e);  // a recurrence kernel may still be reading its gate
+      if (rc) return rc;
+      SDR_CK(e, cudaMemcpyAsync(e->d_threshold, e->threshold.data(), (size_t)e->n * 4, cudaMemcpyHostToDevice, e->stream));
+      SDR_CK(e, cudaMemcpyAsync(e->d_rx_gain, e->rx_gain_db.data(), (size_t)e->n * 4, cudaMemcpyHostToDevice, e->stream));
+    }
+    e->squelch_armed = armed;
+    e->squelch_dirty = false;
+  }
+  if (!e->squelch_armed && !e->signal_reports) return SDR_OK;
+  SquelchParams q;
+  q.iq = iq;
+  q.ch_stride = ch_stride;
+  q.n_bytes = bytes;
+  q.fmt = fmt;
+  q.threshold = e->d_threshold;
+  q.gain_db = e->d_rx_gain;
+  q.tracking = e->d_tracking;
+  q.allowed = e->d_allowed[e->seq & 1];
+  q.magnitude = e->d_magnitude;
+  q.db_table = e->d_db_table;
+  squelch_kernel<<<e->n, 128, 0, e->stream>>>(q);
+  SDR_CK(e, cudaGetLastError());
+  e->launches++;
+  e->last_gated = true;
   return SDR_OK;
 }
 
@@ -362,6 +433,8 @@ int sdr_engine_create(uint32_t n_channels, int device, uint64_t max_bytes_per_ch
   }
   e->stream = e->own_stream;
 
+  e->threshold.assign(n_channels, -200);      // IqDataProcessor.cc:41
+  e->rx_gain_db.assign(n_channels, 0);
   e->mode.assign(n_channels, SDR_MODE_NONE);  // IqDataProcessor.cc:38
   e->lsb.assign(n_channels, 1);               // SsbDemodulator.cc:143
   for (int k = 1; k <= 4; ++k) {
@@ -422,6 +495,13 @@ int sdr_engine_destroy(sdr_engine *e) {
     cudaFree(e->d_scale[k]);
     cudaFree(e->d_list[k]);
   }
+  cudaFree(e->d_threshold);
+  cudaFree(e->d_rx_gain);
+  cudaFree(e->d_magnitude);
+  cudaFree(e->d_tracking);
+  cudaFree(e->d_allowed[0]);
+  cudaFree(e->d_allowed[1]);
+  cudaFree(e->d_db_table);
   cudaFree(e->d_lsb);
   cudaFree(e->d_lut_fm);
   cudaFree(e->d_lut_wbfm);
@@ -533,8 +613,11 @@ int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_str
   const uint32_t n_samples = (uint32_t)(bytes / 2);
   const bool have_rec = !e->list[SDR_KIND_AM].empty() || !e->list[SDR_KIND_SSB].empty();
   const int par = (int)(e->seq & 1);
-  // scratch[par] was last read by the recurrence kernels of the call before the previous one
-  if (have_rec) SDR_CK(e, cudaStreamWaitEvent(e->stream, e->ev_rec[par], 0));
+  // scratch[par] and allowed[par] were last read by the recurrence kernels of the call
+  // before the previous one
+  if (have_rec || e->squelch_armed || e->signal_reports || e->squelch_dirty)
+    SDR_CK(e, cudaStreamWaitEvent(e->stream, e->ev_rec[par], 0));
+  if ((rc = run_squelch(e, dev_iq, dev_stride, bytes, fmt))) return rc;
   if ((rc = launch_amssb<false>(e, SDR_KIND_AM, dev_iq, dev_stride, n_samples, fmt))) return rc;
   if ((rc = launch_amssb<true>(e, SDR_KIND_SSB, dev_iq, dev_stride, n_samples, fmt))) return rc;
   if (have_rec) {
@@ -563,9 +646,15 @@ int sdr_get_pcm(sdr_engine *e, int16_t *pcm, uint32_t *counts) {
   if (pcm && e->last_samples)
     SDR_CK(e, cudaMemcpy2DAsync(pcm, (size_t)e->last_samples * 2, e->d_pcm, e->pcm_stride * 2,
                                 (size_t)e->last_samples * 2, e->n, cudaMemcpyDeviceToHost, e->stream));
+  std::vector<uint8_t> gate;
+  if (counts && e->last_gated && e->seq > 0) {
+    gate.resize(e->n);
+    SDR_CK(e, cudaMemcpyAsync(gate.data(), e->d_allowed[(e->seq + 1) & 1], e->n, cudaMemcpyDeviceToHost, e->stream));
+  }
   SDR_CK(e, cudaStreamSynchronize(e->stream));
   if (counts)
-    for (uint32_t ch = 0; ch < e->n; ++ch) counts[ch] = e->mode[ch] == SDR_MODE_NONE ? 0 : e->last_samples;
+    for (uint32_t ch = 0; ch < e->n; ++ch)
+      counts[ch] = (e->mode[ch] == SDR_MODE_NONE || (!gate.empty() && !gate[ch])) ? 0 : e->last_samples;
   return SDR_OK;
 }
 
@@ -573,6 +662,39 @@ int sdr_pcm_device(sdr_engine *e, int16_t **pcm, uint64_t *stride) {
   if (!e) return SDR_E_ARG;
   if (pcm) *pcm = e->d_pcm;
   if (stride) *stride = e->pcm_stride;
+  return SDR_OK;
+}
+
+int sdr_set_squelch_threshold(sdr_engine *e, uint32_t ch, int32_t threshold_dbfs) {
+  if (!e || ch >= e->n) return SDR_E_ARG;
+  e->threshold[ch] = threshold_dbfs;
+  e->squelch_dirty = true;
+  return SDR_OK;
+}
+
+int sdr_set_receive_gain_db(sdr_engine *e, uint32_t ch, uint32_t gain_db) {
+  if (!e || ch >= e->n) return SDR_E_ARG;
+  e->rx_gain_db[ch] = gain_db;
+  e->squelch_dirty = true;
+  return SDR_OK;
+}
+
+int sdr_enable_signal_reports(sdr_engine *e, int on) {
+  if (!e) return SDR_E_ARG;
+  e->signal_reports = on != 0;
+  e->squelch_dirty = true;
+  return SDR_OK;
+}
+
+int sdr_get_signal(sdr_engine *e, uint8_t *allowed, uint32_t *magnitude) {
+  if (!e) return SDR_E_ARG;
+  if (!e->last_gated || e->seq == 0) return fail(e, SDR_E_ARG, "no squelch result: set a threshold or enable signal reports first");
+  SDR_CK(e, cudaSetDevice(e->device));
+  if (allowed)
+    SDR_CK(e, cudaMemcpyAsync(allowed, e->d_allowed[(e->seq + 1) & 1], e->n, cudaMemcpyDeviceToHost, e->stream));
+  if (magnitude)
+    SDR_CK(e, cudaMemcpyAsync(magnitude, e->d_magnitude, (size_t)e->n * 4, cudaMemcpyDeviceToHost, e->stream));
+  SDR_CK(e, cudaStreamSynchronize(e->stream));
   return SDR_OK;
 }
 

@@ -269,6 +269,7 @@ __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant
 
   char *slots = reinterpret_cast<char *>(smem_raw) + warp * 2 * TILE_BYTES;
   const uint32_t ch = p.chan_ids[li];
+  if (p.allowed && !p.allowed[ch]) return;  // squelched: the demodulator is not called, its state stays
   const uint8_t *src = p.iq + (uint64_t)ch * p.ch_stride;
   uint32_t *blob = reinterpret_cast<uint32_t *>(p.state + (uint64_t)ch * p.state_stride);
   AmSsbCarry<SSB> pv;
@@ -341,20 +342,21 @@ __global__ void __launch_bounds__(32 * (1 + DC_HELPERS)) dc_block_kernel(const _
   const float a1 = (float)(-0.95);
 
   // chain-warp state
-  const bool active = warp == 0 && lane < rows;
   const uint32_t ch = lane < rows ? p.chan_ids[li0 + lane] : 0;
+  const bool open = lane < rows && !(p.allowed && !p.allowed[ch]);  // not squelched
+  const bool active = warp == 0 && open;
   float *tail = reinterpret_cast<float *>(p.state + (uint64_t)ch * p.state_stride + p.aux);
   float y1 = active ? tail[1] : 0.f;
   if (warp == 0) {
     gains[lane] = lane < rows ? p.scale[ch] : 0.f;
-    rowp[lane] = p.pcm + (uint64_t)ch * p.pcm_stride;
+    rowp[lane] = open ? p.pcm + (uint64_t)ch * p.pcm_stride : nullptr;
   }
   // |y| <= max(|y[-1]|, 20 |d|max) and |d| <= 2^17: with |gain| < 500 and |y[-1]| < 2e6 no
   // gain * y can reach 2^31, where cvt.rzi saturates but x86 cvttss2si wraps. Decided once
   // per CTA by the chain warp, read by the helpers after the first barrier.
   __shared__ int s_no_patch;
   if (warp == 0) {
-    const bool ok = __all_sync(FULL, !(lane < rows) || (fabsf(gains[lane]) < 500.f && fabsf(y1) < 2e6f));
+    const bool ok = __all_sync(FULL, !open || (fabsf(gains[lane]) < 500.f && fabsf(y1) < 2e6f));
     if (lane == 0) s_no_patch = ok;
   }
 
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(32 * (1 + DC_HELPERS)) dc_block_kernel(const _
   // t-1 and make sure tile t+1 has landed
   for (uint32_t t = 0; t <= n_tiles; ++t) {
     if (warp == 0) {
-      if (t < n_tiles && lane < rows) {
+      if (t < n_tiles && open) {
         const char *my = ring + (t % DC_STAGES) * DC_STAGE_BYTES + lane * DC_ROW_BYTES;
         char *yo = ybuf + (t & 1) * DC_STAGE_BYTES + lane * DC_ROW_BYTES;
         const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
@@ -439,7 +441,7 @@ __global__ void __launch_bounds__(32 * (1 + DC_HELPERS)) dc_block_kernel(const _
           const int row = warp - 1 + DC_HELPERS * k;
           const float v = fmul(g[k], yv[k]);
           const int o = no_patch ? f2i_rz(v) : f2i16_wrap(v);
-          if (row < rows && lane < r) dst[k][col] = (int16_t)o;
+          if (row < rows && lane < r && dst[k] != nullptr) dst[k][col] = (int16_t)o;
         }
       }
       cp_async_wait<DC_STAGES - 2>();  // tile t+1 has landed before the chain warp asks for it
@@ -602,6 +604,7 @@ __global__ void __launch_bounds__(128, 4) fm_tile_kernel(const __grid_constant__
   if (li >= p.n_list) return;
   char *slots = reinterpret_cast<char *>(smem_raw) + warp * 2 * TILE_BYTES;
   const uint32_t ch = p.chan_ids[li];
+  if (p.allowed && !p.allowed[ch]) return;  // squelched
   const uint8_t *src = p.iq + (uint64_t)ch * p.ch_stride;
   uint32_t *blob = reinterpret_cast<uint32_t *>(p.state + (uint64_t)ch * p.state_stride);
   FmCarry pv;
@@ -880,8 +883,9 @@ __global__ void __launch_bounds__(768, 1) wbfm_tile_kernel(const __grid_constant
   char *ring_base = smem + nw * TILE_BYTES;   // after nw input slots: nw rings of RING_BYTES
 
   const int slot_id = is_iir ? lane : T::worker_index(warp, s3);  // channel slot in this CTA
-  const bool active = (is_iir || is_worker) && slot_id < n_here;
-  const uint32_t ch = active ? p.chan_ids[list0 + slot_id] : 0;
+  const bool owned = (is_iir || is_worker) && slot_id < n_here;
+  const uint32_t ch = owned ? p.chan_ids[list0 + slot_id] : 0;
+  const bool active = owned && !(p.allowed && !p.allowed[ch]);  // a squelched channel is skipped
   uint32_t *blob = reinterpret_cast<uint32_t *>(p.state + (uint64_t)ch * p.state_stride);
   char *ring = ring_base + (active ? slot_id : 0) * T::RING_BYTES;
 
@@ -981,6 +985,65 @@ __global__ void __launch_bounds__(768, 1) wbfm_tile_kernel(const __grid_constant
     } else {
       blob[T::NREG * 32] = f2u(y1);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Squelch (IqDataProcessor.cc:764-765 -> Squelch.cc:227-273): mean of the max + min/2
+// magnitude estimate over the block (SignalDetector.cc:205-273), dBFS through the 7-bit
+// table (DbfsCalculator.cc:111-147), threshold, two-state tracker with a one-block tail
+// (SignalTracker.cc:104-145). One CTA per channel; runs before the demodulation kernels
+// when a threshold that can close is set or signal reports are wanted.
+// ---------------------------------------------------------------------------
+struct SquelchParams {
+  const uint8_t *iq;
+  uint64_t ch_stride;
+  uint64_t n_bytes;
+  int fmt;
+  const int32_t *threshold;   // [n_channels] dBFS
+  const uint32_t *gain_db;    // [n_channels] tuner gain (radio_adjustableReceiveGainInDb)
+  uint8_t *tracking;          // [n_channels] SignalTracker state, carried across calls
+  uint8_t *allowed;           // [n_channels] out: gate of this call
+  uint32_t *magnitude;        // [n_channels] out: mean magnitude of this call's block
+  const int32_t *db_table;    // [128] (int32_t)(20 log10f(i)), built by the host libm
+};
+
+__global__ void __launch_bounds__(128) squelch_kernel(const SquelchParams q) {
+  const uint32_t ch = blockIdx.x;
+  const uint8_t *src = q.iq + (uint64_t)ch * q.ch_stride;
+  const uint32_t flip = q.fmt == FMT_U8_OFFSET_ROTATE ? 0x80808080u : 0u;  // the rotation does not change |.|
+  unsigned long long sum = 0;
+  for (uint64_t c = threadIdx.x; c < q.n_bytes / 16; c += blockDim.x) {
+    const u32x4 v = ld_stream_u4(src + 16 * c);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint32_t part = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t a = __vabs4(w[i] ^ flip);          // |i|, |q| as uint8; |-128| = 128
+      const uint32_t b = __byte_perm(a, 0, 0x2301);     // partner of each byte
+      const uint32_t mx = __vmaxu4(a, b), mn = __vminu4(a, b);
+      const uint32_t m = (mx & 0x00ff00ffu) + ((mn >> 1) & 0x007f007fu);  // two magnitudes <= 192
+      part += (m & 0xffffu) + (m >> 16);
+    }
+    sum += part;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+  __shared__ unsigned long long s_part[4];
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned long long total = s_part[0] + s_part[1] + s_part[2] + s_part[3];
+    const uint32_t n = (uint32_t)(q.n_bytes / 2);
+    const uint32_t mag = (uint32_t)(total / n);
+    const uint32_t idx = mag > 127u ? 127u : mag;
+    int32_t db = q.db_table[idx] - 42;
+    db -= (int32_t)q.gain_db[ch];
+    const bool present = db >= q.threshold[ch];
+    const bool tracking = q.tracking[ch] != 0;
+    q.allowed[ch] = (present || tracking) ? 1 : 0;  // START / PRESENT / END-of-signal tail
+    q.tracking[ch] = present ? 1 : 0;
+    q.magnitude[ch] = mag;
   }
 }
 
