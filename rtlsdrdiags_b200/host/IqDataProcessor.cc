@@ -1,7 +1,13 @@
 // Mode switch in front of the four drop-in demodulators.
 #include "IqDataProcessor.h"
 
+#include <stdint.h>
 #include <stdio.h>
+
+#include <vector>
+
+// Owned by the application, as in the reference (IqDataProcessor.cc:8, Radio.cc).
+extern int32_t radio_adjustableReceiveGainInDb;
 
 IqDataProcessor::IqDataProcessor(char *hostIpAddress, int hostPort)
 {
@@ -10,6 +16,17 @@ IqDataProcessor::IqDataProcessor(char *hostIpAddress, int hostPort)
 
   // Default to no demodulation of the signal (IqDataProcessor.cc:38).
   demodulatorMode = None;
+
+  // Let all signal exceed threshold (IqDataProcessor.cc:41).
+  signalDetectThreshold = -200;
+  gateEngine = NULL;
+  blocksSeen = 0;
+  signalNotificationEnabled = false;
+  signalCallbackPtr = NULL;
+  signalCallbackContextPtr = NULL;
+  signalMagnitudeNotificationEnabled = false;
+  signalMagnitudeCallbackPtr = NULL;
+  signalMagnitudeCallbackContextPtr = NULL;
   amDemodulatorPtr = NULL;
   fmDemodulatorPtr = NULL;
   wbFmDemodulatorPtr = NULL;
@@ -18,7 +35,102 @@ IqDataProcessor::IqDataProcessor(char *hostIpAddress, int hostPort)
 
 IqDataProcessor::~IqDataProcessor(void)
 {
+  if (gateEngine != NULL)
+  {
+    sdr_engine_destroy(gateEngine);
+  } // if
 } // ~IqDataProcessor
+
+void IqDataProcessor::setSignalDetectThreshold(int32_t threshold)
+{
+  signalDetectThreshold = threshold;
+} // setSignalDetectThreshold
+
+void IqDataProcessor::enableSignalNotification(void) { signalNotificationEnabled = true; }
+void IqDataProcessor::disableSignalNotification(void) { signalNotificationEnabled = false; }
+void IqDataProcessor::registerSignalStateCallback(void (*callbackPtr)(bool signalPresent, void *contextPtr),
+                                                  void *contextPtr)
+{
+  signalCallbackContextPtr = contextPtr;
+  signalCallbackPtr = callbackPtr;
+} // registerSignalStateCallback
+void IqDataProcessor::enableSignalMagnitudeNotification(void) { signalMagnitudeNotificationEnabled = true; }
+void IqDataProcessor::disableSignalMagnitudeNotification(void) { signalMagnitudeNotificationEnabled = false; }
+void IqDataProcessor::registerSignalMagnitudeCallback(void (*callbackPtr)(uint32_t signalMagnitude, void *contextPtr),
+                                                      void *contextPtr)
+{
+  signalMagnitudeCallbackContextPtr = contextPtr;
+  signalMagnitudeCallbackPtr = callbackPtr;
+} // registerSignalMagnitudeCallback
+
+// Squelch::run on the block (IqDataProcessor.cc:764-790): returns signalAllowed and fires the
+// signal-state and signal-magnitude callbacks, in the reference's order, before any
+// demodulation.
+bool IqDataProcessor::runSquelch(unsigned char *bufferPtr, unsigned long byteCount)
+{
+  const bool wanted = signalDetectThreshold != -200 || radio_adjustableReceiveGainInDb != 0 ||
+                      (signalNotificationEnabled && signalCallbackPtr != NULL) ||
+                      (signalMagnitudeNotificationEnabled && signalMagnitudeCallbackPtr != NULL);
+  if (!wanted && gateEngine == NULL)
+  {
+    blocksSeen++;
+    return (true); // the default threshold never closes and nobody listens
+  } // if
+  if ((byteCount % 64) != 0 || byteCount == 0)
+  {
+    return (true); // the engine works on whole PCM samples; such a block passes ungated
+  } // if
+  if (gateEngine == NULL)
+  {
+    if (sdr_engine_create(1, 0, 1u << 20, &gateEngine) != SDR_OK)
+    {
+      fprintf(stderr, "IqDataProcessor: cannot create the B200 engine: %s\n", sdr_last_error(NULL));
+      gateEngine = NULL;
+      return (true);
+    } // if
+    sdr_enable_signal_reports(gateEngine, 1);
+    if (blocksSeen != 0)
+    {
+      // Every block so far was above the -200 dBFS default, so the reference's tracker is
+      // in its Tracking state and grants this block the one-block tail: replay that.
+      static const uint8_t primer[64 + 16] = {0};
+      const uint8_t *p16 = (const uint8_t *)(((uintptr_t)primer + 15) & ~(uintptr_t)15);
+      sdr_accept_iq(gateEngine, p16, 64, 64, SDR_IQ_HOST | SDR_IQ_U8_OFFSET);
+      sdr_sync(gateEngine);
+    } // if
+  } // if
+  if (byteCount > (1u << 20))
+  {
+    return (true);
+  } // if
+
+  uint8_t allowed = 1;
+  uint32_t magnitude = 0;
+  sdr_set_squelch_threshold(gateEngine, 0, signalDetectThreshold);
+  sdr_set_receive_gain_db(gateEngine, 0, (uint32_t)radio_adjustableReceiveGainInDb);
+  // the block may sit at any address: stage it 16-byte aligned
+  static thread_local std::vector<uint8_t> staging;
+  staging.resize(byteCount + 16);
+  uint8_t *aligned = (uint8_t *)(((uintptr_t)staging.data() + 15) & ~(uintptr_t)15);
+  for (unsigned long i = 0; i < byteCount; i++) aligned[i] = bufferPtr[i];
+  if (sdr_accept_iq(gateEngine, aligned, byteCount, byteCount, SDR_IQ_HOST | SDR_IQ_U8_OFFSET) != SDR_OK ||
+      sdr_get_signal(gateEngine, &allowed, &magnitude) != SDR_OK)
+  {
+    fprintf(stderr, "IqDataProcessor: squelch failed: %s\n", sdr_last_error(gateEngine));
+    return (true);
+  } // if
+
+  if ((signalNotificationEnabled) && (signalCallbackPtr != NULL))
+  {
+    signalCallbackPtr(allowed != 0, signalCallbackContextPtr);
+  } // if
+  if ((signalMagnitudeNotificationEnabled) && (signalMagnitudeCallbackPtr != NULL))
+  {
+    signalMagnitudeCallbackPtr(magnitude, signalMagnitudeCallbackContextPtr);
+  } // if
+
+  return (allowed != 0);
+} // runSquelch
 
 void IqDataProcessor::setAmDemodulator(AmDemodulator *demodulatorPtr) { amDemodulatorPtr = demodulatorPtr; }
 void IqDataProcessor::setFmDemodulator(FmDemodulator *demodulatorPtr) { fmDemodulatorPtr = demodulatorPtr; }
@@ -48,6 +160,11 @@ void IqDataProcessor::acceptIqData(unsigned long timeStamp, unsigned char *buffe
   {
     fprintf(stderr, "IqDataProcessor: byteCount %lu is not a multiple of 8, block dropped\n", byteCount);
     return;
+  } // if
+
+  if (!runSquelch(bufferPtr, byteCount))
+  {
+    return; // squelched: no demodulator is called (IqDataProcessor.cc:793)
   } // if
 
   switch (demodulatorMode)

@@ -1,9 +1,10 @@
 // Drop-in for radioDiags/hdr_diags/IqDataProcessor.h, reduced to the demodulation
 // path: mode switch, demodulator registration and acceptIqData. The u8 -> s8
 // conversion and the Fs/4 rotation (IqDataProcessor.cc:735-749) run on the GPU as
-// the first phase of the demodulation kernel. Squelch, IQ dump and the signal
-// callbacks are not rebuilt; the squelch default (-200 dBFS,
-// IqDataProcessor.cc:41) is always open, which is what this class implements.
+// the first step of the demodulation kernels. The squelch gate and the signal-state /
+// signal-magnitude callbacks (IqDataProcessor.cc:764-790) run on a one-channel engine of
+// their own, because the reference keeps one Squelch per IqDataProcessor, shared by all
+// modes. The IQ dump (UdpClient) is not rebuilt.
 #ifndef _IQDATAPROCESSOR_H_
 #define _IQDATAPROCESSOR_H_
 
@@ -28,12 +29,33 @@ class IqDataProcessor
   void setWbFmDemodulator(WbFmDemodulator *demodulatorPtr);
   void setSsbDemodulator(SsbDemodulator *demodulatorPtr);
 
+  void setSignalDetectThreshold(int32_t threshold);
+
   void acceptIqData(unsigned long timeStamp, unsigned char *bufferPtr, unsigned long byteCount);
+
+  void enableSignalNotification(void);
+  void disableSignalNotification(void);
+  void registerSignalStateCallback(void (*signalCallbackPtr)(bool signalPresent, void *contextPtr), void *contextPtr);
+  void enableSignalMagnitudeNotification(void);
+  void disableSignalMagnitudeNotification(void);
+  void registerSignalMagnitudeCallback(void (*callbackPtr)(uint32_t signalMagnitude, void *contextPtr),
+                                       void *contextPtr);
 
   void displayInternalInformation(void);
 
   private:
+  bool runSquelch(unsigned char *bufferPtr, unsigned long byteCount);
+
   demodulatorType demodulatorMode;
+  int32_t signalDetectThreshold;
+  sdr_engine *gateEngine;  // mode None: runs only the squelch kernel
+  unsigned long blocksSeen; // blocks that passed while no gate engine existed yet
+  bool signalNotificationEnabled;
+  void *signalCallbackContextPtr;
+  void (*signalCallbackPtr)(bool signalPresent, void *contextPtr);
+  bool signalMagnitudeNotificationEnabled;
+  void *signalMagnitudeCallbackContextPtr;
+  void (*signalMagnitudeCallbackPtr)(uint32_t signalMagnitude, void *contextPtr);
   AmDemodulator *amDemodulatorPtr;
   FmDemodulator *fmDemodulatorPtr;
   WbFmDemodulator *wbFmDemodulatorPtr;

@@ -10,6 +10,8 @@
 //        Without -u the input is signed and already rotated (demod.cc:8-11).
 //   -r   research-tree FM/WBFM scaling (what demod.cc itself links against).
 //   -b   bytes per read (default 16384 like demod.cc:250; 32768 with -u).
+//   -s   squelch threshold in dBFS (with -u; IqDataProcessor::setSignalDetectThreshold),
+//        and print every block's signal state and magnitude to stderr.
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -17,6 +19,20 @@
 #include <unistd.h>
 
 #include "IqDataProcessor.h"
+
+int32_t radio_adjustableReceiveGainInDb = 0;  // Radio.cc owns this in the reference
+
+static void onSignalState(bool signalPresent, void *contextPtr)
+{
+  fprintf(stderr, "signal %d", signalPresent ? 1 : 0);
+  (void)contextPtr;
+} // onSignalState
+
+static void onSignalMagnitude(uint32_t signalMagnitude, void *contextPtr)
+{
+  fprintf(stderr, " magnitude %u\n", signalMagnitude);
+  (void)contextPtr;
+} // onSignalMagnitude
 
 void nprintf(FILE *s, const char *formatPtr, ...)
 {
@@ -34,11 +50,11 @@ static void processPcmData(int16_t *bufferPtr, uint32_t bufferLength)
 int main(int argc, char **argv)
 {
   int demodulatorType = 2;
-  bool rawInput = false, research = false, realLsb = false;
-  long blockBytes = 0;
+  bool rawInput = false, research = false, realLsb = false, squelch = false;
+  long blockBytes = 0, threshold = -200;
   int opt;
 
-  while ((opt = getopt(argc, argv, "d:urlb:h")) != -1)
+  while ((opt = getopt(argc, argv, "d:urlb:s:h")) != -1)
   {
     switch (opt)
     {
@@ -47,6 +63,7 @@ int main(int argc, char **argv)
       case 'r': research = true; break;
       case 'l': realLsb = true; break;
       case 'b': blockBytes = atol(optarg); break;
+      case 's': squelch = true; threshold = atol(optarg); break;
       default:
         fprintf(stderr, "./b200_demod -d [1 - AM | 2 - FM | 3 - WBFM | 4 - LSB | 5 - USB] [-u] [-r] [-l] [-b bytes]"
                         " < inputFile > outputFile\n");
@@ -79,6 +96,14 @@ int main(int argc, char **argv)
   processorPtr->setFmDemodulator(fmDemodPtr);
   processorPtr->setWbFmDemodulator(wbFmDemodPtr);
   processorPtr->setSsbDemodulator(ssbDemodPtr);
+  if (squelch)
+  {
+    processorPtr->setSignalDetectThreshold((int32_t)threshold);
+    processorPtr->registerSignalStateCallback(onSignalState, NULL);
+    processorPtr->enableSignalNotification();
+    processorPtr->registerSignalMagnitudeCallback(onSignalMagnitude, NULL);
+    processorPtr->enableSignalMagnitudeNotification();
+  } // if
 
   switch (demodulatorType)
   {

@@ -16,6 +16,14 @@ Contents (all inputs are synthetic; no reference data file is copied):
                                    set{Lsb,Usb}DemodulationMode)
   yoyo_md5_*                       md5 of the PCM of demodulatorResearch/yoyo.iq (the only
                                    capture shipped with the reference) for both trees
+
+and tests/golden/golden_squelch_v1.npz (the squelch gate, Squelch.cc:227-273):
+  blocks           [12][4096] u8   noise blocks of scheduled amplitude (one radio, FM mode)
+  cfg              [7][2] i32      (threshold dBFS, tuner gain dB) per configuration
+  allowed          [7][12] u8      what the signal-state callback was handed per block
+  magnitude        [7][12] u32     what the signal-magnitude callback was handed per block
+  counts           [7][12] u32     PCM samples that came out per block
+  pcm_<i>          i16             the concatenated PCM of configuration i
 """
 import hashlib
 import os
@@ -86,6 +94,36 @@ def main():
             print(k, out[k])
 
 
+SQUELCH_CFG = [(-200, 0), (-30, 0), (-20, 0), (-12, 3), (-6, 0), (-25, 10), (0, 0)]
+SQUELCH_AMPS = [0.5, 70.0, 1.0, 0.5, 10.0, 33.0, 0.6, 0.6, 100.0, 3.0, 127.0, 0.0]
+
+
+def squelch_golden():
+    rng = np.random.default_rng(77)
+    blocks = np.stack([np.clip(np.round(128 + a * rng.standard_normal(4096)), 0, 255).astype(np.uint8)
+                       for a in SQUELCH_AMPS])
+    out = {"blocks": blocks, "cfg": np.array(SQUELCH_CFG, dtype=np.int32)}
+    allowed = np.zeros((len(SQUELCH_CFG), len(blocks)), dtype=np.uint8)
+    magnitude = np.zeros(allowed.shape, dtype=np.uint32)
+    counts = np.zeros(allowed.shape, dtype=np.uint32)
+    for i, (thr, gain) in enumerate(SQUELCH_CFG):
+        r = O.RefChain()
+        r.set_mode(2)
+        r.set_threshold(thr)
+        r.set_rx_gain(gain)
+        pcm = []
+        for b, blk in enumerate(blocks):
+            pcm.append(r.accept_u8(blk, block=4096))
+            a, m = r.signal()
+            allowed[i, b], magnitude[i, b], counts[i, b] = a, m, pcm[-1].size
+        r.set_rx_gain(0)
+        out["pcm_%d" % i] = np.concatenate(pcm)
+    out.update(allowed=allowed, magnitude=magnitude, counts=counts)
+    path = os.path.join(HERE, "golden_squelch_v1.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def unrotate_to_u8(signed_rotated):
     """Inverse of IqDataProcessor's offset + Fs/4 rotation (values that would need +128 wrap)."""
     s = signed_rotated.astype(np.int16).reshape(-1, 4, 2)
@@ -100,4 +138,6 @@ def unrotate_to_u8(signed_rotated):
 
 
 if __name__ == "__main__":
-    main()
+    if "--squelch-only" not in sys.argv:
+        main()
+    squelch_golden()

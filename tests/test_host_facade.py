@@ -80,3 +80,30 @@ def test_driver_raw_u8_input_matches_product_path(mode, block):
     c.set_mode(mode)
     exp = np.concatenate([c.accept_u8(u8[o:o + block]) for o in range(0, u8.size, block)])
     assert np.array_equal(got, exp)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("first_quiet", [False, True])
+def test_driver_squelch_and_signal_callbacks(first_quiet):
+    """b200_demod -u -s T: IqDataProcessor::setSignalDetectThreshold plus the signal-state
+    and signal-magnitude callbacks, block by block, against the oracle."""
+    block = 32768
+    rng = np.random.default_rng(3)
+    amps = ([0.6] if first_quiet else []) + [40.0, 1.0, 0.7, 0.7, 25.0, 0.7, 0.7, 0.7, 50.0]
+    u8 = np.concatenate([np.clip(np.round(128 + a * rng.standard_normal(block)), 0, 255).astype(np.uint8)
+                         for a in amps])
+    r = subprocess.run([_demod(), "-d", "2", "-u", "-s", "-25"], input=u8.tobytes(),
+                       capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()
+    got = np.frombuffer(r.stdout, dtype=np.int16)
+    c = O.OracleChain()
+    c.set_mode(2)
+    c.set_threshold(-25)
+    exp, lines = [], []
+    for o in range(0, u8.size, block):
+        exp.append(c.accept_u8(u8[o:o + block]))
+        a, m = c.signal()
+        lines.append("signal %d magnitude %d" % (int(a), m))
+    assert [l for l in r.stderr.decode().splitlines() if l.startswith("signal")] == lines
+    assert any(e.size == 0 for e in exp) and any(e.size for e in exp)
+    assert np.array_equal(got, np.concatenate(exp))

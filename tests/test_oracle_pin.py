@@ -114,3 +114,73 @@ def test_oracle_reproduces_yoyo_md5s(mode):
     c.set_mode(mode)
     got = hashlib.md5(c.accept_u8(mg.unrotate_to_u8(yoyo)).tobytes()).hexdigest()
     assert got == str(GOLD["yoyo_md5_radiodiags_" + NAMES[mode]])
+
+
+def _amp_block(rng, amp, nbytes):
+    return np.clip(np.round(128 + amp * rng.standard_normal(nbytes)), 0, 255).astype(np.uint8)
+
+
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref not built")
+@pytest.mark.parametrize("threshold,gain", [(-200, 0), (-30, 0), (-20, 0), (-12, 3), (-6, 0), (-25, 10), (0, 0)])
+def test_squelch_oracle_matches_compiled_reference(threshold, gain):
+    """Squelch::run (Squelch.cc:227-273) through IqDataProcessor: gate, one-block tail,
+    tuner gain, the values handed to both signal callbacks, and the PCM that does or does
+    not come out -- restatement against the reference compiled in place."""
+    rng = np.random.default_rng(abs(threshold) * 7 + gain)
+    ref, orc = O.RefChain(), O.OracleChain()
+    try:
+        for c in (ref, orc):
+            c.set_mode(2)
+            c.set_threshold(threshold)
+            c.set_rx_gain(gain)
+        seen = set()
+        for step, amp in enumerate([0.5, 70.0, 1.0, 0.5, 10.0, 33.0, 0.6, 0.6, 100.0, 3.0, 127.0, 0.0]):
+            nbytes = 32768 if step % 3 else 4096
+            blk = _amp_block(rng, amp, nbytes)
+            a = ref.accept_u8(blk, block=nbytes)
+            b = orc.accept_u8(blk)
+            assert ref.signal() == orc.signal(), "step %d" % step
+            assert np.array_equal(a, b), "step %d" % step
+            seen.add(bool(a.size))
+        if threshold in (-30, -20, -12, -25):
+            assert seen == {True, False}
+    finally:
+        ref.set_rx_gain(0)
+
+
+@pytest.mark.skipif(not have_ref, reason="oracle/_ref not built")
+def test_squelch_db_table_matches_compiled_reference_over_all_magnitudes():
+    """Constant-amplitude blocks sweep the detector's magnitude over its whole range, so every
+    entry of DbfsCalculator's table (DbfsCalculator.cc:30-50) is exercised."""
+    ref, orc = O.RefChain(), O.OracleChain()
+    for c in (ref, orc):
+        c.set_mode(1)
+        c.set_threshold(-18)
+    for i in range(0, 128, 3):
+        for q in (0, i // 2, i):
+            blk = np.empty(1024, dtype=np.uint8)
+            blk[0::2] = 128 + i
+            blk[1::2] = 128 - q
+            a, b = ref.accept_u8(blk, block=1024), orc.accept_u8(blk)
+            assert ref.signal() == orc.signal(), (i, q)
+            assert np.array_equal(a, b), (i, q)
+
+
+SQ = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_squelch_v1.npz"))
+
+
+@pytest.mark.parametrize("i", range(7))
+def test_squelch_oracle_matches_golden(i):
+    """tests/golden/golden_squelch_v1.npz: what the compiled reference's squelch decided,
+    reported and let through (always runs, also where oracle/_ref is absent)."""
+    thr, gain = (int(v) for v in SQ["cfg"][i])
+    c = O.OracleChain()
+    c.set_mode(2)
+    c.set_threshold(thr)
+    c.set_rx_gain(gain)
+    pcm = []
+    for b, blk in enumerate(SQ["blocks"]):
+        pcm.append(c.accept_u8(blk))
+        assert c.signal() == (bool(SQ["allowed"][i, b]), int(SQ["magnitude"][i, b])), b
+        assert pcm[-1].size == SQ["counts"][i, b]
+    assert np.array_equal(np.concatenate(pcm), SQ["pcm_%d" % i])
