@@ -28,6 +28,10 @@
  *   radio_adjustableReceiveGainInDb (IqDataProcessor.cc:8) sdr_set_receive_gain_db
  *   signal-state / signal-magnitude callbacks              sdr_enable_signal_reports,
  *     (src_diags/IqDataProcessor.cc:771-790)                sdr_get_signal
+ *   IqDataProcessor::enableIqDump / disableIqDump          sdr_set_iq_dump
+ *     (src_diags/IqDataProcessor.cc:633-669)
+ *   networkInterfacePtr->sendData(signedBufferPtr, n)      sdr_get_iq_dump / sdr_iq_dump_device
+ *     (IqDataProcessor.cc:756-760, UdpClient.cc:173-241)
  *
  * All functions return 0 on success or a negative SDR_E_* code; none throws.
  * Calls on one engine must be serialised by the caller (the reference calls
@@ -102,6 +106,19 @@ int sdr_enable_signal_reports(sdr_engine *e, int on);
 /* Gate and mean magnitude of the last call, [n_channels] each; either may be NULL.
  * Synchronises. Fails with SDR_E_ARG if the last call did not run the squelch. */
 int sdr_get_signal(sdr_engine *e, uint8_t *allowed, uint32_t *magnitude);
+
+/* IQ dump (IqDataProcessor.cc:756-760): keep, for the channels it is enabled on, the block
+ * of each sdr_accept_iq call as the reference hands it to UdpClient::sendData -- signed,
+ * Fs/4-rotated interleaved I,Q, the .iq file / wire format (demod.cc:8-11) -- whatever the
+ * squelch decides. The reference sends it as consecutive datagrams of at most 2048 bytes
+ * (UdpClient.cc:77, 199-231); the caller slices. Enabling takes effect at the next call. */
+int sdr_set_iq_dump(sdr_engine *e, uint32_t channel, int on);
+/* The last call's dump of one channel: *n_bytes = bytes_per_channel of that call. out may be
+ * NULL to ask for the size only. Synchronises. SDR_E_ARG if the channel was not dumped. */
+int sdr_get_iq_dump(sdr_engine *e, uint32_t channel, int8_t *out, uint64_t capacity, uint64_t *n_bytes);
+/* Device-resident dump of the last call: n_rows rows, row_stride apart, in ascending channel
+ * order of the enabled channels. */
+int sdr_iq_dump_device(sdr_engine *e, int8_t **rows, uint64_t *row_stride, uint32_t *n_rows);
 
 /* One block for every channel: iq is [n_channels][channel_stride] bytes of
  * interleaved I,Q of which the first bytes_per_channel are consumed.

@@ -79,6 +79,10 @@ def oracle():
     L.sdro_chain_set_threshold.argtypes = [_vp, C.c_int32]
     L.sdro_chain_set_rx_gain.argtypes = [_vp, _u32]
     L.sdro_chain_signal.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
+    L.sdro_front_end.argtypes = [_pu8, C.c_uint32]
+    L.sdro_front_end.restype = None
+    L.sdro_dump_datagrams.argtypes = [C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32]
+    L.sdro_dump_datagrams.restype = C.c_uint32
     L.sdro_q15_taps.restype = _i32
     L.sdro_q15_taps.argtypes = [_i32, _pi16]
     L.sdro_atan2f.restype = _f32
@@ -128,6 +132,9 @@ def ref(tree="radiodiags"):
     L.ref_iir_run.argtypes = [_vp, _pf, _u32, _pf]
     if tree == "radiodiags":
         L.ref_iqp_new.restype = _vp
+        L.ref_iqp_new_port.argtypes = [C.c_int]
+        L.ref_iqp_new_port.restype = _vp
+        L.ref_iqp_set_dump.argtypes = [_vp, C.c_int]
         L.ref_iqp_free.argtypes = [_vp]
         L.ref_iqp_set_mode.argtypes = [_vp, _i32]
         L.ref_iqp_set_gain.argtypes = [_vp, _i32, _f32]
@@ -189,14 +196,32 @@ class OracleChain:
         return out[:n].copy()
 
 
+def front_end(iq_u8):
+    """Oracle: the signed, Fs/4-rotated block acceptIqData leaves in the caller's buffer."""
+    buf = np.array(iq_u8, dtype=np.uint8, copy=True)
+    oracle().sdro_front_end(_ptr(buf, _pu8), buf.size)
+    return buf.view(np.int8)
+
+
+def dump_datagrams(nbytes):
+    """Oracle: the datagram sizes UdpClient::sendData cuts nbytes into."""
+    sizes = (C.c_uint32 * (nbytes // 2048 + 2))()
+    k = oracle().sdro_dump_datagrams(nbytes, sizes, len(sizes))
+    return [int(sizes[i]) for i in range(k)]
+
+
 class RefChain:
     """One channel of the compiled reference product path (radioDiags tree)."""
 
-    def __init__(self):
+    def __init__(self, dump_port=None):
         self.L = ref("radiodiags")
         if self.L is None:
             raise RuntimeError("oracle/_ref not built")
-        self.h = self.L.ref_iqp_new()
+        self.h = self.L.ref_iqp_new() if dump_port is None else self.L.ref_iqp_new_port(int(dump_port))
+
+    def set_dump(self, on):
+        """enableIqDump / disableIqDump: UDP datagrams to 127.0.0.1:dump_port."""
+        self.L.ref_iqp_set_dump(self.h, int(bool(on)))
 
     def __del__(self):
         if getattr(self, "h", None):

@@ -194,11 +194,11 @@ struct Chain {
 };
 void onSignalState(bool signalPresent, void *contextPtr) { ((Chain *)contextPtr)->signal_present = signalPresent; }
 void onSignalMagnitude(uint32_t magnitude, void *contextPtr) { ((Chain *)contextPtr)->signal_magnitude = magnitude; }
-Chain *chainNew() {
+Chain *chainNew(int port = 8001) {
   // Mirrors the wiring in radioDiags/src_diags/Radio.cc:150-181.
   static char host[] = "127.0.0.1";
   Chain *c = new Chain();
-  c->iqp = new IqDataProcessor(host, 8001);
+  c->iqp = new IqDataProcessor(host, port);
   c->am = new AmDemodulator(pcmCallback);
   c->fm = new FmDemodulator(pcmCallback);
   c->wbfm = new WbFmDemodulator(pcmCallback);
@@ -226,6 +226,12 @@ void chainFree(Chain *c) {
 }  // namespace
 
 void *ref_iqp_new(void) { return chainNew(); }
+// the IQ dump's link partner listens on 127.0.0.1:port
+void *ref_iqp_new_port(int port) { return chainNew(port); }
+void ref_iqp_set_dump(void *h, int on) {
+  if (on) ((Chain *)h)->iqp->enableIqDump();
+  else ((Chain *)h)->iqp->disableIqDump();
+}
 void ref_iqp_free(void *h) { chainFree((Chain *)h); }
 void ref_iqp_set_mode(void *h, int mode) {
   ((Chain *)h)->iqp->setDemodulatorMode((IqDataProcessor::demodulatorType)mode);

@@ -625,6 +625,33 @@ static void dispatch(sdro_chain *c, int mode, int8_t *buf, uint32_t nbytes, pcm_
 
 /* IqDataProcessor::acceptIqData, IqDataProcessor.cc:722-840, with the squelch
  * at its default always-open threshold (IqDataProcessor.cc:41). */
+/* The conversion half of acceptIqData (IqDataProcessor.cc:735-751), in place. What it leaves
+ * in the buffer is what the IQ dump sends (IqDataProcessor.cc:756-760) and what a .iq file
+ * holds (demod.cc:8-11). */
+void sdro_front_end(uint8_t *ubuf, uint32_t nbytes) {
+  int8_t *buf = (int8_t *)ubuf;
+  for (uint32_t i = 0; i < nbytes; i++) buf[i] = (int8_t)(uint8_t)(ubuf[i] - 128u);
+  for (uint32_t i = 0; i + 7 < nbytes; i += 8) {
+    int8_t x, y;
+    x = buf[i + 2]; y = buf[i + 3]; buf[i + 2] = neg_i8(y); buf[i + 3] = x;
+    x = buf[i + 4]; y = buf[i + 5]; buf[i + 4] = neg_i8(x); buf[i + 5] = neg_i8(y);
+    x = buf[i + 6]; y = buf[i + 7]; buf[i + 6] = y; buf[i + 7] = neg_i8(x);
+  }
+}
+
+/* UdpClient::sendData (UdpClient.cc:173-241): n bytes leave as floor(n/2048) datagrams of
+ * 2048 bytes and one of the remainder. Writes the sizes, returns how many. */
+uint32_t sdro_dump_datagrams(uint32_t nbytes, uint32_t *sizes, uint32_t cap) {
+  uint32_t k = 0;
+  for (uint32_t off = 0; off + 2048 <= nbytes; off += 2048, k++)
+    if (k < cap) sizes[k] = 2048;
+  if (nbytes % 2048) {
+    if (k < cap) sizes[k] = nbytes % 2048;
+    k++;
+  }
+  return k;
+}
+
 uint32_t sdro_chain_accept_u8(sdro_chain *c, uint8_t *ubuf, uint32_t nbytes, int16_t *pcm,
                               uint32_t cap) {
   int8_t *buf = (int8_t *)ubuf;

@@ -72,6 +72,11 @@ void sdro_chain_set_threshold(sdro_chain *c, int32_t threshold);
 void sdro_chain_set_rx_gain(sdro_chain *c, uint32_t gain_db);
 void sdro_chain_signal(const sdro_chain *c, int *allowed, uint32_t *magnitude);
 
+/* IQ dump: the in-place conversion + Fs/4 rotation of acceptIqData, i.e. the bytes the
+ * reference hands to UdpClient::sendData, and the datagram sizes sendData cuts them into */
+void sdro_front_end(uint8_t *buf, uint32_t nbytes);
+uint32_t sdro_dump_datagrams(uint32_t nbytes, uint32_t *sizes, uint32_t cap);
+
 /* quantised taps of every Q15 filter on the path, for table cross-checks.
  * id: 0 am1 1 am2 2 am3 3 fm_tuner 4 fm_post 5 audio40 6 wb_pre 7 wb_dec1
  *     8 ssb_delay 9 ssb_hilbert. Returns the tap count. */

@@ -25,7 +25,8 @@ ABI_SYMBOLS = ["sdr_engine_create", "sdr_engine_destroy", "sdr_set_stream", "sdr
                "sdr_set_mode", "sdr_set_modes", "sdr_set_gain", "sdr_set_gain_all", "sdr_reset",
                "sdr_accept_iq", "sdr_get_pcm", "sdr_pcm_device", "sdr_sync", "sdr_join", "sdr_set_launch_shape",
                "sdr_launch_count", "sdr_state_bytes", "sdr_last_error", "sdr_version", "sdr_set_squelch_threshold",
-               "sdr_set_receive_gain_db", "sdr_enable_signal_reports", "sdr_get_signal"]
+               "sdr_set_receive_gain_db", "sdr_enable_signal_reports", "sdr_get_signal", "sdr_set_iq_dump",
+               "sdr_get_iq_dump", "sdr_iq_dump_device"]
 
 
 class SdrError(RuntimeError):
@@ -65,6 +66,9 @@ def load_library(build_if_missing=True):
     L.sdr_set_receive_gain_db.argtypes = [vp, u32, u32]
     L.sdr_enable_signal_reports.argtypes = [vp, i32]
     L.sdr_get_signal.argtypes = [vp, vp, vp]
+    L.sdr_set_iq_dump.argtypes = [vp, u32, i32]
+    L.sdr_get_iq_dump.argtypes = [vp, u32, vp, u64, C.POINTER(u64)]
+    L.sdr_iq_dump_device.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(u32)]
     L.sdr_set_launch_shape.argtypes = [vp, i32, u32, u32]
     L.sdr_launch_count.argtypes = [vp]
     L.sdr_launch_count.restype = u64
@@ -143,6 +147,20 @@ class Engine:
         m = np.empty(self.n, dtype=np.uint32)
         self._ck(self.L.sdr_get_signal(self.h, a.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p)))
         return a.astype(bool), m
+
+    def set_iq_dump(self, channel, on=True):
+        """IqDataProcessor::enableIqDump / disableIqDump for one channel of the bank."""
+        self._ck(self.L.sdr_set_iq_dump(self.h, channel, int(bool(on))))
+
+    def get_iq_dump(self, channel):
+        """The last accept's block of `channel` as the reference hands it to UdpClient::sendData
+        (signed, Fs/4-rotated int8). Synchronises."""
+        n = C.c_uint64()
+        self._ck(self.L.sdr_get_iq_dump(self.h, channel, None, C.c_uint64(0), C.byref(n)))
+        out = np.empty(n.value, dtype=np.int8)
+        self._ck(self.L.sdr_get_iq_dump(self.h, channel, out.ctypes.data_as(C.c_void_p), C.c_uint64(out.size),
+                                        C.byref(n)))
+        return out
 
     def set_launch_shape(self, kind, channels_per_cta=0, threads=0):
         self._ck(self.L.sdr_set_launch_shape(self.h, kind, channels_per_cta, threads))

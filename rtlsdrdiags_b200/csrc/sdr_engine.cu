@@ -15,6 +15,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -72,6 +73,15 @@ struct sdr_engine {
   uint8_t *d_tracking = nullptr, *d_allowed[2] = {};
   int32_t *d_db_table = nullptr;
   bool last_gated = false;  // the last accept ran the squelch kernel with the gate in force
+
+  // IQ dump (IqDataProcessor::enableIqDump): channels whose converted block is kept
+  std::vector<uint8_t> dump_on;
+  std::vector<uint32_t> dump_list;
+  bool dump_dirty = false;
+  uint32_t *d_dump_list = nullptr;
+  int8_t *d_dump = nullptr;
+  size_t dump_rows = 0;       // rows d_dump holds
+  uint64_t dump_bytes = 0;    // bytes per channel of the last dump (0 = none)
 
   Shape shape[5];
   uint32_t last_samples = 0;  // PCM samples per channel of the last accept
@@ -289,6 +299,49 @@ int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint3
   return SDR_OK;
 }
 
+// Converts the block of every dumped channel into the dump buffer. Runs first in a call:
+// the reference sends the dump whatever the squelch decides (IqDataProcessor.cc:753-760).
+int run_iq_dump(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint64_t bytes, int fmt) {
+  if (e->dump_dirty) {
+    e->dump_list.clear();
+    for (uint32_t ch = 0; ch < e->n; ++ch)
+      if (e->dump_on[ch]) e->dump_list.push_back(ch);
+    if (e->dump_list.size() > e->dump_rows) {
+      SDR_CK(e, cudaStreamSynchronize(e->stream));
+      cudaFree(e->d_dump);
+      cudaFree(e->d_dump_list);
+      e->d_dump = nullptr;
+      e->d_dump_list = nullptr;
+      e->dump_rows = e->dump_list.size();
+      SDR_CK(e, cudaMalloc(&e->d_dump, e->dump_rows * e->max_bytes));
+      SDR_CK(e, cudaMalloc(&e->d_dump_list, e->dump_rows * 4));
+    }
+    if (!e->dump_list.empty()) {
+      SDR_CK(e, cudaStreamSynchronize(e->stream));  // the list may be in use by a queued kernel
+      SDR_CK(e, cudaMemcpy(e->d_dump_list, e->dump_list.data(), e->dump_list.size() * 4, cudaMemcpyHostToDevice));
+    }
+    e->dump_dirty = false;
+  }
+  e->dump_bytes = 0;
+  if (e->dump_list.empty()) return SDR_OK;
+  DumpParams d{};
+  d.iq = iq;
+  d.ch_stride = ch_stride;
+  d.bytes = bytes;
+  d.fmt = fmt;
+  d.list = e->d_dump_list;
+  d.n_list = (uint32_t)e->dump_list.size();
+  d.out = e->d_dump;
+  d.out_stride = e->max_bytes;
+  const uint64_t pieces = bytes / 16;
+  uint32_t gx = (uint32_t)std::min<uint64_t>((pieces + 255) / 256, 64);
+  iq_dump_kernel<<<dim3(gx, d.n_list), 256, 0, e->stream>>>(d);
+  SDR_CK(e, cudaGetLastError());
+  e->launches++;
+  e->dump_bytes = bytes;
+  return SDR_OK;
+}
+
 // Runs the squelch kernel when a threshold that can close is set (the gate is then in force)
 // or when signal reports are wanted. A channel whose threshold can never close
 // (threshold <= -42 - gain: even magnitude 0 passes, DbfsCalculator.cc) needs no kernel.
@@ -433,6 +486,7 @@ int sdr_engine_create(uint32_t n_channels, int device, uint64_t max_bytes_per_ch
   }
   e->stream = e->own_stream;
 
+  e->dump_on.assign(n_channels, 0);           // IqDataProcessor.cc:62
   e->threshold.assign(n_channels, -200);      // IqDataProcessor.cc:41
   e->rx_gain_db.assign(n_channels, 0);
   e->mode.assign(n_channels, SDR_MODE_NONE);  // IqDataProcessor.cc:38
@@ -499,6 +553,8 @@ int sdr_engine_destroy(sdr_engine *e) {
   cudaFree(e->d_rx_gain);
   cudaFree(e->d_magnitude);
   cudaFree(e->d_tracking);
+  cudaFree(e->d_dump);
+  cudaFree(e->d_dump_list);
   cudaFree(e->d_allowed[0]);
   cudaFree(e->d_allowed[1]);
   cudaFree(e->d_db_table);
@@ -617,6 +673,7 @@ int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_str
   // before the previous one
   if (have_rec || e->squelch_armed || e->signal_reports || e->squelch_dirty)
     SDR_CK(e, cudaStreamWaitEvent(e->stream, e->ev_rec[par], 0));
+  if ((rc = run_iq_dump(e, dev_iq, dev_stride, bytes, fmt))) return rc;
   if ((rc = run_squelch(e, dev_iq, dev_stride, bytes, fmt))) return rc;
   if ((rc = launch_amssb<false>(e, SDR_KIND_AM, dev_iq, dev_stride, n_samples, fmt))) return rc;
   if ((rc = launch_amssb<true>(e, SDR_KIND_SSB, dev_iq, dev_stride, n_samples, fmt))) return rc;
@@ -695,6 +752,40 @@ int sdr_get_signal(sdr_engine *e, uint8_t *allowed, uint32_t *magnitude) {
   if (magnitude)
     SDR_CK(e, cudaMemcpyAsync(magnitude, e->d_magnitude, (size_t)e->n * 4, cudaMemcpyDeviceToHost, e->stream));
   SDR_CK(e, cudaStreamSynchronize(e->stream));
+  return SDR_OK;
+}
+
+int sdr_set_iq_dump(sdr_engine *e, uint32_t ch, int on) {
+  if (!e || ch >= e->n) return SDR_E_ARG;
+  if (e->dump_on[ch] != (uint8_t)(on != 0)) {
+    e->dump_on[ch] = on != 0;
+    e->dump_dirty = true;
+  }
+  return SDR_OK;
+}
+
+int sdr_get_iq_dump(sdr_engine *e, uint32_t ch, int8_t *out, uint64_t capacity, uint64_t *n_bytes) {
+  if (!e || ch >= e->n) return SDR_E_ARG;
+  if (n_bytes) *n_bytes = 0;
+  auto it = std::lower_bound(e->dump_list.begin(), e->dump_list.end(), ch);
+  if (e->dump_dirty || it == e->dump_list.end() || *it != ch || e->dump_bytes == 0)
+    return fail(e, SDR_E_ARG, "no IQ dump for this channel: enable it before the call whose block is wanted");
+  if (out && capacity < e->dump_bytes) return fail(e, SDR_E_ARG, "IQ dump buffer too small");
+  SDR_CK(e, cudaSetDevice(e->device));
+  if (out) {
+    SDR_CK(e, cudaMemcpyAsync(out, e->d_dump + (size_t)(it - e->dump_list.begin()) * e->max_bytes, e->dump_bytes,
+                              cudaMemcpyDeviceToHost, e->stream));
+    SDR_CK(e, cudaStreamSynchronize(e->stream));
+  }
+  if (n_bytes) *n_bytes = e->dump_bytes;
+  return SDR_OK;
+}
+
+int sdr_iq_dump_device(sdr_engine *e, int8_t **rows, uint64_t *row_stride, uint32_t *n_rows) {
+  if (!e) return SDR_E_ARG;
+  if (rows) *rows = e->d_dump;
+  if (row_stride) *row_stride = e->max_bytes;
+  if (n_rows) *n_rows = e->dump_bytes ? (uint32_t)e->dump_list.size() : 0;
   return SDR_OK;
 }
 

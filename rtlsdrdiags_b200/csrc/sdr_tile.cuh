@@ -989,6 +989,43 @@ __global__ void __launch_bounds__(768, 1) wbfm_tile_kernel(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------
+// IQ dump (IqDataProcessor.cc:756-760 -> UdpClient::sendData): the block as the demodulators
+// and the dump's link partner see it -- signed, Fs/4-rotated, interleaved I,Q -- for the
+// channels on `list`. One thread converts one 16-byte piece (two rotation periods); the
+// reference sends it on in datagrams of at most 2048 bytes, which are consecutive slices.
+// ---------------------------------------------------------------------------
+struct DumpParams {
+  const uint8_t *iq;
+  uint64_t ch_stride;
+  uint64_t bytes;        // per channel, a multiple of 64
+  int fmt;
+  const uint32_t *list;  // dumped channel ids
+  uint32_t n_list;
+  int8_t *out;           // [n_list][out_stride]
+  uint64_t out_stride;
+};
+
+__global__ void __launch_bounds__(256) iq_dump_kernel(const __grid_constant__ DumpParams p) {
+  const uint64_t pieces = p.bytes / 16;
+  const uint32_t li = blockIdx.y;
+  const uint8_t *src = p.iq + (uint64_t)p.list[li] * p.ch_stride;
+  int8_t *dst = p.out + (uint64_t)li * p.out_stride;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < pieces;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint4 v = __ldg(reinterpret_cast<const uint4 *>(src) + i);
+    if (p.fmt == FMT_U8_OFFSET_ROTATE) {
+      // z0 kept, z1 -> (-Q1, I1); z2 -> (-I2, -Q2), z3 -> (Q3, -I3)   (IqDataProcessor.cc:567-611)
+      v.x = offset_and_negate(byte_perm(v.x, 0u, 0x2310), 0x00ff0000u, 0x00010000u);
+      v.y = offset_and_negate(byte_perm(v.y, 0u, 0x2310), 0xff00ffffu, 0x01000101u);
+      v.z = offset_and_negate(byte_perm(v.z, 0u, 0x2310), 0x00ff0000u, 0x00010000u);
+      v.w = offset_and_negate(byte_perm(v.w, 0u, 0x2310), 0xff00ffffu, 0x01000101u);
+    }
+    reinterpret_cast<uint4 *>(dst)[i] = v;
+  }
+}
+
+
+// ---------------------------------------------------------------------------
 // Squelch (IqDataProcessor.cc:764-765 -> Squelch.cc:227-273): mean of the max + min/2
 // magnitude estimate over the block (SignalDetector.cc:205-273), dBFS through the 7-bit
 // table (DbfsCalculator.cc:111-147), threshold, two-state tracker with a one-block tail

@@ -1,8 +1,13 @@
 // Mode switch in front of the four drop-in demodulators.
 #include "IqDataProcessor.h"
 
+#include <arpa/inet.h>
+#include <netinet/in.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+#include <sys/socket.h>
+#include <unistd.h>
 
 #include <vector>
 
@@ -11,8 +16,29 @@ extern int32_t radio_adjustableReceiveGainInDb;
 
 IqDataProcessor::IqDataProcessor(char *hostIpAddress, int hostPort)
 {
-  (void)hostIpAddress; // the IQ-dump UDP client is not rebuilt
-  (void)hostPort;
+  // The dump's link partner (UdpClient.cc:53-96): one UDP socket, 32768-byte send buffer.
+  iqDumpEnabled = false; // IqDataProcessor.cc:62
+  dumpSocket = socket(PF_INET, SOCK_DGRAM, 0);
+  if (dumpSocket != -1)
+  {
+    struct sockaddr_in peer;
+    int bufferLength = 32768;
+    static_assert(sizeof(peer) <= sizeof(dumpPeer), "peer address storage");
+    memset(&peer, 0, sizeof(peer));
+    peer.sin_family = AF_INET;
+    peer.sin_addr.s_addr = inet_addr(hostIpAddress);
+    peer.sin_port = htons(hostPort);
+    memcpy(dumpPeer, &peer, sizeof(peer));
+    if (setsockopt(dumpSocket, SOL_SOCKET, SO_SNDBUF, &bufferLength, sizeof(int)) == -1)
+    {
+      close(dumpSocket);
+      dumpSocket = 0;
+    } // if
+  } // if
+  else
+  {
+    dumpSocket = 0;
+  } // else
 
   // Default to no demodulation of the signal (IqDataProcessor.cc:38).
   demodulatorMode = None;
@@ -39,7 +65,39 @@ IqDataProcessor::~IqDataProcessor(void)
   {
     sdr_engine_destroy(gateEngine);
   } // if
+  if (dumpSocket != 0)
+  {
+    close(dumpSocket);
+  } // if
 } // ~IqDataProcessor
+
+void IqDataProcessor::enableIqDump(void) { iqDumpEnabled = true; }
+void IqDataProcessor::disableIqDump(void) { iqDumpEnabled = false; }
+bool IqDataProcessor::isIqDumpEnabled(void) { return (iqDumpEnabled); }
+
+// networkInterfacePtr->sendData(signedBufferPtr, byteCount) (IqDataProcessor.cc:759): the
+// engine's dump of this block, in UdpClient::sendData's slices (UdpClient.cc:199-231).
+void IqDataProcessor::sendIqDump(unsigned long byteCount)
+{
+  static thread_local std::vector<int8_t> dump;
+  uint64_t n = 0;
+  dump.resize(byteCount);
+  if (sdr_get_iq_dump(gateEngine, 0, dump.data(), byteCount, &n) != SDR_OK)
+  {
+    fprintf(stderr, "IqDataProcessor: IQ dump failed: %s\n", sdr_last_error(gateEngine));
+    return;
+  } // if
+  if (dumpSocket == 0)
+  {
+    return; // UdpClient only sends to open sockets
+  } // if
+  const uint64_t maxPayloadLength = 2048;
+  for (uint64_t off = 0; off < n; off += maxPayloadLength)
+  {
+    uint64_t len = n - off < maxPayloadLength ? n - off : maxPayloadLength;
+    sendto(dumpSocket, dump.data() + off, len, 0, (struct sockaddr *)dumpPeer, sizeof(struct sockaddr));
+  } // for
+} // sendIqDump
 
 void IqDataProcessor::setSignalDetectThreshold(int32_t threshold)
 {
@@ -68,7 +126,7 @@ void IqDataProcessor::registerSignalMagnitudeCallback(void (*callbackPtr)(uint32
 // demodulation.
 bool IqDataProcessor::runSquelch(unsigned char *bufferPtr, unsigned long byteCount)
 {
-  const bool wanted = signalDetectThreshold != -200 || radio_adjustableReceiveGainInDb != 0 ||
+  const bool wanted = iqDumpEnabled || signalDetectThreshold != -200 || radio_adjustableReceiveGainInDb != 0 ||
                       (signalNotificationEnabled && signalCallbackPtr != NULL) ||
                       (signalMagnitudeNotificationEnabled && signalMagnitudeCallbackPtr != NULL);
   if (!wanted && gateEngine == NULL)
@@ -108,13 +166,19 @@ bool IqDataProcessor::runSquelch(unsigned char *bufferPtr, unsigned long byteCou
   uint32_t magnitude = 0;
   sdr_set_squelch_threshold(gateEngine, 0, signalDetectThreshold);
   sdr_set_receive_gain_db(gateEngine, 0, (uint32_t)radio_adjustableReceiveGainInDb);
+  sdr_set_iq_dump(gateEngine, 0, iqDumpEnabled ? 1 : 0);
   // the block may sit at any address: stage it 16-byte aligned
   static thread_local std::vector<uint8_t> staging;
   staging.resize(byteCount + 16);
   uint8_t *aligned = (uint8_t *)(((uintptr_t)staging.data() + 15) & ~(uintptr_t)15);
   for (unsigned long i = 0; i < byteCount; i++) aligned[i] = bufferPtr[i];
-  if (sdr_accept_iq(gateEngine, aligned, byteCount, byteCount, SDR_IQ_HOST | SDR_IQ_U8_OFFSET) != SDR_OK ||
-      sdr_get_signal(gateEngine, &allowed, &magnitude) != SDR_OK)
+  const bool dumping = iqDumpEnabled;
+  int rc = sdr_accept_iq(gateEngine, aligned, byteCount, byteCount, SDR_IQ_HOST | SDR_IQ_U8_OFFSET);
+  if (rc == SDR_OK && dumping)
+  {
+    sendIqDump(byteCount); // before the squelch speaks, so a display stays live (IqDataProcessor.cc:753)
+  } // if
+  if (rc != SDR_OK || sdr_get_signal(gateEngine, &allowed, &magnitude) != SDR_OK)
   {
     fprintf(stderr, "IqDataProcessor: squelch failed: %s\n", sdr_last_error(gateEngine));
     return (true);

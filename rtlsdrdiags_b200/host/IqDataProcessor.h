@@ -4,7 +4,8 @@
 // the first step of the demodulation kernels. The squelch gate and the signal-state /
 // signal-magnitude callbacks (IqDataProcessor.cc:764-790) run on a one-channel engine of
 // their own, because the reference keeps one Squelch per IqDataProcessor, shared by all
-// modes. The IQ dump (UdpClient) is not rebuilt.
+// modes. The same engine emits the IQ dump (enableIqDump, IqDataProcessor.cc:756-760), which
+// leaves for hostIpAddress:hostPort in datagrams of at most 2048 bytes like UdpClient's.
 #ifndef _IQDATAPROCESSOR_H_
 #define _IQDATAPROCESSOR_H_
 
@@ -31,6 +32,10 @@ class IqDataProcessor
 
   void setSignalDetectThreshold(int32_t threshold);
 
+  void enableIqDump(void);
+  void disableIqDump(void);
+  bool isIqDumpEnabled(void);
+
   void acceptIqData(unsigned long timeStamp, unsigned char *bufferPtr, unsigned long byteCount);
 
   void enableSignalNotification(void);
@@ -45,6 +50,11 @@ class IqDataProcessor
 
   private:
   bool runSquelch(unsigned char *bufferPtr, unsigned long byteCount);
+  void sendIqDump(unsigned long byteCount);
+
+  bool iqDumpEnabled;
+  int dumpSocket;           // 0 = not open, as UdpClient keeps it (UdpClient.cc:77-96)
+  unsigned char dumpPeer[16]; // struct sockaddr_in of the link partner
 
   demodulatorType demodulatorMode;
   int32_t signalDetectThreshold;

@@ -10,6 +10,7 @@
 //        Without -u the input is signed and already rotated (demod.cc:8-11).
 //   -r   research-tree FM/WBFM scaling (what demod.cc itself links against).
 //   -b   bytes per read (default 16384 like demod.cc:250; 32768 with -u).
+//   -p   with -u: enableIqDump towards 127.0.0.1:<port> (IqDataProcessor::enableIqDump).
 //   -s   squelch threshold in dBFS (with -u; IqDataProcessor::setSignalDetectThreshold),
 //        and print every block's signal state and magnitude to stderr.
 #include <stdint.h>
@@ -51,10 +52,10 @@ int main(int argc, char **argv)
 {
   int demodulatorType = 2;
   bool rawInput = false, research = false, realLsb = false, squelch = false;
-  long blockBytes = 0, threshold = -200;
+  long blockBytes = 0, threshold = -200, dumpPort = 0;
   int opt;
 
-  while ((opt = getopt(argc, argv, "d:urlb:s:h")) != -1)
+  while ((opt = getopt(argc, argv, "d:urlb:s:p:h")) != -1)
   {
     switch (opt)
     {
@@ -63,6 +64,7 @@ int main(int argc, char **argv)
       case 'r': research = true; break;
       case 'l': realLsb = true; break;
       case 'b': blockBytes = atol(optarg); break;
+      case 'p': dumpPort = atol(optarg); break;
       case 's': squelch = true; threshold = atol(optarg); break;
       default:
         fprintf(stderr, "./b200_demod -d [1 - AM | 2 - FM | 3 - WBFM | 4 - LSB | 5 - USB] [-u] [-r] [-l] [-b bytes]"
@@ -91,7 +93,11 @@ int main(int argc, char **argv)
   } // if
 
   static char host[] = "127.0.0.1";
-  IqDataProcessor *processorPtr = new IqDataProcessor(host, 8001);
+  IqDataProcessor *processorPtr = new IqDataProcessor(host, dumpPort ? (int)dumpPort : 8001);
+  if (dumpPort)
+  {
+    processorPtr->enableIqDump();
+  } // if
   processorPtr->setAmDemodulator(amDemodPtr);
   processorPtr->setFmDemodulator(fmDemodPtr);
   processorPtr->setWbFmDemodulator(wbFmDemodPtr);

@@ -107,3 +107,28 @@ def test_driver_squelch_and_signal_callbacks(first_quiet):
     assert [l for l in r.stderr.decode().splitlines() if l.startswith("signal")] == lines
     assert any(e.size == 0 for e in exp) and any(e.size for e in exp)
     assert np.array_equal(got, np.concatenate(exp))
+
+
+@pytest.mark.gpu
+def test_driver_iq_dump_datagrams():
+    """b200_demod -u -p PORT: enableIqDump; the datagrams the drop-in sends equal the ones the
+    reference sends (tests/test_iq_dump.py pins the oracle to those), squelched or not."""
+    import socket
+    sock = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+    sock.setsockopt(socket.SOL_SOCKET, socket.SO_RCVBUF, 1 << 22)
+    sock.bind(("127.0.0.1", 0))
+    sock.settimeout(5.0)
+    try:
+        block = 4096 + 64
+        u8 = S.noise(1, block * 3, seed=8)[0]
+        r = subprocess.run([_demod(), "-d", "3", "-u", "-b", str(block), "-p", str(sock.getsockname()[1]), "-s", "0"],
+                           input=u8.tobytes(), capture_output=True, timeout=300)
+        assert r.returncode == 0, r.stderr.decode()
+        assert len(r.stdout) == 0   # threshold 0 dBFS: everything squelched
+        for o in range(0, u8.size, block):
+            sizes = O.dump_datagrams(block)
+            got = [sock.recv(4096) for _ in sizes]
+            assert [len(g) for g in got] == sizes
+            assert np.array_equal(np.frombuffer(b"".join(got), dtype=np.int8), O.front_end(u8[o:o + block]))
+    finally:
+        sock.close()
