@@ -32,6 +32,8 @@
  *     (src_diags/IqDataProcessor.cc:633-669)
  *   networkInterfacePtr->sendData(signedBufferPtr, n)      sdr_get_iq_dump / sdr_iq_dump_device
  *     (IqDataProcessor.cc:756-760, UdpClient.cc:173-241)
+ *   DataConsumer::acceptData(ts, buf, n) + consumer thread  sdr_ingest_accept / _acquire+_commit,
+ *     (src_diags/DataConsumer.cc:220-261, 318-352)           sdr_ingest_retire, sdr_ingest_stats
  *
  * All functions return 0 on success or a negative SDR_E_* code; none throws.
  * Calls on one engine must be serialised by the caller (the reference calls
@@ -71,7 +73,9 @@ enum {
   SDR_E_ARG = -1,      /* bad handle, channel, mode, kind, size or alignment */
   SDR_E_CUDA = -2,     /* CUDA runtime error (sdr_last_error has the text) */
   SDR_E_NOMEM = -3,
-  SDR_E_TOO_LONG = -4  /* bytes_per_channel exceeds the engine's max_bytes_per_channel */
+  SDR_E_TOO_LONG = -4, /* bytes_per_channel exceeds the engine's max_bytes_per_channel */
+  SDR_E_FULL = -5,     /* ingest ring: every slot holds a tick that was not retired yet */
+  SDR_E_EMPTY = -6     /* ingest ring: no tick in flight */
 };
 
 /* One engine = n_channels radios on CUDA device `device`. max_bytes_per_channel
@@ -142,6 +146,34 @@ int sdr_sync(sdr_engine *e);
  * host, so that an event recorded on that stream afterwards covers everything queued so
  * far. sdr_get_pcm and sdr_sync imply it. */
 int sdr_join(sdr_engine *e);
+
+/* Ingest ring: the bank's DataConsumer (DataConsumer.cc:220-352). A tick is one block of
+ * every channel. The ring has n_slots pinned host slots of [n_channels][block_bytes]; a
+ * committed tick's host->device copy, demodulation and PCM read-back are queued on three
+ * streams and overlap those of its neighbours. Ticks retire in order. While a ring is in
+ * use, feed the engine only through it. */
+typedef struct sdr_ingest sdr_ingest;
+int sdr_ingest_create(sdr_engine *e, uint32_t n_slots /* 2..64 */, uint64_t block_bytes, sdr_ingest **out);
+int sdr_ingest_destroy(sdr_ingest *q);
+/* DataConsumer::acceptData for the bank: copies iq ([n_channels][channel_stride], the first
+ * bytes_per_channel of each row) into the next slot and queues it. Like the reference, a
+ * block longer than block_bytes is clipped and a shorter one counts as a short block
+ * (DataConsumer.cc:238-246). flags: SDR_IQ_U8_OFFSET or SDR_IQ_S8_ROTATED. SDR_E_FULL if
+ * no slot is free. */
+int sdr_ingest_accept(sdr_ingest *q, uint32_t timestamp, const void *iq, uint64_t bytes_per_channel,
+                      uint64_t channel_stride, uint32_t flags);
+/* The same without the copy: write the tick straight into the slot (*iq, rows
+ * *channel_stride apart), then commit it. */
+int sdr_ingest_acquire(sdr_ingest *q, void **iq, uint64_t *channel_stride);
+int sdr_ingest_commit(sdr_ingest *q, uint32_t timestamp, uint64_t bytes_per_channel, uint32_t flags);
+/* Waits for the oldest tick in flight and returns its timestamp, its PCM (pinned host memory,
+ * [n_channels][*samples_per_row]) and counts[n_channels]; the pointers stay valid until the
+ * next sdr_ingest_acquire / sdr_ingest_accept. SDR_E_EMPTY if nothing is in flight. */
+int sdr_ingest_retire(sdr_ingest *q, uint32_t *timestamp, const int16_t **pcm, uint32_t *samples_per_row,
+                      const uint32_t **counts);
+/* lastTimeStamp and shortBlockCount (DataConsumer.cc:282-283), ticks committed, ticks in flight */
+int sdr_ingest_stats(const sdr_ingest *q, uint32_t *last_timestamp, uint32_t *short_block_count, uint64_t *ticks,
+                     uint32_t *in_flight);
 
 /* Launch shape of one demodulator kind: channels per CTA (1..32) and threads
  * per CTA (multiple of 32). 0 = let the engine choose. For tuning and tests. */

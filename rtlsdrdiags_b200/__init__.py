@@ -26,7 +26,8 @@ ABI_SYMBOLS = ["sdr_engine_create", "sdr_engine_destroy", "sdr_set_stream", "sdr
                "sdr_accept_iq", "sdr_get_pcm", "sdr_pcm_device", "sdr_sync", "sdr_join", "sdr_set_launch_shape",
                "sdr_launch_count", "sdr_state_bytes", "sdr_last_error", "sdr_version", "sdr_set_squelch_threshold",
                "sdr_set_receive_gain_db", "sdr_enable_signal_reports", "sdr_get_signal", "sdr_set_iq_dump",
-               "sdr_get_iq_dump", "sdr_iq_dump_device"]
+               "sdr_get_iq_dump", "sdr_iq_dump_device", "sdr_ingest_create", "sdr_ingest_destroy",
+               "sdr_ingest_accept", "sdr_ingest_acquire", "sdr_ingest_commit", "sdr_ingest_retire", "sdr_ingest_stats"]
 
 
 class SdrError(RuntimeError):
@@ -69,6 +70,13 @@ def load_library(build_if_missing=True):
     L.sdr_set_iq_dump.argtypes = [vp, u32, i32]
     L.sdr_get_iq_dump.argtypes = [vp, u32, vp, u64, C.POINTER(u64)]
     L.sdr_iq_dump_device.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(u32)]
+    L.sdr_ingest_create.argtypes = [vp, u32, u64, C.POINTER(vp)]
+    L.sdr_ingest_destroy.argtypes = [vp]
+    L.sdr_ingest_accept.argtypes = [vp, u32, vp, u64, u64, u32]
+    L.sdr_ingest_acquire.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+    L.sdr_ingest_commit.argtypes = [vp, u32, u64, u32]
+    L.sdr_ingest_retire.argtypes = [vp, C.POINTER(u32), C.POINTER(vp), C.POINTER(u32), C.POINTER(vp)]
+    L.sdr_ingest_stats.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u64), C.POINTER(u32)]
     L.sdr_set_launch_shape.argtypes = [vp, i32, u32, u32]
     L.sdr_launch_count.argtypes = [vp]
     L.sdr_launch_count.restype = u64
@@ -226,3 +234,59 @@ class Engine:
             pcm, counts = self.get_pcm()
             outs.append(pcm)
         return np.concatenate(outs, axis=1), counts
+
+
+class Ingest:
+    """The bank's DataConsumer (DataConsumer.cc:220-352): a ring of pinned ticks whose
+    host->device copy, demodulation and PCM read-back overlap. Ticks retire in order."""
+
+    def __init__(self, engine, n_slots=3, block_bytes=BLOCK_BYTES):
+        self.e = engine
+        self.L = engine.L
+        self.block_bytes = int(block_bytes)
+        q = C.c_void_p()
+        engine._ck(self.L.sdr_ingest_create(engine.h, int(n_slots), self.block_bytes, C.byref(q)))
+        self.q = q
+
+    def close(self):
+        if getattr(self, "q", None) and getattr(self.e, "h", None):
+            self.L.sdr_ingest_destroy(self.q)
+        self.q = None
+
+    __del__ = close
+
+    def accept(self, timestamp, iq, fmt=IQ_U8_OFFSET):
+        """DataConsumer::acceptData for the whole bank: iq is [n_channels][bytes]."""
+        a = np.ascontiguousarray(iq)
+        if a.ndim != 2 or a.shape[0] != self.e.n or a.itemsize != 1:
+            raise SdrError("iq must be [n_channels][bytes] of 1-byte items")
+        self.e._ck(self.L.sdr_ingest_accept(self.q, int(timestamp) & 0xFFFFFFFF, a.ctypes.data_as(C.c_void_p),
+                                            a.shape[1], a.strides[0], fmt))
+
+    def acquire(self):
+        """The next free slot as a writable [n_channels][block_bytes] uint8 view of pinned memory."""
+        p, stride = C.c_void_p(), C.c_uint64()
+        self.e._ck(self.L.sdr_ingest_acquire(self.q, C.byref(p), C.byref(stride)))
+        buf = (C.c_uint8 * (self.e.n * stride.value)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(self.e.n, stride.value)
+
+    def commit(self, timestamp, bytes_per_channel=None, fmt=IQ_U8_OFFSET):
+        self.e._ck(self.L.sdr_ingest_commit(self.q, int(timestamp) & 0xFFFFFFFF,
+                                            self.block_bytes if bytes_per_channel is None else int(bytes_per_channel),
+                                            fmt))
+
+    def retire(self, copy=True):
+        """(timestamp, pcm [n_channels][samples], counts [n_channels]) of the oldest tick in flight."""
+        ts, samples, p, c = C.c_uint32(), C.c_uint32(), C.c_void_p(), C.c_void_p()
+        self.e._ck(self.L.sdr_ingest_retire(self.q, C.byref(ts), C.byref(p), C.byref(samples), C.byref(c)))
+        n = self.e.n
+        pcm = np.frombuffer((C.c_int16 * (n * samples.value)).from_address(p.value), dtype=np.int16)
+        counts = np.frombuffer((C.c_uint32 * n).from_address(c.value), dtype=np.uint32)
+        pcm = pcm.reshape(n, samples.value)
+        return ts.value, (pcm.copy() if copy else pcm), (counts.copy() if copy else counts)
+
+    def stats(self):
+        ts, short, ticks, fl = C.c_uint32(), C.c_uint32(), C.c_uint64(), C.c_uint32()
+        self.e._ck(self.L.sdr_ingest_stats(self.q, C.byref(ts), C.byref(short), C.byref(ticks), C.byref(fl)))
+        return {"last_timestamp": ts.value, "short_blocks": short.value, "ticks": ticks.value,
+                "in_flight": fl.value}

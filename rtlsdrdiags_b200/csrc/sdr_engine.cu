@@ -802,4 +802,186 @@ int sdr_sync(sdr_engine *e) {
   return SDR_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Ingest ring: the bank's DataConsumer (DataConsumer.cc:220-352). The reference copies each
+// block into one of its message buffers and hands it to the consumer thread; here a block of
+// every channel (a tick) is copied into a pinned slot, and the slot's host->device copy,
+// demodulation and PCM device->host copy are queued on three streams, so the copy of tick
+// k+1 overlaps the demodulation of tick k and the PCM read-back of tick k-1.
+// ---------------------------------------------------------------------------
+struct sdr_ingest {
+  struct Slot {
+    uint8_t *h_iq = nullptr, *d_iq = nullptr;
+    int16_t *h_pcm = nullptr;
+    uint8_t *h_gate = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_done = nullptr;
+    uint32_t timestamp = 0;
+    uint64_t bytes = 0;
+    bool gated = false, queued = false;
+    std::vector<uint8_t> mode;
+    std::vector<uint32_t> counts;
+  };
+  sdr_engine *e = nullptr;
+  uint64_t block_bytes = 0;
+  std::vector<Slot> slot;
+  uint32_t head = 0, tail = 0, in_flight = 0;
+  int prev = -1;             // slot whose PCM read-back the next demodulation has to wait for
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  uint32_t last_timestamp = 0, short_blocks = 0;
+  uint64_t ticks = 0;
+};
+
+int sdr_ingest_destroy(sdr_ingest *q) {
+  if (!q) return SDR_E_ARG;
+  cudaSetDevice(q->e->device);
+  if (q->h2d) cudaStreamSynchronize(q->h2d);
+  cudaStreamSynchronize(q->e->stream);
+  if (q->d2h) cudaStreamSynchronize(q->d2h);
+  for (auto &s : q->slot) {
+    cudaFreeHost(s.h_iq);
+    cudaFreeHost(s.h_pcm);
+    cudaFreeHost(s.h_gate);
+    cudaFree(s.d_iq);
+    if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+    if (s.ev_comp) cudaEventDestroy(s.ev_comp);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+  }
+  if (q->h2d) cudaStreamDestroy(q->h2d);
+  if (q->d2h) cudaStreamDestroy(q->d2h);
+  delete q;
+  return SDR_OK;
+}
+
+int sdr_ingest_create(sdr_engine *e, uint32_t n_slots, uint64_t block_bytes, sdr_ingest **out) {
+  if (!e || !out || n_slots < 2 || n_slots > 64) return SDR_E_ARG;
+  if (block_bytes == 0 || block_bytes % 64 || block_bytes > e->max_bytes)
+    return fail(e, SDR_E_ARG, "ingest block_bytes must be a multiple of 64 within max_bytes_per_channel");
+  SDR_CK(e, cudaSetDevice(e->device));
+  sdr_ingest *q = new (std::nothrow) sdr_ingest();
+  if (!q) return SDR_E_NOMEM;
+  q->e = e;
+  q->block_bytes = block_bytes;
+  q->slot.resize(n_slots);
+#define SDR_CK_Q(call)                                 \
+  do {                                                 \
+    cudaError_t _ce = (call);                          \
+    if (_ce != cudaSuccess) {                          \
+      fail(e, SDR_E_CUDA, #call, _ce);                 \
+      sdr_ingest_destroy(q);                           \
+      return SDR_E_CUDA;                               \
+    }                                                  \
+  } while (0)
+  SDR_CK_Q(cudaStreamCreateWithFlags(&q->h2d, cudaStreamNonBlocking));
+  SDR_CK_Q(cudaStreamCreateWithFlags(&q->d2h, cudaStreamNonBlocking));
+  const size_t iq_bytes = (size_t)e->n * block_bytes, pcm_bytes = (size_t)e->n * (block_bytes / 64) * 2;
+  for (auto &s : q->slot) {
+    SDR_CK_Q(cudaHostAlloc(&s.h_iq, iq_bytes, cudaHostAllocDefault));
+    SDR_CK_Q(cudaHostAlloc(&s.h_pcm, pcm_bytes, cudaHostAllocDefault));
+    SDR_CK_Q(cudaHostAlloc(&s.h_gate, e->n, cudaHostAllocDefault));
+    SDR_CK_Q(cudaMalloc(&s.d_iq, iq_bytes));
+    SDR_CK_Q(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+    SDR_CK_Q(cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming));
+    SDR_CK_Q(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    s.counts.assign(e->n, 0);
+  }
+#undef SDR_CK_Q
+  *out = q;
+  return SDR_OK;
+}
+
+int sdr_ingest_acquire(sdr_ingest *q, void **iq, uint64_t *channel_stride) {
+  if (!q || !iq) return SDR_E_ARG;
+  sdr_ingest::Slot &s = q->slot[q->head];
+  if (s.queued) return fail(q->e, SDR_E_FULL, "ingest ring full: retire a tick first");
+  *iq = s.h_iq;
+  if (channel_stride) *channel_stride = q->block_bytes;
+  return SDR_OK;
+}
+
+int sdr_ingest_commit(sdr_ingest *q, uint32_t timestamp, uint64_t bytes, uint32_t flags) {
+  if (!q) return SDR_E_ARG;
+  sdr_engine *e = q->e;
+  sdr_ingest::Slot &s = q->slot[q->head];
+  if (s.queued) return fail(e, SDR_E_FULL, "ingest ring full: retire a tick first");
+  if (bytes == 0 || bytes % 64) return fail(e, SDR_E_ARG, "bytes_per_channel must be a positive multiple of 64");
+  // DataConsumer::acceptData, DataConsumer.cc:232-246: clip to the buffer, count short blocks
+  q->last_timestamp = timestamp;
+  if (bytes > q->block_bytes) bytes = q->block_bytes;
+  else if (bytes < q->block_bytes) q->short_blocks++;
+  SDR_CK(e, cudaSetDevice(e->device));
+  if (bytes == q->block_bytes)
+    SDR_CK(e, cudaMemcpyAsync(s.d_iq, s.h_iq, (size_t)e->n * bytes, cudaMemcpyHostToDevice, q->h2d));
+  else
+    SDR_CK(e, cudaMemcpy2DAsync(s.d_iq, q->block_bytes, s.h_iq, q->block_bytes, bytes, e->n,
+                                cudaMemcpyHostToDevice, q->h2d));
+  SDR_CK(e, cudaEventRecord(s.ev_h2d, q->h2d));
+  SDR_CK(e, cudaStreamWaitEvent(e->stream, s.ev_h2d, 0));
+  // the engine has one PCM buffer: wait until the previous tick's was read back
+  if (q->prev >= 0) SDR_CK(e, cudaStreamWaitEvent(e->stream, q->slot[q->prev].ev_done, 0));
+  int rc = sdr_accept_iq(e, s.d_iq, bytes, q->block_bytes, SDR_IQ_DEVICE | (flags & SDR_IQ_S8_ROTATED));
+  if (rc) return rc;
+  if ((rc = join_streams(e))) return rc;
+  SDR_CK(e, cudaEventRecord(s.ev_comp, e->stream));
+  SDR_CK(e, cudaStreamWaitEvent(q->d2h, s.ev_comp, 0));
+  const size_t row = (size_t)(bytes / 64) * 2;
+  SDR_CK(e, cudaMemcpy2DAsync(s.h_pcm, row, e->d_pcm, e->pcm_stride * 2, row, e->n, cudaMemcpyDeviceToHost, q->d2h));
+  s.gated = e->last_gated;
+  if (s.gated)
+    SDR_CK(e, cudaMemcpyAsync(s.h_gate, e->d_allowed[(e->seq + 1) & 1], e->n, cudaMemcpyDeviceToHost, q->d2h));
+  SDR_CK(e, cudaEventRecord(s.ev_done, q->d2h));
+  s.timestamp = timestamp;
+  s.bytes = bytes;
+  s.mode = e->mode;
+  s.queued = true;
+  q->prev = (int)q->head;
+  q->head = (q->head + 1) % (uint32_t)q->slot.size();
+  q->in_flight++;
+  q->ticks++;
+  return SDR_OK;
+}
+
+int sdr_ingest_accept(sdr_ingest *q, uint32_t timestamp, const void *iq, uint64_t bytes, uint64_t channel_stride,
+                      uint32_t flags) {
+  if (!q || !iq) return SDR_E_ARG;
+  void *dst = nullptr;
+  int rc = sdr_ingest_acquire(q, &dst, nullptr);
+  if (rc) return rc;
+  const uint64_t take = bytes > q->block_bytes ? q->block_bytes : bytes;
+  if (channel_stride < take) return fail(q->e, SDR_E_ARG, "channel_stride < bytes_per_channel");
+  for (uint32_t ch = 0; ch < q->e->n; ++ch)  // the reference's memcpy into message[].buffer, DataConsumer.cc:251
+    memcpy((uint8_t *)dst + (size_t)ch * q->block_bytes, (const uint8_t *)iq + (size_t)ch * channel_stride, take);
+  return sdr_ingest_commit(q, timestamp, bytes, flags);
+}
+
+int sdr_ingest_retire(sdr_ingest *q, uint32_t *timestamp, const int16_t **pcm, uint32_t *samples_per_row,
+                      const uint32_t **counts) {
+  if (!q) return SDR_E_ARG;
+  sdr_engine *e = q->e;
+  sdr_ingest::Slot &s = q->slot[q->tail];
+  if (!s.queued) return fail(e, SDR_E_EMPTY, "ingest ring empty: nothing to retire");
+  SDR_CK(e, cudaSetDevice(e->device));
+  SDR_CK(e, cudaEventSynchronize(s.ev_done));
+  const uint32_t samples = (uint32_t)(s.bytes / 64);
+  for (uint32_t ch = 0; ch < e->n; ++ch)
+    s.counts[ch] = (s.mode[ch] == SDR_MODE_NONE || (s.gated && !s.h_gate[ch])) ? 0 : samples;
+  if (timestamp) *timestamp = s.timestamp;
+  if (pcm) *pcm = s.h_pcm;
+  if (samples_per_row) *samples_per_row = samples;
+  if (counts) *counts = s.counts.data();
+  s.queued = false;
+  q->tail = (q->tail + 1) % (uint32_t)q->slot.size();
+  q->in_flight--;
+  return SDR_OK;
+}
+
+int sdr_ingest_stats(const sdr_ingest *q, uint32_t *last_timestamp, uint32_t *short_block_count, uint64_t *ticks,
+                     uint32_t *in_flight) {
+  if (!q) return SDR_E_ARG;
+  if (last_timestamp) *last_timestamp = q->last_timestamp;
+  if (short_block_count) *short_block_count = q->short_blocks;
+  if (ticks) *ticks = q->ticks;
+  if (in_flight) *in_flight = q->in_flight;
+  return SDR_OK;
+}
+
 }  // extern "C"

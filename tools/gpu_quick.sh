@@ -8,7 +8,7 @@ for wl in "$@"; do
 import sys, json
 try:
     d = json.loads(sys.stdin.read())
-    print('$wl', d['value'], 'Msps  frac', d['roofline']['frac'], ' ms', d['ms_per_step'], ' e2e', d['e2e']['value'])
+    print('$wl', d['value'], 'Msps  frac', d['roofline']['frac'], ' ms', d['ms_per_step'], ' e2e', d['e2e']['value'], 'sync', d['e2e'].get('synchronous_value'), d['e2e'].get('paths_agree'))
 except Exception as ex:
     print('$wl bench failed', ex)
 " | tee -a gpurun_out/quick_bench.txt
