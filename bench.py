@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary per-mode lines")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the end-to-end leg")
     return ap.parse_args()
 
 
@@ -330,7 +331,9 @@ def main():
         print("note: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
 
     res = bench_one(torch, R, synth, args.workload, channels, n_blocks, args.steps, args.warmup, args.signal,
-                    device, rank, world, dist)
+                    device, rank, world, dist, want_e2e=not args.no_e2e)
+    if args.no_e2e:
+        res.update(e2e_ms_total=float("inf"), e2e_sync_ms_total=float("inf"), e2e_steps=0, e2e_paths_agree=None)
     ms_total = reduce_max(torch, dist, world, device, res["ms_total"])
     e2e_ms_total = reduce_max(torch, dist, world, device, res["e2e_ms_total"])
     total_samples_step = res["samples_per_step"] * world

@@ -169,14 +169,16 @@ int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride,
     const size_t max_tiles = (size_t)((e->max_bytes / 2 + TILE - 1) / TILE);
     SDR_CK(e, cudaMalloc(&e->d_scratch[kind][par], (size_t)e->n * max_tiles * 32 * sizeof(float)));
   }
-  // time segments per channel: aim at ~18 worker warps per SM, keep segments >= 8 tiles
-  static const int nseg_env = getenv("SDR_AM_NSEG") ? atoi(getenv("SDR_AM_NSEG")) : 0;
-  uint32_t nseg = (uint32_t)((18L * e->n_sm + n_list - 1) / n_list);
-  if (nseg_env > 0) nseg = (uint32_t)nseg_env;
-  if (nseg > 8) nseg = 8;
-  while (nseg > 1 && (n_tiles + nseg - 1) / nseg < 8) --nseg;
-  if (nseg < 1) nseg = 1;
-  LaunchParams p;
+  // The launch's tiles are dealt out in equal shares to 48 worker warps per SM (12 CTAs of 4
+  // warps, of which 4-5 are resident at a time): shares small enough that SMs which also host
+  // the previous call's recurrence CTAs simply take fewer of them, large enough (>= 8 tiles)
+  // that the warm-up tiles stay in the noise. Measured: profiles/r01v5_am_sweep.txt.
+  static const int wps_env = getenv("SDR_AM_WARPS_PER_SM") ? atoi(getenv("SDR_AM_WARPS_PER_SM")) : 0;
+  const uint64_t total_tiles = (uint64_t)n_list * n_tiles;
+  uint64_t n_warps = (uint64_t)e->n_sm * (wps_env > 0 ? wps_env : 48);
+  n_warps = std::min<uint64_t>(n_warps, (total_tiles + 7) / 8);
+  n_warps = std::max<uint64_t>(n_warps, 1);
+  LaunchParams p = {};
   p.iq = iq;
   p.ch_stride = ch_stride;
   p.n_samples = n_samples;
@@ -191,11 +193,11 @@ int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride,
   p.pcm = e->d_pcm;
   p.pcm_stride = e->pcm_stride;
   p.lut = nullptr;
-  p.aux = nseg;
+  p.aux = (uint32_t)n_warps;
+  p.call_id = (uint32_t)(e->seq % 0x7fffffffull) + 1;
   p.scratch = e->d_scratch[kind][par];
   p.allowed = e->last_gated ? e->d_allowed[par] : nullptr;
-  const uint64_t warps = (uint64_t)n_list * nseg;
-  amssb_fir_kernel<SSB><<<(uint32_t)((warps + 3) / 4), 128, 4 * 2 * TILE_BYTES, e->stream>>>(p);
+  amssb_fir_kernel<SSB><<<(uint32_t)((n_warps + 3) / 4), 128, 4 * 2 * TILE_BYTES, e->stream>>>(p);
   SDR_CK(e, cudaGetLastError());
   e->launches++;
   return SDR_OK;
@@ -215,11 +217,20 @@ int launch_dc_block(sdr_engine *e, int kind, uint32_t n_samples) {
   p.scale = e->d_scale[kind];
   p.pcm = e->d_pcm;
   p.pcm_stride = e->pcm_stride;
-  p.aux = (uint32_t)nreg * 128;  // byte offset of the IIR tail in the state blob
+  p.aux = (uint32_t)nreg * 256;  // byte offset of the IIR tail in the state blob (after both carry buffers)
   p.scratch = e->d_scratch[kind][par];
   p.allowed = e->last_gated ? e->d_allowed[par] : nullptr;
-  SDR_CK(e, cudaFuncSetAttribute(dc_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM_BYTES));
-  dc_block_kernel<<<(n_list + 31) / 32, 32 * (1 + DC_HELPERS), DC_SMEM_BYTES, e->rec_stream>>>(p);
+  // Small banks: few CTAs, so each gets seven helper warps and the chain warp is never kept
+  // waiting; large banks: three helpers, so the many CTAs leave the FIR kernel its registers.
+  static const int helpers_env = getenv("SDR_DC_HELPERS") ? atoi(getenv("SDR_DC_HELPERS")) : 0;
+  const int helpers = helpers_env ? helpers_env : (n_list <= 32u * (uint32_t)e->n_sm ? 7 : 3);
+  if (helpers > 3) {
+    SDR_CK(e, cudaFuncSetAttribute(dc_block_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM_BYTES));
+    dc_block_kernel<7><<<(n_list + 31) / 32, 32 * 8, DC_SMEM_BYTES, e->rec_stream>>>(p);
+  } else {
+    SDR_CK(e, cudaFuncSetAttribute(dc_block_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM_BYTES));
+    dc_block_kernel<3><<<(n_list + 31) / 32, 32 * 4, DC_SMEM_BYTES, e->rec_stream>>>(p);
+  }
   SDR_CK(e, cudaGetLastError());
   e->launches++;
   return SDR_OK;
@@ -232,7 +243,7 @@ int launch_fm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_
   uint32_t G = e->shape[kind].G ? e->shape[kind].G : 4;  // worker warps per CTA; they never synchronise
   if (G > 4) G = 4;
   const int smem = (int)G * 2 * TILE_BYTES;
-  LaunchParams p;
+  LaunchParams p = {};
   p.iq = iq;
   p.ch_stride = ch_stride;
   p.n_samples = n_samples;
@@ -271,7 +282,7 @@ int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint3
   if (e->shape[kind].G) G = e->shape[kind].G;
   if (G > (uint32_t)T::MAX_WORKERS) G = T::MAX_WORKERS;
   const int smem = T::smem_bytes((int)G);
-  LaunchParams p;
+  LaunchParams p = {};
   p.iq = iq;
   p.ch_stride = ch_stride;
   p.n_samples = n_samples;

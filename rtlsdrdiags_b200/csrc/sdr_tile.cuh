@@ -40,6 +40,26 @@ __device__ __forceinline__ T roll_prev(T cur, T prev, int r, int lane) {
   return __shfl_sync(FULL, lane >= r ? prev : cur, (lane + r) & 31);
 }
 
+// shfl_prev with the source-lane choice done by one LOP3 on a precomputed lane mask
+// (all-ones where lane >= 32 - j) instead of ISETP + SEL: in a loop with many different j the
+// compiler runs out of predicate registers and recomputes the comparisons every tile.
+struct PrevMasks {
+  uint32_t m[8];  // m[j], j = 1..7
+  __device__ __forceinline__ void init(int lane) {
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+      m[j] = lane >= 32 - j ? 0xffffffffu : 0u;
+      asm volatile("" : "+r"(m[j]));  // keep it a register value, not a re-derived predicate
+    }
+    m[0] = 0;
+  }
+};
+__device__ __forceinline__ uint32_t shfl_prev_m(uint32_t cur, uint32_t prev, int j, int lane, const PrevMasks &pm) {
+  uint32_t v;
+  asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(v) : "r"(pm.m[j]), "r"(prev), "r"(cur));  // m ? prev : cur
+  return __shfl_sync(FULL, v, (lane - j) & 31);
+}
+
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
@@ -67,6 +87,42 @@ __device__ __forceinline__ void tile_read(const char *slot_base, int lane, uint3
     w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
   }
 }
+
+// The same fill and read for FULL tiles with every address computed once per warp: the lane's
+// shared addresses are loop invariants and the chunk offsets are immediates, so a tile costs
+// four LDGSTS and four LDS.128 plus a handful of integer instructions (the generic versions
+// above re-derive the swizzle and the shared window per tile: ~80 instructions).
+//   fill: chunk 32 j + lane lands in slot 32 j + (lane ^ ((lane >> 3) & 3))
+//   read: chunk 4 lane + j sits in slot 4 lane + (j ^ ((lane >> 1) & 3))
+struct TileIo {
+  uint32_t fill;    // shared address of the lane's chunk-0 destination in slot buffer 0
+  uint32_t rd[4];   // shared addresses of the lane's four chunks in slot buffer 0
+  __device__ __forceinline__ void init(const char *slots, int lane) {
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(slots);
+    fill = base + 16u * (uint32_t)(lane ^ ((lane >> 3) & 3));
+    const uint32_t x = (uint32_t)(lane >> 1) & 3u;
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) rd[j] = base + 64u * (uint32_t)lane + 16u * (j ^ x);
+  }
+  // g = the tile's first byte + 16 * lane; buf = 0 or TILE_BYTES
+  __device__ __forceinline__ void fill_full(uint32_t buf, const uint8_t *g) const {
+    const uint32_t s = fill + buf;
+    asm volatile(
+        "cp.async.cg.shared.global [%0], [%1], 16;\n\t"
+        "cp.async.cg.shared.global [%0+512], [%1+512], 16;\n\t"
+        "cp.async.cg.shared.global [%0+1024], [%1+1024], 16;\n\t"
+        "cp.async.cg.shared.global [%0+1536], [%1+1536], 16;" ::"r"(s), "l"(g)
+        : "memory");
+  }
+  __device__ __forceinline__ void read(uint32_t buf, uint32_t (&w)[16]) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(w[4 * j]), "=r"(w[4 * j + 1]), "=r"(w[4 * j + 2]), "=r"(w[4 * j + 3])
+                   : "r"(rd[j] + buf)
+                   : "memory");
+  }
+};
 
 // two (int16_t)float conversions with x86 wrap semantics, packed
 __device__ __forceinline__ uint32_t f2i16x2_wrap(float v0, float v1) {
@@ -107,8 +163,15 @@ __device__ __forceinline__ uint32_t pack_b2x4(int a0, int a1, int a2, int a3) {
 template <bool SSB>
 struct AmSsbTile {
   static constexpr int NREG = SSB ? 10 : 8;
-  // state blob: NREG words per lane, then (unused), y[n-1] of the DC-removal IIR
-  static constexpr int STATE_BYTES = NREG * 128 + 16;
+  // state blob: two carry buffers of NREG words per lane, then a 16-byte tail: word 1 = y[n-1] of the
+  // DC-removal IIR (dc_block_kernel's), word 2 = the VERSION word that says which carry buffer is
+  // current: bit 31 = buffer index, bits 0-30 = id of the call that wrote it. The FIR kernel
+  // reads a channel's carry and writes its new carry from different warps at unrelated times
+  // of one launch, so the new carry goes to the OTHER buffer; a reader that already finds this
+  // call's id in the version word takes the buffer the word does not name. All-zero = fresh.
+  static constexpr int CARRY_WORDS = NREG * 32;
+  static constexpr int TAIL_OFFSET = 2 * NREG * 128;
+  static constexpr int STATE_BYTES = TAIL_OFFSET + 16;
   static constexpr int WARMUP_TILES = SSB ? 2 : 1;  // see amssb_fir_kernel
 
   __device__ __forceinline__ static void load_carry(AmSsbCarry<SSB> &c, const uint32_t *blob, int lane) {
@@ -133,7 +196,10 @@ struct AmSsbTile {
   // recurrence warp consumes for this lane's PCM sample: the numerator of the DC-removal
   // filter, fl(x[n] - x[n-1]) (float bits), where x is the AM magnitude estimate or the
   // SSB phased sum. Updates the carry to this tile's registers rolled by r valid lanes.
-  __device__ __forceinline__ static uint32_t tile(const uint32_t (&w)[16], int fmt, bool lsb, AmSsbCarry<SSB> &pv, int lane, int r) {
+  // FULL_TILE: r == 32 is known at compile time (the hot loop); otherwise 1 <= r <= 32.
+  template <bool FULL_TILE = false>
+  __device__ __forceinline__ static uint32_t tile(const uint32_t (&w)[16], int fmt, bool lsb, AmSsbCarry<SSB> &pv, int lane, int r,
+                                                  const PrevMasks &pm) {
     AmSsbCarry<SSB> cu;
     uint32_t a[8], b[8];
 #pragma unroll
@@ -175,7 +241,7 @@ struct AmSsbTile {
     uint32_t q[8];
     q[7] = cu.p;
 #pragma unroll
-    for (int j = 1; j < 8; ++j) q[7 - j] = shfl_prev(cu.p, pv.p, j, lane);
+    for (int j = 1; j < 8; ++j) q[7 - j] = shfl_prev_m(cu.p, pv.p, j, lane, pm);
     int acc_i = 1 << 14, acc_q = 1 << 14;
     stage3<0>(q, acc_i, acc_q);
     cu.y3a = (int)(int16_t)(acc_i >> 15);
@@ -183,9 +249,10 @@ struct AmSsbTile {
 
     if constexpr (!SSB) {
       // magnitude estimate, tie -> q branch (AmDemodulator.cc:441-458)
-      const int im = (int)(int16_t)iabs(cu.y3a), qm = (int)(int16_t)iabs(cu.y3b);
-      const int mag = (int)(int16_t)(im > qm ? im + (qm >> 1) : qm + (im >> 1));
-      cu.dem = i2f(mag);
+      // |y3| <= 128 * 48394 / 32768 < 190 for 8-bit input, so none of the reference's int16 casts
+      // can bite and max + min/2 is the same whichever branch a tie takes
+      const int im = iabs(cu.y3a), qm = iabs(cu.y3b);
+      cu.dem = i2f(max(im, qm) + (min(im, qm) >> 1));
     } else {
       // phasing network (SsbDemodulator.cc:569-590): delay line {0 x15, -32768}, Hilbert 31 taps
       const int x15 = shfl_prev(cu.y3a, pv.y3a, 15, lane);
@@ -202,7 +269,7 @@ struct AmSsbTile {
     const uint32_t out = f2u(fadd(cu.dem, fmul(-1.0f, shfl_prev(cu.dem, pv.dem, 1, lane))));
 
     // the last 32 lanes of the stream become the next tile's "previous" registers
-    if (r == 32) {
+    if (FULL_TILE || r == 32) {
       pv = cu;
     } else {
       pv.a7 = roll_prev(cu.a7, pv.a7, r, lane); pv.b7 = roll_prev(cu.b7, pv.b7, r, lane);
@@ -239,14 +306,15 @@ struct AmSsbTile {
 
 // AM / SSB run as two kernels.
 //
-// amssb_fir_kernel: barrier-free worker warps, one per (channel, time segment). Everything up
-// to the numerator of the DC-removal filter is finite-memory, so a channel's launch can be cut
-// into `nseg` segments that run concurrently: a segment that does not start at tile 0 first
-// runs WARMUP tiles from an all-zero carry and discards their outputs, after which every
-// register the next tile reads from the carry is exact (AM: the carry of tile t is a function
-// of tile t's own lanes >= 22; SSB: the Hilbert history of lane 2 reaches five lanes into
-// the tile before, hence two tiles). Small banks (1024 channels = 7 per SM) get their
-// parallelism from nseg, large banks use nseg = 1.
+// amssb_fir_kernel: barrier-free worker warps. Everything up to the numerator of the
+// DC-removal filter is finite-memory, so a channel's block can be cut anywhere in time: a
+// warp that does not start at tile 0 first runs WARMUP tiles from an all-zero carry and
+// discards their outputs, after which every register the next tile reads from the carry is
+// exact (AM: the carry of tile t is a function of tile t's own lanes >= 22; SSB: the Hilbert
+// history of lane 2 reaches five lanes into the tile before, hence two tiles). The launch is
+// therefore treated as ONE sequence of tiles, cut into as many equal shares as the GPU holds
+// worker warps in a single wave: the load balance is exact for any bank size (1024 channels
+// or 8192) and there is no tail wave.
 //
 // dc_block_kernel: the sequential recurrence, lane == channel, over the numerators the FIR
 // kernel left in `scratch`. The engine launches it on a second stream, so it overlaps the
@@ -254,60 +322,99 @@ struct AmSsbTile {
 template <bool SSB>
 __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant__ LaunchParams p) {
   using T = AmSsbTile<SSB>;
-  constexpr uint32_t WARMUP = SSB ? 2 : 1;
+  constexpr uint32_t WARMUP = T::WARMUP_TILES;
   extern __shared__ uint4 smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t nseg = p.aux;
+  const uint32_t n_warps = p.aux;  // worker warps of the whole grid
   const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;
-  const uint32_t li = gw / nseg, seg = gw - li * nseg;
-  if (li >= p.n_list) return;
+  if (gw >= n_warps) return;
   const uint32_t n_tiles = (p.n_samples + TILE - 1) / TILE;
-  const uint32_t per = (n_tiles + nseg - 1) / nseg;
-  const uint32_t t0 = seg * per, t1 = min(n_tiles, t0 + per);
-  if (t0 >= t1) return;
-  const uint32_t tw = seg == 0 ? 0 : t0 - WARMUP;  // the host guarantees per >= WARMUP
+  // The launch is one sequence of n_list * n_tiles tiles (channel-major); warp gw takes the
+  // gw-th of n_warps equal shares of it, whatever channel boundaries fall inside.
+  const uint64_t total = (uint64_t)p.n_list * n_tiles;
+  uint64_t g0 = total * gw / n_warps;
+  const uint64_t g1 = total * (gw + 1) / n_warps;
 
   char *slots = reinterpret_cast<char *>(smem_raw) + warp * 2 * TILE_BYTES;
-  const uint32_t ch = p.chan_ids[li];
-  if (p.allowed && !p.allowed[ch]) return;  // squelched: the demodulator is not called, its state stays
-  const uint8_t *src = p.iq + (uint64_t)ch * p.ch_stride;
-  uint32_t *blob = reinterpret_cast<uint32_t *>(p.state + (uint64_t)ch * p.state_stride);
-  AmSsbCarry<SSB> pv;
-  if (seg == 0) {
-    T::load_carry(pv, blob, lane);
-  } else {
-    pv.a7 = pv.b7 = pv.s1a0 = pv.s1a1 = pv.s1b0 = pv.s1b1 = pv.p = 0;
-    pv.dem = 0.f;
-    pv.y3a = pv.y3b = 0;
-  }
-  const bool lsb = SSB && p.lsb[ch] != 0;
+  TileIo io;
+  io.init(slots, lane);
+  PrevMasks pm;
+  pm.init(lane);
   const int fmt = p.fmt;
-
-  // running pointers: the input tile to prefetch next and the scratch row to write
-  const uint8_t *gnext = src + (uint64_t)tw * TILE_BYTES;
-  float *sp = p.scratch + ((uint64_t)t0 * p.n_list + li) * 32 + lane;
   const uint64_t sp_step = (uint64_t)p.n_list * 32;
-  tile_fill(slots + (tw & 1) * TILE_BYTES, gnext, lane, (int)min((uint32_t)TILE, p.n_samples - tw * TILE) >> 3);
-  cp_async_commit();
-  for (uint32_t t = tw; t < t1; ++t) {
-    gnext += TILE_BYTES;
-    if (t + 1 < t1)
-      tile_fill(slots + ((t + 1) & 1) * TILE_BYTES, gnext, lane,
-                (int)min((uint32_t)TILE, p.n_samples - (t + 1) * TILE) >> 3);
+
+  while (g0 < g1) {
+    // the piece of one channel: tiles [t0, t1) of list entry li
+    const uint32_t li = (uint32_t)(g0 / n_tiles);
+    const uint32_t t0 = (uint32_t)(g0 - (uint64_t)li * n_tiles);
+    const uint32_t t1 = (uint32_t)min((uint64_t)n_tiles, t0 + (g1 - g0));
+    g0 += t1 - t0;
+    const uint32_t ch = p.chan_ids[li];
+    if (p.allowed && !p.allowed[ch]) continue;  // squelched: the demodulator is not called, its state stays
+    const uint8_t *src = p.iq + (uint64_t)ch * p.ch_stride;
+    uint32_t *blob = reinterpret_cast<uint32_t *>(p.state + (uint64_t)ch * p.state_stride);
+    // a piece that starts within WARMUP tiles of the block's head starts AT the head, from the
+    // carried state; any other starts WARMUP tiles early from an all-zero carry
+    const uint32_t tw = t0 <= WARMUP ? 0 : t0 - WARMUP;
+    AmSsbCarry<SSB> pv;
+    uint32_t *version = blob + T::TAIL_OFFSET / 4 + 2;  // tail words 0-1 belong to dc_block_kernel
+    if (tw == 0) {
+      const uint32_t v = *reinterpret_cast<volatile uint32_t *>(version);
+      const uint32_t cur = (v & 0x7fffffffu) == p.call_id ? (v >> 31) ^ 1u : v >> 31;
+      T::load_carry(pv, blob + cur * T::CARRY_WORDS, lane);
+    } else {
+      pv.a7 = pv.b7 = pv.s1a0 = pv.s1a1 = pv.s1b0 = pv.s1b1 = pv.p = 0;
+      pv.dem = 0.f;
+      pv.y3a = pv.y3b = 0;
+    }
+    const bool lsb = SSB && p.lsb[ch] != 0;
+
+    // Full tiles [tw, tf) go through the lean loop; a partial last tile of the block (any
+    // multiple of 32 samples) takes the generic path once.
+    const uint32_t partial = (t1 == n_tiles && (p.n_samples & (TILE - 1))) ? 1u : 0u;
+    const uint32_t tf = t1 - partial;
+    const uint8_t *g = src + (uint64_t)tw * TILE_BYTES + 16 * lane;  // the lane's chunk 0 of the tile to fetch next
+    // the scratch row of tile tw; rows of warm-up tiles are walked over but not written
+    float *sp = p.scratch + ((uint64_t)tw * p.n_list + li) * 32 + lane;
+    uint32_t buf = 0;
+    __syncwarp();  // the previous piece's last reads of the slot buffers are done
+    if (tw < tf) io.fill_full(buf, g);
+    else tile_fill(slots + buf, g - 16 * lane, lane, (int)(p.n_samples - tw * TILE) >> 3);
     cp_async_commit();
-    cp_async_wait<1>();
-    __syncwarp();
-    uint32_t w[16];
-    tile_read(slots + (t & 1) * TILE_BYTES, lane, w);
-    __syncwarp();  // slot t&1 may be refilled (tile t+2) once every lane has read it
-    const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
-    const uint32_t d = T::tile(w, fmt, lsb, pv, lane, r);
-    if (t >= t0) {
-      if (lane < r) *sp = u2f(d);
+    for (uint32_t t = tw; t < tf; ++t) {
+      g += TILE_BYTES;
+      if (t + 1 < tf) io.fill_full(buf ^ TILE_BYTES, g);
+      else if (partial) tile_fill(slots + (buf ^ TILE_BYTES), g - 16 * lane, lane, (int)(p.n_samples - (t + 1) * TILE) >> 3);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncwarp();
+      uint32_t w[16];
+      io.read(buf, w);
+      __syncwarp();  // this buffer may be refilled (tile t+2) once every lane has read it
+      const uint32_t d = T::template tile<true>(w, fmt, lsb, pv, lane, 32, pm);
+      if (t >= t0) *sp = u2f(d);
       sp += sp_step;
+      buf ^= TILE_BYTES;
+    }
+    if (partial) {
+      cp_async_wait<0>();
+      __syncwarp();
+      uint32_t w[16];
+      tile_read(slots + buf, lane, w);
+      const int r = (int)(p.n_samples - tf * TILE) >> 5;
+      const uint32_t d = T::template tile<false>(w, fmt, lsb, pv, lane, r, pm);
+      if (lane < r) *sp = u2f(d);  // tf >= t0 always
+    }
+    // Only the piece that ends the block leaves the channel's state: into the carry buffer
+    // that is not current, then it publishes the switch. Pieces that read the carry later in
+    // this launch recognise the call id and keep reading the old buffer.
+    if (t1 == n_tiles) {
+      const uint32_t nxt = (*reinterpret_cast<volatile uint32_t *>(version) >> 31) ^ 1u;
+      T::store_carry(pv, blob + nxt * T::CARRY_WORDS, lane);
+      __syncwarp();
+      if (lane == 0) *reinterpret_cast<volatile uint32_t *>(version) = (nxt << 31) | p.call_id;
     }
   }
-  if (t1 == n_tiles) T::store_carry(pv, blob, lane);
 }
 
 // y[n] = fl(d[n] - fl(-0.95f * y[n-1])), pcm[n] = (int16_t)(gain * y[n])
@@ -324,10 +431,10 @@ __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant
 constexpr int DC_STAGES = 8;
 constexpr int DC_ROW_BYTES = 144;  // 128 + 16: lane-per-row 128-bit accesses are bank-conflict free
 constexpr int DC_STAGE_BYTES = 32 * DC_ROW_BYTES;
-constexpr int DC_HELPERS = 3;
 constexpr int DC_SMEM_BYTES = (DC_STAGES + 2) * DC_STAGE_BYTES + 32 * 16;  // + gain and PCM-row tables
 
-__global__ void __launch_bounds__(32 * (1 + DC_HELPERS)) dc_block_kernel(const __grid_constant__ LaunchParams p) {
+template <int DC_HELPERS>
+__global__ void __launch_bounds__(32 * (1 + DC_HELPERS), DC_HELPERS > 3 ? 4 : 6) dc_block_kernel(const __grid_constant__ LaunchParams p) {
   extern __shared__ uint4 smem_raw[];
   char *ring = reinterpret_cast<char *>(smem_raw);            // DC_STAGES numerator tiles
   char *ybuf = ring + DC_STAGES * DC_STAGE_BYTES;             // two tiles of y
@@ -360,15 +467,27 @@ __global__ void __launch_bounds__(32 * (1 + DC_HELPERS)) dc_block_kernel(const _
     if (lane == 0) s_no_patch = ok;
   }
 
-  // helpers fill the ring: chunk q = (row, 16-byte piece) of a tile, 256 per tile
+  // helpers fill the ring: chunk q = (row, 16-byte piece) of a tile, 256 per tile; helper
+  // thread hid owns chunks hid and (for the first 32 threads) 224 + hid of every tile
   const int hid = (warp - 1) * 32 + lane;  // helper thread index, < 0 for the chain warp
+  constexpr int NH = 32 * DC_HELPERS;
+  constexpr int NQ = (256 + NH - 1) / NH;  // chunks per helper thread
+  bool fq[NQ];
+  uint32_t so[NQ];
+#pragma unroll
+  for (int i = 0; i < NQ; ++i) {
+    const int q = hid + i * NH;
+    fq[i] = hid >= 0 && q < 256 && (q >> 3) < rows;
+    so[i] = (uint32_t)((q >> 3) * DC_ROW_BYTES + 16 * (q & 7));
+  }
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(ring);
   auto fill = [&](uint32_t t) {
-    char *stage = ring + (t % DC_STAGES) * DC_STAGE_BYTES;
-    const float *ts = src + (uint64_t)t * tile_stride;
-    for (int q = hid; q < 256; q += 32 * DC_HELPERS) {
-      const int row = q >> 3, c = q & 7;
-      if (row < rows) cp_async16(stage + row * DC_ROW_BYTES + 16 * c, ts + row * 32 + 4 * c);
-    }
+    const uint32_t stage = ring_s + (t % DC_STAGES) * DC_STAGE_BYTES;
+    const float *ts = src + (uint64_t)t * tile_stride + 4 * hid;
+#pragma unroll
+    for (int i = 0; i < NQ; ++i)
+      if (fq[i])
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage + so[i]), "l"(ts + 4 * i * NH) : "memory");
   };
   if (warp > 0) {
 #pragma unroll 1
@@ -380,6 +499,18 @@ __global__ void __launch_bounds__(32 * (1 + DC_HELPERS)) dc_block_kernel(const _
   }
   __syncthreads();
   const bool no_patch = s_no_patch != 0;
+  // helper rows (warp - 1 + DC_HELPERS k): gain and PCM row pointer are loop invariants
+  constexpr int PER = (32 + DC_HELPERS - 1) / DC_HELPERS;
+  float hg[PER];
+  int16_t *hdst[PER];
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int row = warp - 1 + DC_HELPERS * k;
+    const bool ok = warp > 0 && row < rows;
+    hg[k] = ok ? gains[row] : 0.f;
+    hdst[k] = ok ? rowp[row] : nullptr;   // nullptr: squelched or past the list
+    if (hdst[k]) hdst[k] += lane;
+  }
 
   // iteration t: chain warp turns numerators of tile t into y; helpers store the PCM of tile
   // t-1 and make sure tile t+1 has landed
@@ -422,26 +553,18 @@ __global__ void __launch_bounds__(32 * (1 + DC_HELPERS)) dc_block_kernel(const _
       if (t >= 1) {
         const uint32_t tp = t - 1;
         const int r = (int)min((uint32_t)TILE, p.n_samples - tp * TILE) >> 5;
-        const char *yb = ybuf + (tp & 1) * DC_STAGE_BYTES;
-        constexpr int PER = (32 + DC_HELPERS - 1) / DC_HELPERS;
+        const char *yb = ybuf + (tp & 1) * DC_STAGE_BYTES + 4 * lane;
         // all loads first, then the conversions, then the stores: the rows are independent
         // and their shared-memory and conversion latencies must overlap
-        float yv[PER], g[PER];
-        int16_t *dst[PER];
+        float yv[PER];
+#pragma unroll
+        for (int k = 0; k < PER; ++k) yv[k] = lds<float>(yb + min(warp - 1 + DC_HELPERS * k, 31) * DC_ROW_BYTES);
+        const uint32_t col = tp * 32;
 #pragma unroll
         for (int k = 0; k < PER; ++k) {
-          const int row = min(warp - 1 + DC_HELPERS * k, 31);
-          yv[k] = lds<float>(yb + row * DC_ROW_BYTES + 4 * lane);
-          g[k] = gains[row];
-          dst[k] = rowp[row];
-        }
-        const uint32_t col = tp * 32 + lane;
-#pragma unroll
-        for (int k = 0; k < PER; ++k) {
-          const int row = warp - 1 + DC_HELPERS * k;
-          const float v = fmul(g[k], yv[k]);
+          const float v = fmul(hg[k], yv[k]);
           const int o = no_patch ? f2i_rz(v) : f2i16_wrap(v);
-          if (row < rows && lane < r && dst[k] != nullptr) dst[k][col] = (int16_t)o;
+          if (lane < r && hdst[k] != nullptr) hdst[k][col] = (int16_t)o;
         }
       }
       cp_async_wait<DC_STAGES - 2>();  // tile t+1 has landed before the chain warp asks for it
