@@ -47,7 +47,8 @@ struct LaunchParams {
   float *scratch;            // AM/SSB: IIR numerators between the FIR and the recurrence kernel,
                              // [tile][list index][32 lanes]
   const uint8_t *allowed;    // [n_channels] squelch gate of this call, or nullptr = all open
-  uint32_t call_id;          // AM/SSB: 31-bit id of this call, never 0 (versions the carry buffers)
+  uint32_t call_id;          // AM/SSB/FM: 31-bit id of this call, never 0 (versions the carry buffers)
+  const uint32_t *tab;       // FM: tensor-core tuner tables (fm_mma_table in sdr_engine.cu)
 };
 
 // ---------------------------------------------------------------------------
@@ -174,6 +175,74 @@ SDR_DEV int fir_s16_exact(const uint32_t (&w)[NW], int acc = 1 << 14) {
     return acc;
   }
 }
+// --- guarded path for windows in which the clamp IS reachable (some |x| > F::SAFE). A clamp
+// needs a prefix sum beyond 2^30, and the filters here carry most of their weight in a few
+// centre taps. So: the first HEAD taps, whose absolute sum is at most 8191, cannot clamp
+// whatever the data (16384 + 32768 * 8191 < 2^30) and are summed with IDP.2A; the middle taps
+// run in the reference's order with the clamp; and if the sum then leaves room for the worst
+// the remaining taps could add (|acc| <= 2^30 - 1 - 32768 * their absolute sum) the tail is
+// summed plainly too -- otherwise it takes the clamped loop. Bit-identical to fir_s16_exact.
+template <class F, int K0, int K1>
+struct TapRange {
+  static constexpr int N = F::N;
+  SDR_HD static constexpr int tap(int k) { return (k >= K0 && k < K1) ? F::tap(k) : 0; }
+};
+template <class F>
+struct Guard {
+  SDR_HD static constexpr int aabs(int v) { return v < 0 ? -v : v; }
+  SDR_HD static constexpr int head() {
+    int s = 0, k = 0;
+    while (k < F::N && s + aabs(F::tap(k)) <= 8191) { s += aabs(F::tap(k)); ++k; }
+    return k;
+  }
+  SDR_HD static constexpr int tail() {
+    int s = 0, k = F::N;
+    while (k > head() && s + aabs(F::tap(k - 1)) <= 6144) { s += aabs(F::tap(k - 1)); --k; }
+    return k;
+  }
+  SDR_HD static constexpr int tail_sum() {
+    int s = 0;
+    for (int k = tail(); k < F::N; ++k) s += aabs(F::tap(k));
+    return s;
+  }
+  static constexpr int HEAD = head(), TAIL = tail();
+  static constexpr int LIMIT = 0x3fffffff - 32768 * tail_sum();
+};
+template <class F, int P, int NW, int K, int KEND>
+SDR_DEV int fir_s16_exact_range(const uint32_t (&w)[NW], int acc) {
+  if constexpr (K < KEND) {
+    constexpr int pos = P - K;
+    constexpr int t = F::tap(K);
+    if constexpr (pos >= 0 && pos < 2 * NW) {
+      const int x = (pos & 1) ? ((int)w[pos / 2] >> 16) : (int)(int16_t)(w[pos / 2] & 0xffffu);
+      acc += t * x;
+      acc = acc > 0x3fffffff ? 0x3fffffff : acc;
+      acc = acc < -0x40000000 ? -0x40000000 : acc;
+    }
+    return fir_s16_exact_range<F, P, NW, K + 1, KEND>(w, acc);
+  } else {
+    return acc;
+  }
+}
+// head + clamped middle; the caller decides about the tail (warp-uniformly on the GPU)
+template <class F, int P, int NW>
+SDR_DEV int fir_s16_guard_mid(const uint32_t (&w)[NW]) {
+  int h = 0, l = 1 << 14;
+  fir_s16_acc<TapRange<F, 0, Guard<F>::HEAD>, P, NW>(w, h, l);
+  return fir_s16_exact_range<F, P, NW, Guard<F>::HEAD, Guard<F>::TAIL>(w, (h << 8) + l);
+}
+template <class F>
+SDR_DEV bool fir_s16_guard_tail_is_free(int acc) {
+  return acc <= Guard<F>::LIMIT && acc >= -Guard<F>::LIMIT;
+}
+template <class F, int P, int NW>
+SDR_DEV int fir_s16_guard_tail(const uint32_t (&w)[NW], int acc, bool clamped) {
+  if (clamped) return fir_s16_exact_range<F, P, NW, Guard<F>::TAIL, F::N>(w, acc);
+  int h = 0, l = 0;
+  fir_s16_acc<TapRange<F, Guard<F>::TAIL, F::N>, P, NW>(w, h, l);
+  return acc + (h << 8) + l;
+}
+
 template <class F, int P, int NW>
 SDR_DEV int fir_s16(const uint32_t (&w)[NW], bool exact) {
   if constexpr (F::SAFE >= 32768) {

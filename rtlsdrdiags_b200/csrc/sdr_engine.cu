@@ -60,6 +60,7 @@ struct sdr_engine {
   uint32_t *d_list[5] = {};
   uint8_t *d_lsb = nullptr;
   float *d_lut_fm = nullptr, *d_lut_wbfm = nullptr;
+  uint32_t *d_fm_tab = nullptr;  // tensor-core tuner tables, fm_mma_table()
   uint8_t *d_iq = nullptr;
   int16_t *d_pcm = nullptr;
   uint64_t pcm_stride = 0;
@@ -236,13 +237,83 @@ int launch_dc_block(sdr_engine *e, int kind, uint32_t n_samples) {
   return SDR_OK;
 }
 
+// Tables of the tensor-core tuner (FmTile::theta_mma): D = A * B with B = raw input bytes.
+// A[row][kk]: row p < 8 gives I' output p of a window, row 8 + p gives Q'; kk = 0..127 indexes
+// the raw bytes from 64 before the window's first byte to its last (sample j = floor((kk-64)/2),
+// I at even bytes). Output p is sum_k q[k] x'[4p + 3 - k] (Decimator_int16.cc:310-351) where x' is
+// the rotated sample (IqDataProcessor.cc:567-611): I' = I0, -Q1, -I2, Q3; Q' = Q0, I1, -Q2, -I3
+// by j mod 4 -- or plain I, Q for input that is already rotated. Each int16 tap is split as
+// 256 * hi + lo with both parts int8. The accumulators start at the rounding constant 1 << 14
+// (lo) and, for u8 input (u = s + 128), at -128 * sum of the row.
+// Layout per format: nine entries of [lane][4 words]: entries 0-7 the A fragments [hi/lo][k-step],
+// entry 8 the starts [hi row g, hi row g+8, lo row g, lo row g+8]; mma.m16n8k32 A fragment: word 0 =
+// (row g, k 4tq..4tq+3), 1 = (row g+8, same k), 2 = (row g, k+16), 3 = (row g+8, k+16).
+std::vector<uint32_t> fm_mma_table() {
+  std::vector<uint32_t> tab(2 * FM_TAB_WORDS_PER_FMT, 0);
+  for (int f = 0; f < 2; ++f) {
+    int A[16][128] = {};
+    for (int kk = 0; kk < 128; ++kk) {
+      const int j = (kk - 64) >> 1, c = kk & 1, jm = ((j % 4) + 4) % 4;
+      int arm, sign;  // which output arm this byte feeds and with what sign
+      if (f == 0) {
+        static const int arm_of[4][2] = {{0, 1}, {1, 0}, {0, 1}, {1, 0}};     // [jm][c]: 0 = I', 1 = Q'
+        static const int sign_of[4][2] = {{1, 1}, {1, -1}, {-1, -1}, {-1, 1}};
+        arm = arm_of[jm][c];
+        sign = sign_of[jm][c];
+      } else {
+        arm = c;
+        sign = 1;
+      }
+      for (int pp = 0; pp < 8; ++pp) {
+        const int k = 4 * pp + 3 - j;
+        if (k >= 0 && k < taps::FM_TUNER::N) A[8 * arm + pp][kk] = sign * taps::FM_TUNER::tap(k);
+      }
+    }
+    uint32_t *t = tab.data() + (size_t)f * FM_TAB_WORDS_PER_FMT;
+    auto part = [](int v, int h) {
+      const int lo = ((v + 128) & 255) - 128;
+      return h == 0 ? (v - lo) / 256 : lo;
+    };
+    for (int lane = 0; lane < 32; ++lane) {
+      const int g = lane >> 2, tq = lane & 3;
+      for (int h = 0; h < 2; ++h)
+        for (int s4 = 0; s4 < 4; ++s4)
+          for (int r = 0; r < 4; ++r) {
+            const int row = g + 8 * (r & 1), k0 = 32 * s4 + 16 * (r >> 1) + 4 * tq;
+            uint32_t w = 0;
+            for (int b = 0; b < 4; ++b) w |= (uint32_t)(uint8_t)(int8_t)part(A[row][k0 + b], h) << (8 * b);
+            t[((h * 4 + s4) * 32 + lane) * 4 + r] = w;
+          }
+      for (int i = 0; i < 4; ++i) {
+        const int h = i >> 1, row = g + 8 * (i & 1);
+        int sum = 0;
+        for (int kk = 0; kk < 128; ++kk) sum += part(A[row][kk], h);
+        int start = (h == 1 ? 1 << 14 : 0) - (f == 0 ? 128 * sum : 0);
+        t[(8 * 32 + lane) * 4 + i] = (uint32_t)start;
+      }
+    }
+  }
+  return tab;
+}
+
 int launch_fm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples, int fmt) {
   const int kind = SDR_KIND_FM;
   const uint32_t n_list = (uint32_t)e->list[kind].size();
   if (n_list == 0) return SDR_OK;
-  uint32_t G = e->shape[kind].G ? e->shape[kind].G : 4;  // worker warps per CTA; they never synchronise
-  if (G > 4) G = 4;
-  const int smem = (int)G * 2 * TILE_BYTES;
+  const uint32_t G = 4;  // worker warps per CTA; they never synchronise
+  const int smem = (int)G * FM_WARP_SMEM;
+  if (!e->d_fm_tab) {
+    const std::vector<uint32_t> tab = fm_mma_table();
+    SDR_CK(e, cudaMalloc(&e->d_fm_tab, tab.size() * 4));
+    SDR_CK(e, cudaMemcpy(e->d_fm_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+  }
+  // equal shares of the launch's tiles, as for AM/SSB (launch_amssb)
+  static const int wps_env = getenv("SDR_FM_WARPS_PER_SM") ? atoi(getenv("SDR_FM_WARPS_PER_SM")) : 0;
+  const uint32_t n_tiles = (n_samples + TILE - 1) / TILE;
+  const uint64_t total_tiles = (uint64_t)n_list * n_tiles;
+  uint64_t n_warps = (uint64_t)e->n_sm * (wps_env > 0 ? wps_env : 48);
+  n_warps = std::min<uint64_t>(n_warps, (total_tiles + 7) / 8);
+  n_warps = std::max<uint64_t>(n_warps, 1);
   LaunchParams p = {};
   p.iq = iq;
   p.ch_stride = ch_stride;
@@ -258,11 +329,18 @@ int launch_fm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_
   p.pcm = e->d_pcm;
   p.pcm_stride = e->pcm_stride;
   p.lut = e->d_lut_fm;
-  p.aux = 0;
+  p.aux = (uint32_t)n_warps;
+  p.call_id = (uint32_t)(e->seq % 0x7fffffffull) + 1;
+  p.tab = e->d_fm_tab;
   p.scratch = nullptr;
   p.allowed = e->last_gated ? e->d_allowed[e->seq & 1] : nullptr;
-  const uint32_t grid = (n_list + G - 1) / G;
-  fm_tile_kernel<<<grid, 32 * G, smem, e->stream>>>(p);
+  const uint32_t grid = (uint32_t)((n_warps + G - 1) / G);
+  static const int minb_env = getenv("SDR_FM_MIN_CTAS") ? atoi(getenv("SDR_FM_MIN_CTAS")) : 0;
+  switch (minb_env) {
+    case 5: fm_tile_kernel<5><<<grid, 32 * G, smem, e->stream>>>(p); break;
+    case 6: fm_tile_kernel<6><<<grid, 32 * G, smem, e->stream>>>(p); break;
+    default: fm_tile_kernel<4><<<grid, 32 * G, smem, e->stream>>>(p); break;
+  }
   SDR_CK(e, cudaGetLastError());
   e->launches++;
   return SDR_OK;
@@ -571,6 +649,7 @@ int sdr_engine_destroy(sdr_engine *e) {
   cudaFree(e->d_db_table);
   cudaFree(e->d_lsb);
   cudaFree(e->d_lut_fm);
+  cudaFree(e->d_fm_tab);
   cudaFree(e->d_lut_wbfm);
   cudaFree(e->d_iq);
   cudaFree(e->d_pcm);

@@ -576,36 +576,80 @@ __global__ void __launch_bounds__(32 * (1 + DC_HELPERS), DC_HELPERS > 3 ? 4 : 6)
 
 
 // ---------------------------------------------------------------------------
-// Narrow-band FM (FmDemodulator.cc): no recurrence anywhere, so a worker warp runs
-// the whole chain for its channel and stores PCM itself; the CTA never synchronises.
+// Narrow-band FM (FmDemodulator.cc): no recurrence anywhere, so a worker warp runs the whole
+// chain for its share of the launch's tiles and stores PCM itself; the CTA never synchronises.
+//
+// The 32-tap 4:1 tuner decimators (two thirds of the chain's multiply-adds) run on the tensor
+// cores as a warp-private Toeplitz GEMM, mma.sync m16n8k32 int8 (IMMA.16832):
+//   D[16 x 8] = A[16 x 128] * B[128 x 8]
+//   B column n = the 128 RAW input bytes that end with window n's own 64 (a window = one
+//     lane's 32 samples; the 64 bytes before it are the filter's history), fetched straight
+//     from the cp.async tile buffer with ldmatrix -- no de-interleave, no offset, no rotation;
+//   A row p (p < 8) = the taps that turn those bytes into I' output p of the window, row 8 + p
+//     the same for Q': the Fs/4 rotation, the I/Q de-interleave and the decimation are all in
+//     where the taps sit and which sign they carry. int16 taps = 256 * hi + lo, two int8
+//     matrices; the u8 offset (u = s + 128) is a per-row constant folded into the accumulator
+//     start together with the rounding constant 1 << 14. Tables: fm_mma_table() in the engine.
+// 32 IMMA replace 256 IDP.2A + the packed-byte front end + the window shuffles. One thing is
+// not linear: int8 negation leaves -128 alone (IqDataProcessor.cc:594-607), so a raw byte 0 in
+// a position the rotation negates would come out as +128. Such bytes (a clipping ADC) are
+// detected on the fragments already in registers and the tile takes the exact SIMT path.
 // ---------------------------------------------------------------------------
 struct FmCarry {
-  uint32_t a[7], b[7];  // the lane's rotation groups 1..7 (I' and Q' words): 28 samples of tuner history
   float th[4];          // theta of the lane's last four 64 kS/s samples
   uint32_t dw[4];       // the lane's eight discriminator outputs (int16 x 2 per word)
   uint32_t ew;          // the lane's two 16 kS/s samples (int16 x 2)
+  uint32_t hist;        // lanes 0-15: the last 64 raw input bytes (tuner history, logical order);
+                        // lanes 16, 17: the sticky clamp-path flags
 };
 
+constexpr int FM_HIST_BYTES = 64;                          // raw bytes of tuner history before a tile
+constexpr int FM_BUF_STRIDE = FM_HIST_BYTES + TILE_BYTES;  // [history | tile] twice per warp
+constexpr int FM_TH_STRIDE = 12;                           // words per window row of the theta transpose
+constexpr int FM_WARP_SMEM = 2 * FM_BUF_STRIDE + 32 * FM_TH_STRIDE * 4 + 64 * 4;  // + the audio ring
+// fm_mma_table(): per format nine entries of [lane][4 words]: the A fragments [hi/lo][k-step]
+// and the accumulator starts
+constexpr int FM_TAB_WORDS_PER_FMT = 9 * 32 * 4;
+
 struct FmTile {
-  static constexpr int NREG = 23;
-  // state blob: NREG words per lane, then two sticky clamp-path flags
-  static constexpr int STATE_BYTES = NREG * 128 + 16;
+  static constexpr int NREG = 10;
+  // state blob: two carry buffers of NREG words per lane (versioned like AM/SSB, see
+  // AmSsbTile), then a 16-byte tail whose word 2 is the version
+  static constexpr int CARRY_WORDS = NREG * 32;
+  static constexpr int TAIL_OFFSET = 2 * NREG * 128;
+  static constexpr int STATE_BYTES = TAIL_OFFSET + 16;
+  static constexpr int WARMUP_TILES = 1;
 
   __device__ __forceinline__ static void load_carry(FmCarry &c, const uint32_t *blob, int lane) {
 #pragma unroll
-    for (int i = 0; i < 7; ++i) { c.a[i] = blob[i * 32 + lane]; c.b[i] = blob[(7 + i) * 32 + lane]; }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { c.th[i] = u2f(blob[(14 + i) * 32 + lane]); c.dw[i] = blob[(18 + i) * 32 + lane]; }
-    c.ew = blob[22 * 32 + lane];
+    for (int i = 0; i < 4; ++i) { c.th[i] = u2f(blob[i * 32 + lane]); c.dw[i] = blob[(4 + i) * 32 + lane]; }
+    c.ew = blob[8 * 32 + lane];
+    c.hist = blob[9 * 32 + lane];
   }
   __device__ __forceinline__ static void store_carry(const FmCarry &c, uint32_t *blob, int lane) {
 #pragma unroll
-    for (int i = 0; i < 7; ++i) { blob[i * 32 + lane] = c.a[i]; blob[(7 + i) * 32 + lane] = c.b[i]; }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { blob[(14 + i) * 32 + lane] = f2u(c.th[i]); blob[(18 + i) * 32 + lane] = c.dw[i]; }
-    blob[22 * 32 + lane] = c.ew;
+    for (int i = 0; i < 4; ++i) { blob[i * 32 + lane] = f2u(c.th[i]); blob[(4 + i) * 32 + lane] = c.dw[i]; }
+    blob[8 * 32 + lane] = c.ew;
+    blob[9 * 32 + lane] = c.hist;
   }
 
+  // The raw history travels between calls in the format-independent form of the IQ dump
+  // (signed, rotated, interleaved), so all-zero means "no signal yet" as in a fresh reference
+  // object and a caller may change the input format between calls. Word `even` = bytes 0-3 of
+  // a rotation group (I0 Q0 I1 Q1), else bytes 4-7 (I2 Q2 I3 Q3). Wrapping int8 negation is
+  // its own inverse, so the round trip is exact.
+  __device__ __forceinline__ static uint32_t hist_to_state(uint32_t raw, int fmt, bool even) {
+    if (fmt != FMT_U8_OFFSET_ROTATE) return raw;
+    return even ? offset_and_negate(byte_perm(raw, 0u, 0x2310), 0x00ff0000u, 0x00010000u)    // I0 Q0 -Q1 I1
+                : offset_and_negate(byte_perm(raw, 0u, 0x2310), 0xff00ffffu, 0x01000101u);   // -I2 -Q2 Q3 -I3
+  }
+  __device__ __forceinline__ static uint32_t hist_from_state(uint32_t st, int fmt, bool even) {
+    if (fmt != FMT_U8_OFFSET_ROTATE) return st;
+    return even ? offset_and_negate(byte_perm(st, 0u, 0x2310), 0xff000000u, 0x01000000u)
+                : offset_and_negate(byte_perm(st, 0u, 0x2310), 0x00ffffffu, 0x00010101u);
+  }
+
+  // ---- exact SIMT tuner (tiles with a clipping byte, and the reference for the GEMM) ----
   template <int M>
   __device__ __forceinline__ static int tuner_one(const uint32_t (&ext)[15]) {
     const uint32_t w[8] = {ext[M], ext[M + 1], ext[M + 2], ext[M + 3], ext[M + 4], ext[M + 5], ext[M + 6], ext[M + 7]};
@@ -621,6 +665,129 @@ struct FmTile {
       tuner_all<M + 1>(ea, eb, lut, th);
     }
   }
+  // window `win` (-1 = the history) of the tile buffer: its 64 raw bytes in logical order
+  __device__ __forceinline__ static void read_window(const char *buf, int win, uint32_t (&w)[16]) {
+    const int x = (win >> 1) & 3;  // -1 -> 3: the history is kept in window 31's physical order
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const u32x4 v = lds_u4(buf + 64 * win + 16 * (j ^ x));
+      w[4 * j] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+    }
+  }
+  __device__ __noinline__ static void theta_simt(const char *buf, int fmt, const float *lut, int lane, float (&th)[8]) {
+    uint32_t w[16], a[8], b[8], ea[15], eb[15];
+    read_window(buf, lane - 1, w);
+#pragma unroll
+    for (int g = 1; g < 8; ++g) front_end_group(fmt, w[2 * g], w[2 * g + 1], ea[g - 1], eb[g - 1]);
+    read_window(buf, lane, w);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) front_end_group(fmt, w[2 * g], w[2 * g + 1], a[g], b[g]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { ea[7 + i] = a[i]; eb[7 + i] = b[i]; }
+    tuner_all<0>(ea, eb, lut, th);
+  }
+
+  // ---- tensor-core tuner ----
+  // Per-lane constants. The A fragments (32 words per lane) stay in shared memory, one
+  // LDS.128 per fragment and use, so that six CTAs fit an SM: the chain is latency bound
+  // (table gathers, shared-memory hand-overs, votes) and lives on occupancy.
+  struct Mma {
+    uint32_t tab_s;       // shared address of this lane's first A fragment ([hi/lo][k-step] 512 B apart)
+    uint32_t rel0, rel1;  // ldmatrix row address of this lane for K bytes 0-63 / 64-127 of N-tile 0
+    uint32_t zmask;       // which bytes of this lane's B words sit in negated positions
+    __device__ __forceinline__ void init(const uint32_t *tab_smem, int lane) {
+      tab_s = (uint32_t)__cvta_generic_to_shared(tab_smem) + 16u * (uint32_t)lane;
+      const int row = lane & 7, i = lane >> 3;
+      rel1 = (uint32_t)(64 * row + 16 * (i ^ ((row >> 1) & 3)));
+      rel0 = (uint32_t)(64 * (row - 1) + 16 * (i ^ (((row - 1) >> 1) & 3)));  // row 0: the window before
+      zmask = (lane & 1) ? 0x00808080u : 0x80000000u;  // tq odd: group bytes 4,5,6; even: byte 3
+    }
+  };
+  __device__ __forceinline__ static void lds128(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+  }
+  template <bool U8>
+  __device__ __forceinline__ static void imma(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    if constexpr (U8)
+      asm("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+          : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+          : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else
+      asm("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+          : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+          : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+  __device__ __forceinline__ static void ldmatrix4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr)
+                 : "memory");
+  }
+  // theta of the tile's 256 tuner outputs, left in `thbuf` (row = window, FM_TH_STRIDE words).
+  // buf_s = shared address of the tile buffer (its history sits in the 64 bytes before it).
+  // Returns false, with nothing written, if a raw byte 0 sits where the rotation negates.
+  template <bool U8>
+  __device__ __forceinline__ static bool theta_mma(uint32_t buf_s, const Mma &m, const float *lut, float *thbuf, int lane) {
+    const int g = lane >> 2, tq = lane & 3;
+    uint32_t z = 0;
+    float th[4][2];
+    uint32_t c0[4];  // accumulator starts: hi row g, hi row g+8, lo row g, lo row g+8
+    lds128(m.tab_s + 8 * 512, c0);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {  // two N-tiles (8 windows each) at a time: their MMA chains interleave
+      uint32_t b[2][2][4];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        ldmatrix4(buf_s + m.rel0 + 512 * (2 * half + cc), b[cc][0]);
+        ldmatrix4(buf_s + m.rel1 + 512 * (2 * half + cc), b[cc][1]);
+      }
+      if constexpr (U8) {  // zero-byte test: every window's own bytes, and the history before window 0
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) z |= (b[cc][1][i] - 0x01010101u) & ~b[cc][1][i];
+        if (half == 0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) z |= (b[0][0][i] - 0x01010101u) & ~b[0][0][i];
+        }
+      }
+      int hi[2][4], lo[2][4];
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc) {
+        hi[cc][0] = hi[cc][1] = (int)c0[0]; hi[cc][2] = hi[cc][3] = (int)c0[1];
+        lo[cc][0] = lo[cc][1] = (int)c0[2]; lo[cc][2] = lo[cc][3] = (int)c0[3];
+      }
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        uint32_t ahi[4], alo[4];
+        lds128(m.tab_s + s * 512, ahi);
+        lds128(m.tab_s + (4 + s) * 512, alo);
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          imma<U8>(hi[cc], ahi, b[cc][s >> 1][2 * (s & 1)], b[cc][s >> 1][2 * (s & 1) + 1]);
+          imma<U8>(lo[cc], alo, b[cc][s >> 1][2 * (s & 1)], b[cc][s >> 1][2 * (s & 1) + 1]);
+        }
+      }
+      // (int16_t)(acc >> 15), acc = 256 hi + lo: I' of windows 8c+2tq, +1 in [0],[1]; Q' in [2],[3]
+#pragma unroll
+      for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int yi = (256 * hi[cc][e] + lo[cc][e]) >> 15, yq = (256 * hi[cc][2 + e] + lo[cc][2 + e]) >> 15;
+          th[2 * half + cc][e] = ld_lut(lut + (yq - FM_LUT_MIN) * FM_LUT_DIM + (yi - FM_LUT_MIN));
+        }
+    }
+    if constexpr (U8) {
+      if (__any_sync(FULL, (z & m.zmask) != 0)) return false;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      thbuf[(8 * c + 2 * tq) * FM_TH_STRIDE + g] = th[c][0];
+      thbuf[(8 * c + 2 * tq + 1) * FM_TH_STRIDE + g] = th[c][1];
+    }
+    return true;
+  }
+
   template <int J>
   __device__ __forceinline__ static void gather_e(uint32_t (&e)[20], uint32_t cur, uint32_t prev, int lane) {
     if constexpr (J <= 19) {
@@ -629,28 +796,11 @@ struct FmTile {
     }
   }
 
-  // One tile. big_a / big_b: sticky "clamp reachable" flags of the previous tile
-  // (in) and of this tile (out). Returns the lane's PCM sample.
-  __device__ __forceinline__ static int tile(const uint32_t (&w)[16], int fmt, float k, const float *lut, FmCarry &pv,
-                                             int lane, int r, bool &big_a, bool &big_b) {
+  // Everything after the tuner, from the lane's eight theta. big_a / big_b: sticky "clamp
+  // reachable" flags of the previous tile (in) and of this tile (out). Returns the lane's PCM.
+  __device__ __forceinline__ static int tile(const float (&th)[8], float k, FmCarry &pv, int lane, int r, bool &big_a,
+                                             bool &big_b, uint32_t *ering) {
     FmCarry cu;
-    uint32_t a[8], b[8];
-#pragma unroll
-    for (int g = 0; g < 8; ++g) front_end_group(fmt, w[2 * g], w[2 * g + 1], a[g], b[g]);
-#pragma unroll
-    for (int i = 0; i < 7; ++i) { cu.a[i] = a[i + 1]; cu.b[i] = b[i + 1]; }
-
-    // tuner decimators: 32 taps, 4:1. Output m uses rotation groups m-7 .. m.
-    uint32_t ea[15], eb[15];
-#pragma unroll
-    for (int i = 0; i < 7; ++i) {
-      ea[i] = shfl_prev(cu.a[i], pv.a[i], 1, lane);
-      eb[i] = shfl_prev(cu.b[i], pv.b[i], 1, lane);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { ea[7 + i] = a[i]; eb[7 + i] = b[i]; }
-    float th[8];
-    tuner_all<0>(ea, eb, lut, th);
 #pragma unroll
     for (int i = 0; i < 4; ++i) cu.th[i] = th[4 + i];
 
@@ -660,13 +810,30 @@ struct FmTile {
     for (int i = 0; i < 4; ++i) te[i] = shfl_prev(cu.th[i], pv.th[i], 1, lane);
 #pragma unroll
     for (int i = 0; i < 8; ++i) te[4 + i] = th[i];
-    int d[8];
-    bool big = false;
+    // A quiet channel (a carrier that deviates a few kHz) never leaves (-pi, pi), and with the
+    // default gains k * pi stays far below 2^31: both the FP64 wrap and the conversion's range
+    // patch are skipped unless some lane of the warp needs them (one vote per tile).
+    float df[8];
+    float dmax = 0.f;
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
-      d[m] = f2i16_wrap(fmul(k, wrap_pi(fsub(te[m + 2], te[m]))));
-      big |= iabs(d[m]) > taps::FM_POST::SAFE;
+      df[m] = fsub(te[m + 2], te[m]);
+      dmax = fmaxf(dmax, fabsf(df[m]));
     }
+    const bool wraps = __any_sync(FULL, dmax >= 3.14159274101257324f);
+    const bool patch = !(fabsf(k) < 3.0e8f);  // |k * dtheta| <= |k| * 2 pi < 2^31: cvt.rzi cannot saturate
+    int d[8];
+    if (wraps || patch) {  // warp-uniform: a real branch, so the quiet path executes none of it
+#pragma unroll
+      for (int m = 0; m < 8; ++m) d[m] = f2i16_wrap(fmul(k, wrap_pi(df[m])));
+    } else {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) d[m] = (int)(int16_t)f2i_rz(fmul(k, df[m]));
+    }
+    int dabs = 0;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) dabs = max(dabs, iabs(d[m]));
+    const bool big = dabs > taps::FM_POST::SAFE;
 #pragma unroll
     for (int i = 0; i < 4; ++i) cu.dw[i] = pack_i16x2(d[2 * i], d[2 * i + 1]);
     const bool cur_a = __any_sync(FULL, big && lane < r);
@@ -691,22 +858,31 @@ struct FmTile {
         __any_sync(FULL, (iabs(e0) > taps::AUDIO40::SAFE || iabs(e1) > taps::AUDIO40::SAFE) && lane < r);
     const bool exact_b = cur_b || big_b;
 
-    // audio decimator: 40 taps, 2:1: the lane's two samples and the 19 lanes below
+    // audio decimator: 40 taps, 2:1: the lane's two samples and the 19 lanes below, through the
+    // warp's 64-word ring in shared memory (previous tile's 32 words, then this tile's): one
+    // store and twenty conflict-free loads instead of nineteen select-and-shuffle pairs
+    ering[32 + lane] = cu.ew;
+    __syncwarp();
     uint32_t ee[20];
-    ee[19] = cu.ew;
-    gather_e<1>(ee, cu.ew, pv.ew, lane);
-    const int pcm = (int)(int16_t)(fir_s16<taps::AUDIO40, 39, 20>(ee, exact_b) >> 15);
+#pragma unroll
+    for (int i = 0; i < 20; ++i) ee[i] = ering[13 + lane + i];
+    int acc;
+    if (!exact_b) {
+      acc = fir_s16_fast<taps::AUDIO40, 39, 20>(ee);
+    } else {
+      acc = fir_s16_guard_mid<taps::AUDIO40, 39, 20>(ee);
+      const bool clamped = __any_sync(FULL, !fir_s16_guard_tail_is_free<taps::AUDIO40>(acc));
+      acc = fir_s16_guard_tail<taps::AUDIO40, 39, 20>(ee, acc, clamped);
+    }
+    const int pcm = (int)(int16_t)(acc >> 15);
 
     big_a = cur_a || (r < 32 && big_a);
     big_b = cur_b || (r < 32 && big_b);
     if (r == 32) {
-      pv = cu;
-    } else {
 #pragma unroll
-      for (int i = 0; i < 7; ++i) {
-        pv.a[i] = roll_prev(cu.a[i], pv.a[i], r, lane);
-        pv.b[i] = roll_prev(cu.b[i], pv.b[i], r, lane);
-      }
+      for (int i = 0; i < 4; ++i) { pv.th[i] = cu.th[i]; pv.dw[i] = cu.dw[i]; }
+      pv.ew = cu.ew;
+    } else {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         pv.th[i] = roll_prev(cu.th[i], pv.th[i], r, lane);
@@ -714,52 +890,133 @@ struct FmTile {
       }
       pv.ew = roll_prev(cu.ew, pv.ew, r, lane);
     }
+    __syncwarp();
+    ering[lane] = pv.ew;  // the next tile's "previous" words
     return pcm;
   }
 };
 
-// every warp is a worker; blockDim = 32 * workers
-__global__ void __launch_bounds__(128, 4) fm_tile_kernel(const __grid_constant__ LaunchParams p) {
+// Every warp is a worker. As in amssb_fir_kernel the launch is one channel-major sequence of
+// tiles dealt out in equal shares: the chain has finite memory (the 40-tap audio decimator
+// looks 20 lanes back, everything before it less), so a share that starts inside a block warms
+// up on the tile before it; a share that starts within a tile of the head starts at the head.
+template <int MIN_CTAS>
+__global__ void __launch_bounds__(128, MIN_CTAS) fm_tile_kernel(const __grid_constant__ LaunchParams p) {
   extern __shared__ uint4 smem_raw[];
+  __shared__ uint4 s_tab[FM_TAB_WORDS_PER_FMT / 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nw = (int)(blockDim.x >> 5);
-  const uint32_t li = blockIdx.x * (uint32_t)nw + warp;
-  if (li >= p.n_list) return;
-  char *slots = reinterpret_cast<char *>(smem_raw) + warp * 2 * TILE_BYTES;
-  const uint32_t ch = p.chan_ids[li];
-  if (p.allowed && !p.allowed[ch]) return;  // squelched
-  const uint8_t *src = p.iq + (uint64_t)ch * p.ch_stride;
-  uint32_t *blob = reinterpret_cast<uint32_t *>(p.state + (uint64_t)ch * p.state_stride);
-  FmCarry pv;
-  FmTile::load_carry(pv, blob, lane);
-  bool big_a = blob[FmTile::NREG * 32] != 0, big_b = blob[FmTile::NREG * 32 + 1] != 0;
-  const float k = p.scale[ch];
-  const int fmt = p.fmt;
-  const uint32_t n_tiles = (p.n_samples + TILE - 1) / TILE;
-  int16_t *out = p.pcm + (uint64_t)ch * p.pcm_stride;
-
-  tile_fill(slots, src, lane, (int)min((uint32_t)TILE, p.n_samples) >> 3);
-  cp_async_commit();
-  for (uint32_t t = 0; t < n_tiles; ++t) {
-    if (t + 1 < n_tiles) {
-      const uint32_t s1 = (t + 1) * TILE;
-      tile_fill(slots + ((t + 1) & 1) * TILE_BYTES, src + (uint64_t)s1 * 2, lane,
-                (int)min((uint32_t)TILE, p.n_samples - s1) >> 3);
-    }
-    cp_async_commit();
-    cp_async_wait<1>();
-    __syncwarp();
-    uint32_t w[16];
-    tile_read(slots + (t & 1) * TILE_BYTES, lane, w);
-    __syncwarp();  // slot t&1 may be refilled (tile t+2) once every lane has read it
-    const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
-    const int pcm = FmTile::tile(w, fmt, k, p.lut, pv, lane, r, big_a, big_b);
-    if (lane < r) out[(uint64_t)t * 32 + lane] = (int16_t)pcm;
+  {
+    const uint4 *src4 = reinterpret_cast<const uint4 *>(p.tab + (p.fmt == FMT_U8_OFFSET_ROTATE ? 0 : FM_TAB_WORDS_PER_FMT));
+    for (int i = threadIdx.x; i < FM_TAB_WORDS_PER_FMT / 4; i += blockDim.x) s_tab[i] = src4[i];
   }
-  FmTile::store_carry(pv, blob, lane);
-  if (lane == 0) {
-    blob[FmTile::NREG * 32] = big_a;
-    blob[FmTile::NREG * 32 + 1] = big_b;
+  __syncthreads();
+  const uint32_t n_warps = p.aux;
+  const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (gw >= n_warps) return;
+  const uint32_t n_tiles = (p.n_samples + TILE - 1) / TILE;
+  const uint64_t total = (uint64_t)p.n_list * n_tiles;
+  uint64_t g0 = total * gw / n_warps;
+  const uint64_t g1 = total * (gw + 1) / n_warps;
+
+  char *wbase = reinterpret_cast<char *>(smem_raw) + warp * FM_WARP_SMEM;
+  char *buf0 = wbase + FM_HIST_BYTES;  // tile buffers at buf0 and buf0 + FM_BUF_STRIDE
+  float *thbuf = reinterpret_cast<float *>(wbase + 2 * FM_BUF_STRIDE);
+  uint32_t *ering = reinterpret_cast<uint32_t *>(wbase + 2 * FM_BUF_STRIDE + 32 * FM_TH_STRIDE * 4);
+  TileIo io;
+  io.init(buf0, lane);
+  const uint32_t buf0_s = (uint32_t)__cvta_generic_to_shared(buf0);
+  const int fmt = p.fmt;
+  FmTile::Mma mm;
+  mm.init(reinterpret_cast<const uint32_t *>(s_tab), lane);
+  constexpr uint32_t WARMUP = FmTile::WARMUP_TILES;
+
+  while (g0 < g1) {
+    const uint32_t li = (uint32_t)(g0 / n_tiles);
+    const uint32_t t0 = (uint32_t)(g0 - (uint64_t)li * n_tiles);
+    const uint32_t t1 = (uint32_t)min((uint64_t)n_tiles, t0 + (g1 - g0));
+    g0 += t1 - t0;
+    const uint32_t ch = p.chan_ids[li];
+    if (p.allowed && !p.allowed[ch]) continue;  // squelched
+    const uint8_t *src = p.iq + (uint64_t)ch * p.ch_stride;
+    uint32_t *blob = reinterpret_cast<uint32_t *>(p.state + (uint64_t)ch * p.state_stride);
+    uint32_t *tail = blob + FmTile::TAIL_OFFSET / 4;
+    const uint32_t tw = t0 <= WARMUP ? 0 : t0 - WARMUP;
+    FmCarry pv;
+    bool big_a = false, big_b = false;
+    __syncwarp();  // the previous piece is done with the buffers
+    uint32_t off = 0;  // byte offset of the current tile buffer: 0 or FM_BUF_STRIDE
+    if (tw == 0) {
+      const uint32_t v = *reinterpret_cast<volatile uint32_t *>(tail + 2);
+      const uint32_t cur = (v & 0x7fffffffu) == p.call_id ? (v >> 31) ^ 1u : v >> 31;
+      FmTile::load_carry(pv, blob + cur * FmTile::CARRY_WORDS, lane);
+      big_a = __shfl_sync(FULL, pv.hist, 16) != 0;
+      big_b = __shfl_sync(FULL, pv.hist, 17) != 0;
+      // raw history of the block's head, into window 31's physical order (chunk i at i ^ 3)
+      if (lane < 16)
+        *reinterpret_cast<uint32_t *>(buf0 - 64 + 16 * ((lane >> 2) ^ 3) + 4 * (lane & 3)) =
+            FmTile::hist_from_state(pv.hist, fmt, (lane & 1) == 0);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { pv.th[i] = 0.f; pv.dw[i] = 0; }
+      pv.ew = 0;
+      pv.hist = 0;
+      // the history of the warm-up tile only feeds outputs that are thrown away
+      if (lane < 16) *reinterpret_cast<uint32_t *>(buf0 - 64 + 4 * lane) = 0x80808080u;
+    }
+    ering[lane] = pv.ew;
+    const float k = p.scale[ch];
+    int16_t *out = p.pcm + (uint64_t)ch * p.pcm_stride;
+    const uint32_t partial = (t1 == n_tiles && (p.n_samples & (TILE - 1))) ? 1u : 0u;
+    const uint32_t tf = t1 - partial;
+    const uint8_t *g = src + (uint64_t)tw * TILE_BYTES + 16 * lane;
+    if (tw < tf) io.fill_full(off, g);
+    else tile_fill(buf0 + off, g - 16 * lane, lane, (int)(p.n_samples - tw * TILE) >> 3);
+    cp_async_commit();
+    for (uint32_t t = tw; t < t1; ++t) {
+      const uint32_t nxt = FM_BUF_STRIDE - off;
+      g += TILE_BYTES;
+      if (t + 1 < tf) io.fill_full(nxt, g);
+      else if (t + 1 < t1) tile_fill(buf0 + nxt, g - 16 * lane, lane, (int)(p.n_samples - (t + 1) * TILE) >> 3);
+      cp_async_commit();
+      cp_async_wait<1>();
+      __syncwarp();
+      const int r = (int)min((uint32_t)TILE, p.n_samples - t * TILE) >> 5;
+      bool ok = r == 32;  // a partial tile (stale bytes behind the data) takes the SIMT path
+      if (ok) {
+        ok = fmt == FMT_U8_OFFSET_ROTATE ? FmTile::theta_mma<true>(buf0_s + off, mm, p.lut, thbuf, lane)
+                                         : FmTile::theta_mma<false>(buf0_s + off, mm, p.lut, thbuf, lane);
+      }
+      float th[8];
+      if (ok) {
+        __syncwarp();
+        const u32x4 v0 = lds_u4(thbuf + lane * FM_TH_STRIDE), v1 = lds_u4(thbuf + lane * FM_TH_STRIDE + 4);
+        th[0] = u2f(v0.x); th[1] = u2f(v0.y); th[2] = u2f(v0.z); th[3] = u2f(v0.w);
+        th[4] = u2f(v1.x); th[5] = u2f(v1.y); th[6] = u2f(v1.z); th[7] = u2f(v1.w);
+      } else {
+        FmTile::theta_simt(buf0 + off, fmt, p.lut, lane, th);
+      }
+      // the next tile's history: this tile's last valid window, physical order kept
+      if (lane < 16) {
+        const int last = r - 1;
+        const uint32_t wv = *reinterpret_cast<const uint32_t *>(buf0 + off + 64 * last + 16 * ((lane >> 2) ^ ((last >> 1) & 3)) +
+                                                                4 * (lane & 3));
+        *reinterpret_cast<uint32_t *>(buf0 + nxt - 64 + 16 * ((lane >> 2) ^ 3) + 4 * (lane & 3)) = wv;
+        pv.hist = wv;  // raw, logical order: chunk lane >> 2, word lane & 3
+      }
+      __syncwarp();  // buffer `off` may be refilled (tile t+2), thbuf rewritten
+      const int pcm = FmTile::tile(th, k, pv, lane, r, big_a, big_b, ering);
+      if (t >= t0 && lane < r) out[(uint64_t)t * 32 + lane] = (int16_t)pcm;
+      off = nxt;
+    }
+    if (t1 == n_tiles) {
+      const uint32_t nv = (*reinterpret_cast<volatile uint32_t *>(tail + 2) >> 31) ^ 1u;
+      if (lane < 16) pv.hist = FmTile::hist_to_state(pv.hist, fmt, (lane & 1) == 0);
+      if (lane == 16) pv.hist = big_a;
+      if (lane == 17) pv.hist = big_b;
+      FmTile::store_carry(pv, blob + nv * FmTile::CARRY_WORDS, lane);
+      __syncwarp();
+      if (lane == 0) *reinterpret_cast<volatile uint32_t *>(tail + 2) = (nv << 31) | p.call_id;
+    }
   }
 }
 

@@ -195,3 +195,47 @@ def test_channel_permutation_and_duplicates():
     pcm, _ = e.demodulate(iq)
     for ch in range(5, n):
         assert np.array_equal(pcm[ch], pcm[ch % 5])
+
+
+@pytest.mark.parametrize("fmt", ["u8", "s8"])
+def test_fm_tensor_core_tuner_and_clipping_fallback(fmt):
+    """NBFM's tuner decimators run as an int8 Toeplitz GEMM on the tensor cores unless a raw
+    byte 0 sits where the Fs/4 rotation negates (-(-128) = -128 is not linear); then the tile
+    takes the SIMT path. Clean tone input (GEMM path), the same with clipping bytes sprinkled
+    into some tiles (mixed paths within one stream), block sizes that leave partial tiles, the
+    signed/rotated input format, and state carried across calls: all bit-exact."""
+    import rtlsdrdiags_b200 as R
+    n, nbytes = 6, 3 * 32768
+    rng = np.random.default_rng(99)
+    iq = np.stack([S.tone(2, nbytes // 2, seed=40 + ch) for ch in range(n)])
+    assert iq.min() > 0                      # no clipping anywhere: GEMM path only
+    # channel 1: zeros at negated positions (group bytes 3..6) of a few tiles
+    for pos in (3, 2048 * 5 + 4, 2048 * 5 + 13, 2048 * 17 + 2046, 2048 * 30 + 6, nbytes - 3):
+        iq[1, pos] = 0
+    # channel 2: zeros only at positions the rotation does not negate, and 255s
+    for pos in (0, 1, 2, 7, 2048 * 9 + 8, 2048 * 9 + 15):
+        iq[2, pos] = 0
+    iq[2, 5000:5032] = 255
+    # channel 3: a burst of clipping across a tile boundary (history of the next tile)
+    iq[3, 2048 * 11 - 40:2048 * 11 + 8] = 0
+    # channel 4: noise in the middle of a tone
+    iq[4, 30000:50000] = rng.integers(0, 256, 20000, dtype=np.uint8)
+    e = R.Engine(n, 0, nbytes)
+    e.set_modes(np.full(n, 2, dtype=np.uint8))
+    chains = []
+    for ch in range(n):
+        c = O.OracleChain()
+        c.set_mode(2)
+        chains.append(c)
+    cuts = [0, 32768, 32768 + 2048 * 3 + 64, 32768 * 2 + 640, nbytes]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        piece = np.ascontiguousarray(iq[:, a:b])
+        if fmt == "u8":
+            e.accept_iq_host(piece)
+        else:
+            e.accept_iq_host(np.stack([O.front_end(piece[ch]) for ch in range(n)]), R.IQ_S8_ROTATED)
+        pcm, counts = e.get_pcm()
+        for ch in range(n):
+            want = chains[ch].accept_u8(piece[ch])
+            assert counts[ch] == want.size
+            assert np.array_equal(pcm[ch][:counts[ch]], want), (fmt, a, ch)
