@@ -185,10 +185,12 @@ def bench_one(torch, R, synth, workload, channels, n_blocks, steps, warmup, sign
         return a, b
 
     # ---- device-resident: the kernel(s) alone ----
-    a, b = timed(max(warmup, 3))
+    a, b = timed(max(warmup, 3))  # untimed warm-up: includes the engine's lazy allocations
     barrier()
     if steps <= 0:  # auto: about two seconds of device time, identical on every rank
-        per = reduce_max(torch, dist, world, device, a.elapsed_time(b) / max(warmup, 3))
+        a, b = timed(20)          # calibration on the warmed-up engine
+        barrier()
+        per = reduce_max(torch, dist, world, device, a.elapsed_time(b) / 20)
         steps = int(min(20000, max(30, 2000.0 / max(per, 1e-3))))
     l0 = eng.launch_count
     sampler = ClockSampler(device.index) if rank == 0 else None
