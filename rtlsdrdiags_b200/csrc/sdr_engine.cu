@@ -46,6 +46,11 @@ struct sdr_engine {
   float *d_scratch[5][2] = {};
   uint64_t seq = 0;        // sdr_accept_iq calls so far
   bool rec_pending = false;  // work on rec_stream that `stream` has not waited for yet
+  // Mixed banks: the WBFM kernel (one long-lived CTA per SM that leaves issue slots, registers
+  // and shared memory unused) runs on its own stream next to the other kinds' kernels
+  cudaStream_t wb_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_wb = nullptr;
+  bool wb_pending = false;   // work on wb_stream that `stream` has not waited for yet
   int scaling = SDR_SCALING_RADIODIAGS;
 
   // host mirrors (index 1..4 = kind)
@@ -154,6 +159,10 @@ int join_streams(sdr_engine *e) {
   if (e->rec_pending) {
     SDR_CK(e, cudaStreamWaitEvent(e->stream, e->ev_rec[(e->seq + 1) & 1], 0));
     e->rec_pending = false;
+  }
+  if (e->wb_pending) {
+    SDR_CK(e, cudaStreamWaitEvent(e->stream, e->ev_wb, 0));
+    e->wb_pending = false;
   }
   return SDR_OK;
 }
@@ -346,7 +355,8 @@ int launch_fm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_
   return SDR_OK;
 }
 
-int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples, int fmt) {
+int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples, int fmt,
+                     cudaStream_t stream) {
   using T = WbTile;
   const int kind = SDR_KIND_WBFM;
   const uint32_t n_list = (uint32_t)e->list[kind].size();
@@ -382,7 +392,7 @@ int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint3
   p.allowed = e->last_gated ? e->d_allowed[e->seq & 1] : nullptr;
   SDR_CK(e, cudaFuncSetAttribute(wbfm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const uint32_t grid = (n_list + G - 1) / G;
-  wbfm_tile_kernel<<<grid, 32 * T::warps_for((int)G, s3_env), smem, e->stream>>>(p);
+  wbfm_tile_kernel<<<grid, 32 * T::warps_for((int)G, s3_env), smem, stream>>>(p);
   SDR_CK(e, cudaGetLastError());
   e->launches++;
   return SDR_OK;
@@ -568,6 +578,9 @@ int sdr_engine_create(uint32_t n_channels, int device, uint64_t max_bytes_per_ch
     int prio_lo = 0, prio_hi = 0;
     SDR_CK_CREATE(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     SDR_CK_CREATE(cudaStreamCreateWithPriority(&e->rec_stream, cudaStreamNonBlocking, prio_hi));
+    SDR_CK_CREATE(cudaStreamCreateWithPriority(&e->wb_stream, cudaStreamNonBlocking, prio_hi));
+    SDR_CK_CREATE(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
+    SDR_CK_CREATE(cudaEventCreateWithFlags(&e->ev_wb, cudaEventDisableTiming));
   }
   for (int i = 0; i < 2; ++i) {
     SDR_CK_CREATE(cudaEventCreateWithFlags(&e->ev_fir[i], cudaEventDisableTiming));
@@ -627,6 +640,12 @@ int sdr_engine_destroy(sdr_engine *e) {
     cudaStreamSynchronize(e->rec_stream);
     cudaStreamDestroy(e->rec_stream);
   }
+  if (e->wb_stream) {
+    cudaStreamSynchronize(e->wb_stream);
+    cudaStreamDestroy(e->wb_stream);
+  }
+  if (e->ev_in) cudaEventDestroy(e->ev_in);
+  if (e->ev_wb) cudaEventDestroy(e->ev_wb);
   for (int i = 0; i < 2; ++i) {
     if (e->ev_fir[i]) cudaEventDestroy(e->ev_fir[i]);
     if (e->ev_rec[i]) cudaEventDestroy(e->ev_rec[i]);
@@ -662,7 +681,9 @@ int sdr_set_stream(sdr_engine *e, void *cuda_stream) {
   if (!e) return SDR_E_ARG;
   SDR_CK(e, cudaStreamSynchronize(e->stream));
   SDR_CK(e, cudaStreamSynchronize(e->rec_stream));
+  SDR_CK(e, cudaStreamSynchronize(e->wb_stream));
   e->rec_pending = false;
+  e->wb_pending = false;
   e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
   return SDR_OK;
 }
@@ -747,6 +768,11 @@ int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_str
   SDR_CK(e, cudaSetDevice(e->device));
   int rc = upload_tables(e);
   if (rc) return rc;
+  // the previous call's WBFM kernel may still be reading the input buffer this call refills
+  if (e->wb_pending) {
+    SDR_CK(e, cudaStreamWaitEvent(e->stream, e->ev_wb, 0));
+    e->wb_pending = false;
+  }
   const uint8_t *dev_iq = (const uint8_t *)iq;
   uint64_t dev_stride = ch_stride;
   if (!(flags & SDR_IQ_DEVICE)) {
@@ -765,6 +791,18 @@ int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_str
     SDR_CK(e, cudaStreamWaitEvent(e->stream, e->ev_rec[par], 0));
   if ((rc = run_iq_dump(e, dev_iq, dev_stride, bytes, fmt))) return rc;
   if ((rc = run_squelch(e, dev_iq, dev_stride, bytes, fmt))) return rc;
+  // WBFM first, and beside the others when there are others: its CTAs (one per SM for the whole
+  // launch) take their place on every SM, the short-lived CTAs of the other kinds flow around them
+  static const int wb_split_env = getenv("SDR_WB_SPLIT") ? atoi(getenv("SDR_WB_SPLIT")) : 1;
+  const bool wb_beside = wb_split_env && !e->list[SDR_KIND_WBFM].empty() &&
+                         (have_rec || !e->list[SDR_KIND_FM].empty());
+  if (wb_beside) {
+    SDR_CK(e, cudaEventRecord(e->ev_in, e->stream));
+    SDR_CK(e, cudaStreamWaitEvent(e->wb_stream, e->ev_in, 0));
+    if ((rc = launch_wbfm_tile(e, dev_iq, dev_stride, n_samples, fmt, e->wb_stream))) return rc;
+    SDR_CK(e, cudaEventRecord(e->ev_wb, e->wb_stream));
+    e->wb_pending = true;
+  }
   if ((rc = launch_amssb<false>(e, SDR_KIND_AM, dev_iq, dev_stride, n_samples, fmt))) return rc;
   if ((rc = launch_amssb<true>(e, SDR_KIND_SSB, dev_iq, dev_stride, n_samples, fmt))) return rc;
   if (have_rec) {
@@ -777,7 +815,7 @@ int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_str
   SDR_CK(e, cudaEventRecord(e->ev_rec[par], e->rec_stream));
   e->rec_pending = true;
   if ((rc = launch_fm_tile(e, dev_iq, dev_stride, n_samples, fmt))) return rc;
-  if ((rc = launch_wbfm_tile(e, dev_iq, dev_stride, n_samples, fmt))) return rc;
+  if (!wb_beside && (rc = launch_wbfm_tile(e, dev_iq, dev_stride, n_samples, fmt, e->stream))) return rc;
   e->seq++;
   e->last_samples = (uint32_t)(bytes / 64);
   return SDR_OK;
