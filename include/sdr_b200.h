@@ -34,6 +34,12 @@
  *     (IqDataProcessor.cc:756-760, UdpClient.cc:173-241)
  *   DataConsumer::acceptData(ts, buf, n) + consumer thread  sdr_ingest_accept / _acquire+_commit,
  *     (src_diags/DataConsumer.cc:220-261, 318-352)           sdr_ingest_retire, sdr_ingest_stats
+ *   new Decimator / Interpolator / Decimator_int16 /        sdr_filter_bank_create
+ *     Interpolator_int16 (N, taps, factor)
+ *     (Filters/Decimator.cc:41-76, Filters/Interpolator.cc:39-61, Filters/Int16/*.cc)
+ *   decimate(x, &y) / interpolate(x, y[L]) per sample       sdr_filter_bank_run (blocks of samples)
+ *     (Filters/Decimator.cc:281-322, Filters/Interpolator.cc interpolate)
+ *   resetFilterState()                                      sdr_filter_bank_reset
  *
  * All functions return 0 on success or a negative SDR_E_* code; none throws.
  * Calls on one engine must be serialised by the caller (the reference calls
@@ -174,6 +180,42 @@ int sdr_ingest_retire(sdr_ingest *q, uint32_t *timestamp, const int16_t **pcm, u
 /* lastTimeStamp and shortBlockCount (DataConsumer.cc:282-283), ticks committed, ticks in flight */
 int sdr_ingest_stats(const sdr_ingest *q, uint32_t *last_timestamp, uint32_t *short_block_count, uint64_t *ticks,
                      uint32_t *in_flight);
+
+/* ---- batched multirate filter banks ----
+ * The reference's generic filter classes that the IQ->PCM path does not instantiate itself.
+ * One bank = n_rows independent objects of one class with the same taps; a row is one object's
+ * sample stream. Results are those of feeding the reference object the same samples one by one
+ * (bit-identical: float taps accumulate in tap order with single-rounded multiply and add, the
+ * Q15 classes quantise taps with round(h*32768) and clamp after every tap), however the stream
+ * is cut into calls. factor = 1 makes a decimator the plain FirFilter / FirFilter_int16. */
+typedef struct sdr_filter_bank sdr_filter_bank;
+enum {
+  SDR_FILTER_DECIMATOR_F32 = 1,     /* Filters/Decimator.cc (factor 1: Filters/FirFilter.cc) */
+  SDR_FILTER_INTERPOLATOR_F32 = 2,  /* Filters/Interpolator.cc; n_taps must be a multiple of factor */
+  SDR_FILTER_DECIMATOR_I16 = 3,     /* Filters/Int16/Decimator_int16.cc (factor 1: FirFilter_int16.cc) */
+  SDR_FILTER_INTERPOLATOR_I16 = 4   /* Filters/Int16/Interpolator_int16.cc */
+};
+/* taps: the prototype filter h[0..n_taps-1] exactly as the reference constructor takes it. */
+int sdr_filter_bank_create(int device, int kind, uint32_t n_rows, const float *taps, uint32_t n_taps,
+                           uint32_t factor, sdr_filter_bank **out);
+int sdr_filter_bank_destroy(sdr_filter_bank *b);
+int sdr_filter_bank_set_stream(sdr_filter_bank *b, void *cuda_stream);
+int sdr_filter_bank_reset(sdr_filter_bank *b);
+/* Outputs per row a run of n_in samples per row will produce now: n_in * L for an interpolator,
+ * (pending + n_in) / M for a decimator (pending = samples a previous run left in the
+ * reference's decimationBuffer, Decimator.cc:291-303). */
+uint64_t sdr_filter_bank_out_count(const sdr_filter_bank *b, uint64_t n_in);
+/* in: [n_rows][in_stride] elements (float or int16_t by kind), n_in used per row; out:
+ * [n_rows][out_stride]. flags: SDR_IQ_HOST (copied in and out, returns when out is filled) or
+ * SDR_IQ_DEVICE (queued on the bank's stream). *n_out = outputs written per row. */
+int sdr_filter_bank_run(sdr_filter_bank *b, const void *in, uint64_t in_stride, uint64_t n_in, void *out,
+                        uint64_t out_stride, uint64_t *n_out, uint32_t flags);
+int sdr_filter_bank_sync(sdr_filter_bank *b);
+/* The Q15 taps the int16 classes compute in their constructors (Decimator_int16.cc:58-62);
+ * returns n_taps. */
+int sdr_filter_bank_taps_q15(const sdr_filter_bank *b, int16_t *q);
+uint64_t sdr_filter_bank_launch_count(const sdr_filter_bank *b);
+const char *sdr_filter_bank_last_error(const sdr_filter_bank *b);
 
 /* Launch shape of one demodulator kind: channels per CTA (1..32) and threads
  * per CTA (multiple of 32). 0 = let the engine choose. For tuning and tests. */

@@ -89,6 +89,12 @@ def oracle():
     L.sdro_atan2f.argtypes = [_i32, _i32]
     L.sdro_bank_run.restype = C.c_double
     L.sdro_bank_run.argtypes = [_pu8, _u32, _pu8, C.c_uint64, _u32, _pi16, _u32, _i32]
+    L.sdro_mr_new.restype = _vp
+    L.sdro_mr_new.argtypes = [_i32, _i32, _pf, _i32]
+    L.sdro_mr_free.argtypes = [_vp]
+    L.sdro_mr_reset.argtypes = [_vp]
+    L.sdro_mr_run.restype = C.c_uint64
+    L.sdro_mr_run.argtypes = [_vp, _vp, C.c_uint64, _vp]
     _oracle = L
     return L
 
@@ -146,6 +152,12 @@ def ref(tree="radiodiags"):
         L.ref_iqp_signal.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_uint32)]
         L.ref_bank_run.restype = C.c_double
         L.ref_bank_run.argtypes = [_pu8, _u32, _pu8, C.c_uint64, _u32, _pi16, _u32]
+        L.ref_mr_new.restype = _vp
+        L.ref_mr_new.argtypes = [_i32, _i32, _pf, _i32]
+        L.ref_mr_free.argtypes = [_vp]
+        L.ref_mr_reset.argtypes = [_vp]
+        L.ref_mr_run.restype = C.c_uint64
+        L.ref_mr_run.argtypes = [_vp, _vp, C.c_uint64, _vp]
     _refs[tree] = L
     return L
 
@@ -324,3 +336,42 @@ def q15_taps(filter_id):
     q = np.zeros(64, dtype=np.int16)
     n = oracle().sdro_q15_taps(filter_id, _ptr(q, _pi16))
     return q[:n].copy()
+
+
+# ---- generic multirate classes ----
+MR_DECIMATOR_F32, MR_INTERPOLATOR_F32, MR_DECIMATOR_I16, MR_INTERPOLATOR_I16 = 1, 2, 3, 4
+
+
+class Multirate:
+    """One Decimator / Interpolator / Decimator_int16 / Interpolator_int16 object: the C
+    restatement (impl="oracle") or the compiled reference class itself (impl="ref")."""
+
+    def __init__(self, kind, taps, factor, impl="oracle"):
+        self.kind, self.factor = int(kind), int(factor)
+        self.dtype = np.float32 if kind <= 2 else np.int16
+        self.interp = kind in (MR_INTERPOLATOR_F32, MR_INTERPOLATOR_I16)
+        h = np.ascontiguousarray(taps, dtype=np.float32)
+        if impl == "oracle":
+            self.L, self.pre = oracle(), "sdro_mr_"
+        else:
+            self.L, self.pre = ref("radiodiags"), "ref_mr_"
+            if self.L is None:
+                raise RuntimeError("oracle/_ref is not built")
+        self.h = getattr(self.L, self.pre + "new")(self.kind, h.size, _ptr(h, _pf), self.factor)
+        if not self.h:
+            raise ValueError("bad multirate parameters")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            getattr(self.L, self.pre + "free")(self.h)
+            self.h = None
+
+    def reset(self):
+        getattr(self.L, self.pre + "reset")(self.h)
+
+    def run(self, x):
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        cap = x.size * self.factor if self.interp else x.size // self.factor + 2
+        out = np.zeros(cap, dtype=self.dtype)
+        n = getattr(self.L, self.pre + "run")(self.h, x.ctypes.data_as(_vp), x.size, out.ctypes.data_as(_vp))
+        return out[:n].copy()

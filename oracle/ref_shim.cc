@@ -29,6 +29,9 @@
 #include "SsbDemodulator.h"
 #include "WbFmDemodulator.h"
 #ifdef REF_HAS_IQP
+#include "Decimator.h"
+#include "Interpolator.h"
+#include "Interpolator_int16.h"
 #include "IqDataProcessor.h"
 #endif
 
@@ -181,6 +184,59 @@ void ref_iir_run(void *p, const float *in, uint32_t n, float *out) {
 }
 
 #ifdef REF_HAS_IQP
+// ---------------- generic multirate classes ---------------
+// kind 1 Decimator, 2 Interpolator, 3 Decimator_int16, 4 Interpolator_int16; same contract
+// as sdro_mr_* in sdr_oracle.h. Samples go through the reference objects one at a time.
+namespace {
+struct Multirate {
+  int kind, factor;
+  void *obj;
+};
+}  // namespace
+void *ref_mr_new(int kind, int N, float *h, int factor) {
+  Multirate *m = new Multirate{kind, factor, nullptr};
+  switch (kind) {
+    case 1: m->obj = new Decimator(N, h, factor); break;
+    case 2: m->obj = new Interpolator(N, h, factor); break;
+    case 3: m->obj = new Decimator_int16(N, h, factor); break;
+    case 4: m->obj = new Interpolator_int16(N, h, factor); break;
+    default: delete m; return nullptr;
+  }
+  return m;
+}
+void ref_mr_free(void *p) {
+  Multirate *m = (Multirate *)p;
+  switch (m->kind) {
+    case 1: delete (Decimator *)m->obj; break;
+    case 2: delete (Interpolator *)m->obj; break;
+    case 3: delete (Decimator_int16 *)m->obj; break;
+    case 4: delete (Interpolator_int16 *)m->obj; break;
+  }
+  delete m;
+}
+void ref_mr_reset(void *p) {
+  Multirate *m = (Multirate *)p;
+  switch (m->kind) {
+    case 1: ((Decimator *)m->obj)->resetFilterState(); break;
+    case 2: ((Interpolator *)m->obj)->resetFilterState(); break;
+    case 3: ((Decimator_int16 *)m->obj)->resetFilterState(); break;
+    case 4: ((Interpolator_int16 *)m->obj)->resetFilterState(); break;
+  }
+}
+uint64_t ref_mr_run(void *p, const void *in, uint64_t n, void *out) {
+  Multirate *m = (Multirate *)p;
+  uint64_t c = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    switch (m->kind) {
+      case 1: if (((Decimator *)m->obj)->decimate(((const float *)in)[i], (float *)out + c)) c++; break;
+      case 2: ((Interpolator *)m->obj)->interpolate(((const float *)in)[i], (float *)out + c); c += m->factor; break;
+      case 3: if (((Decimator_int16 *)m->obj)->decimate(((const int16_t *)in)[i], (int16_t *)out + c)) c++; break;
+      case 4: ((Interpolator_int16 *)m->obj)->interpolate(((const int16_t *)in)[i], (int16_t *)out + c); c += m->factor; break;
+    }
+  }
+  return c;
+}
+
 // ---------------- product path: IqDataProcessor -> demodulator ------------
 namespace {
 struct Chain {

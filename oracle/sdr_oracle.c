@@ -121,6 +121,105 @@ void sdro_fir16_run(sdro_fir16 *f, const int16_t *in, uint32_t n, int16_t *out) 
 }
 
 /* ------------------------------------------------------------------ */
+/* Generic multirate classes (not on the IQ->PCM path):     */
+/*   Filters/Decimator.cc:168-209 (filterData), 281-322 (decimate)        */
+/*   Filters/Interpolator.cc: createPolyphaseCoefficients, filterData,    */
+/*     interpolate (p_i[k] = h[i + kL]; L outputs per input)               */
+/*   Filters/Int16/Decimator_int16.cc, Interpolator_int16.cc: Q15 twins    */
+/* Histories are shift registers, newest at [0].                          */
+/* ------------------------------------------------------------------ */
+struct sdro_mr {
+  int kind, N, F, q; /* q = taps per output */
+  float *hf;         /* float taps, prototype order */
+  int16_t *hq;       /* Q15 taps, prototype order */
+  float *xf;         /* float history, q entries */
+  int16_t *xq;
+  float *pf;         /* decimator: waiting samples */
+  int16_t *pq;
+  int npend;
+};
+
+sdro_mr *sdro_mr_new(int kind, int N, const float *h, int factor) {
+  if (kind < 1 || kind > 4 || N < 1 || factor < 1) return NULL;
+  int interp = (kind == 2 || kind == 4);
+  if (interp && N % factor) return NULL;
+  sdro_mr *m = (sdro_mr *)calloc(1, sizeof(*m));
+  m->kind = kind;
+  m->N = N;
+  m->F = factor;
+  m->q = interp ? N / factor : N;
+  m->hf = (float *)calloc((size_t)N, sizeof(float));
+  m->hq = (int16_t *)calloc((size_t)N, sizeof(int16_t));
+  m->xf = (float *)calloc((size_t)m->q, sizeof(float));
+  m->xq = (int16_t *)calloc((size_t)m->q, sizeof(int16_t));
+  m->pf = (float *)calloc((size_t)factor, sizeof(float));
+  m->pq = (int16_t *)calloc((size_t)factor, sizeof(int16_t));
+  for (int k = 0; k < N; k++) { m->hf[k] = h[k]; m->hq[k] = quantise_tap(h[k]); }
+  return m;
+}
+void sdro_mr_free(sdro_mr *m) {
+  if (!m) return;
+  free(m->hf); free(m->hq); free(m->xf); free(m->xq); free(m->pf); free(m->pq);
+  free(m);
+}
+void sdro_mr_reset(sdro_mr *m) {
+  memset(m->xf, 0, (size_t)m->q * sizeof(float));
+  memset(m->xq, 0, (size_t)m->q * sizeof(int16_t));
+  m->npend = 0;
+}
+/* taps h[first], h[first+step], ... against the history, newest first */
+static float mr_mac_f(const sdro_mr *m, int first, int step) {
+  float y = 0;
+  for (int k = 0; k < m->q; k++) y = y + (m->hf[first + k * step] * m->xf[k]);
+  return y;
+}
+static int16_t mr_mac_q(const sdro_mr *m, int first, int step) {
+  int32_t acc = 1 << 14;
+  for (int k = 0; k < m->q; k++) {
+    acc += (int32_t)m->hq[first + k * step] * (int32_t)m->xq[k];
+    if (acc > 0x3fffffff) acc = 0x3fffffff;
+    else if (acc < -0x40000000) acc = -0x40000000;
+  }
+  return (int16_t)(acc >> 15);
+}
+uint64_t sdro_mr_run(sdro_mr *m, const void *in, uint64_t n, void *out) {
+  const int is16 = m->kind >= 3, interp = (m->kind == 2 || m->kind == 4);
+  uint64_t c = 0;
+  for (uint64_t i = 0; i < n; i++) {
+    if (interp) {
+      if (is16) {
+        memmove(m->xq + 1, m->xq, (size_t)(m->q - 1) * sizeof(int16_t));
+        m->xq[0] = ((const int16_t *)in)[i];
+        for (int j = 0; j < m->F; j++) ((int16_t *)out)[c++] = mr_mac_q(m, j, m->F);
+      } else {
+        memmove(m->xf + 1, m->xf, (size_t)(m->q - 1) * sizeof(float));
+        m->xf[0] = ((const float *)in)[i];
+        for (int j = 0; j < m->F; j++) ((float *)out)[c++] = mr_mac_f(m, j, m->F);
+      }
+    } else if (is16) {
+      m->pq[m->npend++] = ((const int16_t *)in)[i];
+      if (m->npend < m->F) continue;
+      for (int j = 0; j < m->F; j++) {
+        memmove(m->xq + 1, m->xq, (size_t)(m->q - 1) * sizeof(int16_t));
+        m->xq[0] = m->pq[j];
+      }
+      m->npend = 0;
+      ((int16_t *)out)[c++] = mr_mac_q(m, 0, 1);
+    } else {
+      m->pf[m->npend++] = ((const float *)in)[i];
+      if (m->npend < m->F) continue;
+      for (int j = 0; j < m->F; j++) {
+        memmove(m->xf + 1, m->xf, (size_t)(m->q - 1) * sizeof(float));
+        m->xf[0] = m->pf[j];
+      }
+      m->npend = 0;
+      ((float *)out)[c++] = mr_mac_f(m, 0, 1);
+    }
+  }
+  return c;
+}
+
+/* ------------------------------------------------------------------ */
 /* float FIR: FirFilter.cc:144-185. y = 0; y = y + h[k]*x[n-k], k up.    */
 /* ------------------------------------------------------------------ */
 struct sdro_fir {

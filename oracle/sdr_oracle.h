@@ -50,6 +50,16 @@ sdro_iir *sdro_iir_new(int nb, const float *b, int na, const float *a);
 void sdro_iir_free(sdro_iir *f);
 void sdro_iir_run(sdro_iir *f, const float *in, uint32_t n, float *out);
 
+/* ---- the generic multirate classes the path does not instantiate:
+ * kind 1 Decimator (float), 2 Interpolator (float), 3 Decimator_int16, 4 Interpolator_int16;
+ * any tap count. Samples are float for kinds 1-2 and int16_t for kinds 3-4. ---- */
+typedef struct sdro_mr sdro_mr;
+sdro_mr *sdro_mr_new(int kind, int N, const float *h, int factor);
+void sdro_mr_free(sdro_mr *m);
+void sdro_mr_reset(sdro_mr *m);
+/* feeds n samples one by one; returns the outputs written (n*L, or one per M inputs) */
+uint64_t sdro_mr_run(sdro_mr *m, const void *in, uint64_t n, void *out);
+
 /* ---- one channel: IqDataProcessor + Am/Fm/WbFm/Ssb demodulators ---- */
 typedef struct sdro_chain sdro_chain;
 sdro_chain *sdro_chain_new(int variant);

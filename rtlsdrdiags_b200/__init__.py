@@ -27,7 +27,10 @@ ABI_SYMBOLS = ["sdr_engine_create", "sdr_engine_destroy", "sdr_set_stream", "sdr
                "sdr_launch_count", "sdr_state_bytes", "sdr_last_error", "sdr_version", "sdr_set_squelch_threshold",
                "sdr_set_receive_gain_db", "sdr_enable_signal_reports", "sdr_get_signal", "sdr_set_iq_dump",
                "sdr_get_iq_dump", "sdr_iq_dump_device", "sdr_ingest_create", "sdr_ingest_destroy",
-               "sdr_ingest_accept", "sdr_ingest_acquire", "sdr_ingest_commit", "sdr_ingest_retire", "sdr_ingest_stats"]
+               "sdr_ingest_accept", "sdr_ingest_acquire", "sdr_ingest_commit", "sdr_ingest_retire", "sdr_ingest_stats",
+               "sdr_filter_bank_create", "sdr_filter_bank_destroy", "sdr_filter_bank_set_stream",
+               "sdr_filter_bank_reset", "sdr_filter_bank_out_count", "sdr_filter_bank_run", "sdr_filter_bank_sync",
+               "sdr_filter_bank_taps_q15", "sdr_filter_bank_launch_count", "sdr_filter_bank_last_error"]
 
 
 class SdrError(RuntimeError):
@@ -84,6 +87,19 @@ def load_library(build_if_missing=True):
     L.sdr_last_error.argtypes = [vp]
     L.sdr_last_error.restype = C.c_char_p
     L.sdr_version.restype = C.c_char_p
+    L.sdr_filter_bank_create.argtypes = [i32, i32, u32, vp, u32, u32, C.POINTER(vp)]
+    L.sdr_filter_bank_destroy.argtypes = [vp]
+    L.sdr_filter_bank_set_stream.argtypes = [vp, vp]
+    L.sdr_filter_bank_reset.argtypes = [vp]
+    L.sdr_filter_bank_out_count.argtypes = [vp, u64]
+    L.sdr_filter_bank_out_count.restype = u64
+    L.sdr_filter_bank_run.argtypes = [vp, vp, u64, u64, vp, u64, C.POINTER(u64), u32]
+    L.sdr_filter_bank_sync.argtypes = [vp]
+    L.sdr_filter_bank_taps_q15.argtypes = [vp, vp]
+    L.sdr_filter_bank_launch_count.argtypes = [vp]
+    L.sdr_filter_bank_launch_count.restype = u64
+    L.sdr_filter_bank_last_error.argtypes = [vp]
+    L.sdr_filter_bank_last_error.restype = C.c_char_p
     _lib = L
     return L
 
@@ -290,3 +306,76 @@ class Ingest:
         self.e._ck(self.L.sdr_ingest_stats(self.q, C.byref(ts), C.byref(short), C.byref(ticks), C.byref(fl)))
         return {"last_timestamp": ts.value, "short_blocks": short.value, "ticks": ticks.value,
                 "in_flight": fl.value}
+
+
+FILTER_DECIMATOR_F32, FILTER_INTERPOLATOR_F32, FILTER_DECIMATOR_I16, FILTER_INTERPOLATOR_I16 = 1, 2, 3, 4
+
+
+class FilterBank:
+    """`n_rows` independent Decimator / Interpolator / Decimator_int16 / Interpolator_int16
+    objects with the same taps on one GPU (Filters/Decimator.cc, Filters/Interpolator.cc,
+    Filters/Int16/*.cc); factor 1 makes a decimator the plain FirFilter / FirFilter_int16."""
+
+    def __init__(self, kind, n_rows, taps, factor, device=0):
+        self.L = load_library()
+        self.kind, self.rows, self.factor = int(kind), int(n_rows), int(factor)
+        self.dtype = np.float32 if kind in (FILTER_DECIMATOR_F32, FILTER_INTERPOLATOR_F32) else np.int16
+        h = np.ascontiguousarray(taps, dtype=np.float32)
+        self.n_taps = h.size
+        b = C.c_void_p()
+        rc = self.L.sdr_filter_bank_create(int(device), self.kind, self.rows, h.ctypes.data_as(C.c_void_p), h.size,
+                                           self.factor, C.byref(b))
+        if rc != 0:
+            raise SdrError("sdr_filter_bank_create failed (%d): %s" % (rc, self.L.sdr_filter_bank_last_error(None).decode()))
+        self.b = b
+
+    def close(self):
+        if getattr(self, "b", None):
+            self.L.sdr_filter_bank_destroy(self.b)
+            self.b = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SdrError("sdr error %d: %s" % (rc, self.L.sdr_filter_bank_last_error(self.b).decode()))
+
+    def reset(self):
+        self._ck(self.L.sdr_filter_bank_reset(self.b))
+
+    def set_stream(self, cuda_stream_handle):
+        self._ck(self.L.sdr_filter_bank_set_stream(self.b, C.c_void_p(cuda_stream_handle or 0)))
+
+    def out_count(self, n_in):
+        return int(self.L.sdr_filter_bank_out_count(self.b, int(n_in)))
+
+    def taps_q15(self):
+        q = np.zeros(self.n_taps, dtype=np.int16)
+        self.L.sdr_filter_bank_taps_q15(self.b, q.ctypes.data_as(C.c_void_p))
+        return q
+
+    @property
+    def launch_count(self):
+        return int(self.L.sdr_filter_bank_launch_count(self.b))
+
+    def run(self, x):
+        """x: [n_rows][n] host samples; returns [n_rows][n_out]."""
+        x = np.ascontiguousarray(x, dtype=self.dtype)
+        if x.ndim != 2 or x.shape[0] != self.rows:
+            raise SdrError("x must be [n_rows][n]")
+        n_out = self.out_count(x.shape[1])
+        out = np.zeros((self.rows, max(n_out, 1)), dtype=self.dtype)
+        got = C.c_uint64()
+        self._ck(self.L.sdr_filter_bank_run(self.b, x.ctypes.data_as(C.c_void_p), x.shape[1], x.shape[1],
+                                            out.ctypes.data_as(C.c_void_p), out.shape[1], C.byref(got), IQ_HOST))
+        return out[:, :got.value]
+
+    def run_device(self, in_ptr, in_stride, n_in, out_ptr, out_stride):
+        """Device pointers (e.g. torch tensors' data_ptr()); queued on the bank's stream."""
+        got = C.c_uint64()
+        self._ck(self.L.sdr_filter_bank_run(self.b, C.c_void_p(in_ptr), int(in_stride), int(n_in), C.c_void_p(out_ptr),
+                                            int(out_stride), C.byref(got), IQ_DEVICE))
+        return got.value
+
+    def sync(self):
+        self._ck(self.L.sdr_filter_bank_sync(self.b))

@@ -35,7 +35,7 @@ def build(force=False, defines=(), verbose=False):
     cmd = [_nvcc()] + NVCC_FLAGS + ["-D%s" % d for d in defines]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB, os.path.join(CSRC, "sdr_engine.cu")]
+    cmd += ["-o", LIB, os.path.join(CSRC, "sdr_engine.cu"), os.path.join(CSRC, "sdr_filter_bank.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), r.stderr))
