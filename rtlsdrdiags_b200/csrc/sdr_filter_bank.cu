@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -24,6 +25,7 @@ struct sdr_filter_bank {
   cudaStream_t own_stream = nullptr, stream = nullptr;
   void *d_taps = nullptr, *d_carry[2] = {};
   std::vector<int16_t> q15;
+  uint32_t sum_abs_q15 = 0;
   // staging for host callers
   void *d_in = nullptr, *d_out = nullptr;
   uint64_t cap_in = 0, cap_out = 0;
@@ -97,7 +99,11 @@ int sdr_filter_bank_create(int device, int kind, uint32_t n_rows, const float *t
   b->stream = b->own_stream;
   std::vector<int32_t> q32(n_taps);
   b->q15.resize(n_taps);
-  for (uint32_t i = 0; i < n_taps; ++i) { b->q15[i] = quantise_q15(taps[i]); q32[i] = b->q15[i]; }
+  for (uint32_t i = 0; i < n_taps; ++i) {
+    b->q15[i] = quantise_q15(taps[i]);
+    q32[i] = b->q15[i];
+    b->sum_abs_q15 += (uint32_t)abs((int)b->q15[i]);
+  }
   const void *src = b->i16 ? (const void *)q32.data() : (const void *)taps;
   const size_t cbytes = (size_t)(b->C ? b->C : 1) * n_rows * b->esize;
   if ((ce = cudaMalloc(&b->d_taps, 4 * (size_t)n_taps)) != cudaSuccess ||
@@ -210,6 +216,7 @@ int sdr_filter_bank_run(sdr_filter_bank *b, const void *in, uint64_t in_stride, 
   p.q = b->q;
   p.C = b->C;
   p.pending = b->pending;
+  p.sum_abs_taps = b->sum_abs_q15;
   // tile: as many outputs (<= 2048) as the staged span fits next to the taps
   const uint32_t M = b->interp ? 1 : b->F;
   const uint32_t budget = FB_SMEM_WORDS - b->N - 64;
@@ -234,12 +241,22 @@ int sdr_filter_bank_run(sdr_filter_bank *b, const void *in, uint64_t in_stride, 
   const uint64_t tiles = n_out ? (n_out + tile - 1) / tile : 1;
   if (tiles > 0x7fffffffull) return fb_fail(b, SDR_E_TOO_LONG, "too many tiles");
   dim3 grid((unsigned)tiles, b->rows);
-  switch (b->kind) {
-    case SDR_FILTER_DECIMATOR_F32: filter_bank_kernel<float, false><<<grid, FB_THREADS, smem, b->stream>>>(p); break;
-    case SDR_FILTER_INTERPOLATOR_F32: filter_bank_kernel<float, true><<<grid, FB_THREADS, smem, b->stream>>>(p); break;
-    case SDR_FILTER_DECIMATOR_I16: filter_bank_kernel<int16_t, false><<<grid, FB_THREADS, smem, b->stream>>>(p); break;
-    case SDR_FILTER_INTERPOLATOR_I16: filter_bank_kernel<int16_t, true><<<grid, FB_THREADS, smem, b->stream>>>(p); break;
+#define FB_LAUNCH(T, INTERP, MT) filter_bank_kernel<T, INTERP, MT><<<grid, FB_THREADS, smem, b->stream>>>(p)
+#define FB_LAUNCH_DEC(T)                      \
+  switch (b->F) {                             \
+    case 1: FB_LAUNCH(T, false, 1); break;    \
+    case 2: FB_LAUNCH(T, false, 2); break;    \
+    case 4: FB_LAUNCH(T, false, 4); break;    \
+    default: FB_LAUNCH(T, false, 0); break;   \
   }
+  switch (b->kind) {
+    case SDR_FILTER_DECIMATOR_F32: FB_LAUNCH_DEC(float); break;
+    case SDR_FILTER_INTERPOLATOR_F32: FB_LAUNCH(float, true, 0); break;
+    case SDR_FILTER_DECIMATOR_I16: FB_LAUNCH_DEC(int16_t); break;
+    case SDR_FILTER_INTERPOLATOR_I16: FB_LAUNCH(int16_t, true, 0); break;
+  }
+#undef FB_LAUNCH_DEC
+#undef FB_LAUNCH
   FB_CK(b, cudaGetLastError());
   ++b->launches;
   b->cur ^= 1;

@@ -42,24 +42,27 @@ struct FilterBankParams {
   uint32_t tile_out;      // outputs per CTA
   uint32_t span;          // input samples a full tile needs
   uint32_t pitch;         // words per phase row of X
+  uint32_t sum_abs_taps;  // Q15 kinds: sum |q[k]|
 };
 
-template <class T> struct FbAcc;
-template <> struct FbAcc<float> {
+// CLAMP = false: the tile's samples are small enough that no partial sum can reach the Q15
+// clamp (sum|q| * max|x| + 2^14 < 2^30), so the per-tap clamp is skipped -- same result
+template <class T, bool CLAMP> struct FbAcc;
+template <bool CLAMP> struct FbAcc<float, CLAMP> {
   using acc_t = float;
   using tap_t = float;
   __device__ __forceinline__ static float init() { return 0.f; }
   __device__ __forceinline__ static float mac(float acc, float h, float x) { return fadd(acc, fmul(h, x)); }
   __device__ __forceinline__ static float done(float acc) { return acc; }
 };
-template <> struct FbAcc<int16_t> {
+template <bool CLAMP> struct FbAcc<int16_t, CLAMP> {
   using acc_t = int32_t;
   using tap_t = int32_t;
   __device__ __forceinline__ static int32_t init() { return 1 << 14; }
   __device__ __forceinline__ static int32_t mac(int32_t acc, int32_t h, int16_t x) {
     // |acc| <= 2^30 and |h x| <= 2^30: the sum cannot leave int32 before the clamp
     acc += h * (int32_t)x;
-    return max(min(acc, 0x3fffffff), -0x40000000);
+    return CLAMP ? max(min(acc, 0x3fffffff), -0x40000000) : acc;
   }
   __device__ __forceinline__ static int16_t done(int32_t acc) { return (int16_t)(acc >> 15); }
 };
@@ -71,10 +74,70 @@ __device__ __forceinline__ T fb_sample(const T *in_row, const T *carry_row, uint
   return s >= -(int64_t)C ? carry_row[(int64_t)C + s] : (T)0;
 }
 
-template <class T, bool INTERP>
-__global__ void __launch_bounds__(FB_THREADS) filter_bank_kernel(const __grid_constant__ FilterBankParams p) {
-  using A = FbAcc<T>;
+// the outputs of one tile from the staged span
+template <class T, bool INTERP, int MT, bool CLAMP>
+__device__ __forceinline__ void fb_compute(const FilterBankParams &p, const typename FbAcc<T, CLAMP>::tap_t *h, const T *X,
+                                           uint32_t row, uint64_t o0, uint32_t M) {
+  using A = FbAcc<T, CLAMP>;
   using tap_t = typename A::tap_t;
+  using acc_t = typename A::acc_t;
+  T *out_row = reinterpret_cast<T *>(p.out) + (uint64_t)row * p.out_stride;
+  // R outputs per thread and pass (t, t + 256, ..): one tap load serves R accumulators. Outputs
+  // past the tile or the row read staged zeros / neighbours and are simply not stored.
+  constexpr int R = 4;
+  for (uint32_t t0 = threadIdx.x; t0 < p.tile_out; t0 += R * FB_THREADS) {
+    if (o0 + t0 >= p.n_out) break;
+    acc_t acc[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc[j] = A::init();
+    if (INTERP) {
+      // lanes own consecutive outputs: the same input for L lanes, taps h[i + kL] consecutive in i
+      const T *xp[R];
+      const tap_t *hp[R];
+#pragma unroll
+      for (int j = 0; j < R; ++j) {
+        const uint32_t t = min(t0 + j * FB_THREADS, p.tile_out - 1);
+        xp[j] = X + t / p.F + (p.q - 1);  // newest input of this output, span index
+        hp[j] = h + t % p.F;
+      }
+      for (uint32_t k = 0; k < p.q; ++k) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[j] = A::mac(acc[j], hp[j][k * p.F], *(xp[j] - k));
+      }
+    } else {
+      // newest input of output t at span index M t + N-1; tap k reads index M t + (N-1-k),
+      // which sits at X[(N-1-k) % M][t + (N-1-k) / M]: consecutive words across lanes
+      const uint32_t last = min(t0 + (R - 1) * FB_THREADS, p.tile_out - 1) - t0;  // clamp the last pass
+      uint32_t k = 0;
+      int32_t ph = (int32_t)((p.N - 1) % M);
+      const T *xb = X + t0 + (p.N - 1) / M;
+      for (; ph >= 0; --ph, ++k) {  // the partial group of the newest samples
+        const tap_t hk = h[k];
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[j] = A::mac(acc[j], hk, xb[(uint32_t)ph * p.pitch + min((uint32_t)j * FB_THREADS, last)]);
+      }
+      while (k < p.N) {  // full groups of M, one word further back each
+        --xb;
+#pragma unroll
+        for (int32_t f = (int32_t)M - 1; f >= 0; --f, ++k) {
+          const tap_t hk = h[k];
+#pragma unroll
+          for (int j = 0; j < R; ++j) acc[j] = A::mac(acc[j], hk, xb[(uint32_t)f * p.pitch + min((uint32_t)j * FB_THREADS, last)]);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const uint32_t t = t0 + j * FB_THREADS;
+      if (t < p.tile_out && o0 + t < p.n_out) out_row[o0 + t] = A::done(acc[j]);
+    }
+  }
+}
+
+// MT = decimation factor known at compile time (0: use p.F), so the phase loop unrolls
+template <class T, bool INTERP, int MT>
+__global__ void __launch_bounds__(FB_THREADS) filter_bank_kernel(const __grid_constant__ FilterBankParams p) {
+  using tap_t = typename FbAcc<T, true>::tap_t;
   extern __shared__ uint4 fb_smem_raw[];
   tap_t *h = reinterpret_cast<tap_t *>(fb_smem_raw);
   T *X = reinterpret_cast<T *>(h + p.N);
@@ -82,7 +145,7 @@ __global__ void __launch_bounds__(FB_THREADS) filter_bank_kernel(const __grid_co
   const T *in_row = reinterpret_cast<const T *>(p.in) + (uint64_t)row * p.in_stride;
   const T *carry_row = reinterpret_cast<const T *>(p.carry_in) + (uint64_t)row * p.C;
   const uint64_t o0 = (uint64_t)blockIdx.x * p.tile_out;  // first output of this tile
-  const uint32_t M = INTERP ? 1u : p.F;
+  const uint32_t M = INTERP ? 1u : (MT ? (uint32_t)MT : p.F);
 
   // first stream sample the tile touches: the oldest tap of its first output
   //   decimator: newest input of output o is M o + M-1 - pending (Decimator.cc:296-316)
@@ -90,28 +153,49 @@ __global__ void __launch_bounds__(FB_THREADS) filter_bank_kernel(const __grid_co
   const int64_t s0 = INTERP ? (int64_t)(o0 / p.F) - (int64_t)(p.q - 1)
                             : (int64_t)(o0 * M) + (int64_t)(M - 1) - (int64_t)p.pending - (int64_t)(p.N - 1);
   for (uint32_t i = threadIdx.x; i < p.N; i += FB_THREADS) h[i] = reinterpret_cast<const tap_t *>(p.taps)[i];
-  for (uint32_t i = threadIdx.x; i < p.span; i += FB_THREADS)
-    X[(i % M) * p.pitch + i / M] = fb_sample(in_row, carry_row, p.C, s0 + i, p.n_in);
-  __syncthreads();
-
-  T *out_row = reinterpret_cast<T *>(p.out) + (uint64_t)row * p.out_stride;
-  for (uint32_t t = threadIdx.x; t < p.tile_out; t += FB_THREADS) {
-    const uint64_t o = o0 + t;
-    if (o >= p.n_out) break;
-    typename A::acc_t acc = A::init();
-    if (INTERP) {
-      const uint32_t n = (uint32_t)(o / p.F - o0 / p.F) + (p.q - 1);  // newest input, span index
-      const uint32_t i = (uint32_t)(o % p.F);
-      for (uint32_t k = 0; k < p.q; ++k) acc = A::mac(acc, h[i + k * p.F], X[n - k]);
-    } else {
-      // newest input at span index M t + N-1; tap k reads index M t + (N-1-k)
-      uint32_t ph = (p.N - 1) % M, base = t + (p.N - 1) / M;
-      for (uint32_t k = 0; k < p.N; ++k) {
-        acc = A::mac(acc, h[k], X[ph * p.pitch + base]);
-        if (ph == 0) { ph = M - 1; --base; } else --ph;
+  if (s0 >= 0 && (uint64_t)s0 + p.span <= p.n_in) {
+    // interior tile (all but the first and last of a row): 16-byte loads from the first aligned
+    // element on, scalar head and tail
+    constexpr uint32_t VEC = 16 / sizeof(T);
+    const T *src = in_row + s0;
+    const uint32_t head = min(p.span, (uint32_t)(((16 - (uint32_t)((uintptr_t)src & 15)) & 15) / sizeof(T)));
+    const uint32_t nvec = (p.span - head) / VEC;
+    const uint4 *vsrc = reinterpret_cast<const uint4 *>(src + head);
+    for (uint32_t v = threadIdx.x; v < nvec; v += FB_THREADS) {
+      const uint4 raw = __ldg(vsrc + v);
+      T e[VEC];
+      memcpy(e, &raw, 16);
+#pragma unroll
+      for (uint32_t j = 0; j < VEC; ++j) {
+        const uint32_t i = head + v * VEC + j;
+        X[(i % M) * p.pitch + i / M] = e[j];
       }
     }
-    out_row[o] = A::done(acc);
+    for (uint32_t i = threadIdx.x; i < head; i += FB_THREADS) X[(i % M) * p.pitch + i / M] = src[i];
+    for (uint32_t i = head + nvec * VEC + threadIdx.x; i < p.span; i += FB_THREADS)
+      X[(i % M) * p.pitch + i / M] = src[i];
+  } else {
+    for (uint32_t i = threadIdx.x; i < p.span; i += FB_THREADS)
+      X[(i % M) * p.pitch + i / M] = fb_sample(in_row, carry_row, p.C, s0 + i, p.n_in);
+  }
+  __syncthreads();
+
+  if (sizeof(T) == 2) {
+    // largest |x| of the staged span decides whether the clamp can fire anywhere in this tile
+    __shared__ uint32_t tile_max;
+    if (threadIdx.x == 0) tile_max = 0;
+    __syncthreads();
+    uint32_t m = 0;
+    for (uint32_t i = threadIdx.x; i < p.span; i += FB_THREADS) m = max(m, (uint32_t)abs((int)X[(i % M) * p.pitch + i / M]));
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0) atomicMax(&tile_max, m);
+    __syncthreads();
+    if ((uint64_t)p.sum_abs_taps * tile_max + (1u << 14) < (1u << 30))
+      fb_compute<T, INTERP, MT, false>(p, h, X, row, o0, M);
+    else
+      fb_compute<T, INTERP, MT, true>(p, h, X, row, o0, M);
+  } else {
+    fb_compute<T, INTERP, MT, true>(p, h, X, row, o0, M);
   }
 
   // the row's next carry: the last C samples of (carry ++ input)
