@@ -76,6 +76,20 @@ SDR_DEV float wrap_pi(float d) {
   return dadd_to_f(d, off);
 }
 
+// The same wrap without FP64, for differences of WBFM atan2-TABLE values only: 2 pi = HI + LO
+// with HI = (float)(2 pi); d - HI is exact (Sterbenz), and subtracting LO in float rounds to the
+// value the reference's double subtraction rounds to for every pair of the table's 39,920
+// distinct values (checked exhaustively, 1.59e9 pairs: tests/test_emu_parity.py). Not valid
+// for arbitrary floats (NBFM's per-sample atan2 of wider operands keeps wrap_pi).
+SDR_DEV float wrap_pi_table(float d) {
+  const float PI_F = 3.14159274101257324f;
+  const uint32_t s = f2u(d) & 0x80000000u;
+  const float hi = u2f(0x40C90FDBu | s);   // copysign((float)(2 pi), d)
+  const float lo = u2f(0xB43BBD2Eu ^ s);   // copysign(2 pi - (float)(2 pi), ..) = -1.7484555e-7 * sign
+  const float w = fsub(fsub(d, hi), lo);
+  return fabsf(d) >= PI_F ? w : d;
+}
+
 // ---------------------------------------------------------------------------
 // Front end: u8 offset-binary -> s8, multiply by {1, j, -1, -j}, de-interleave
 // (IqDataProcessor.cc:735-738 and 567-611). Works on packed bytes.

@@ -65,6 +65,7 @@ struct sdr_engine {
   uint32_t *d_list[5] = {};
   uint8_t *d_lsb = nullptr;
   float *d_lut_fm = nullptr, *d_lut_wbfm = nullptr;
+  float *d_lut_wbfm_half = nullptr;  // q >= 0 half plane for wbfm_tile2_kernel, [129][256]
   uint32_t *d_fm_tab = nullptr;  // tensor-core tuner tables, fm_mma_table()
   uint8_t *d_iq = nullptr;
   int16_t *d_pcm = nullptr;
@@ -355,12 +356,60 @@ int launch_fm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_
   return SDR_OK;
 }
 
+// wbfm_tile2_kernel: the atan2 half-plane table in shared memory, 15 channels per CTA
+int launch_wbfm_tile2(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples, int fmt,
+                      cudaStream_t stream) {
+  using T = WbTile2;
+  const int kind = SDR_KIND_WBFM;
+  const uint32_t n_list = (uint32_t)e->list[kind].size();
+  // one CTA per SM (table and rings fill shared memory): spread the channels evenly over the
+  // waves. 14 workers leave the recurrence warp's scheduler two warps lighter than the others.
+  static const int g_env = getenv("SDR_WB_G") ? atoi(getenv("SDR_WB_G")) : 0;  // tuning override
+  const long max_g = g_env ? g_env : 14;
+  const long slots = e->n_sm;
+  const long W = ((long)n_list + slots * max_g - 1) / (slots * max_g);
+  uint32_t G = (uint32_t)(((long)n_list + slots * W - 1) / (slots * W));
+  static const int gx_env = getenv("SDR_WB_GX") ? atoi(getenv("SDR_WB_GX")) : 0;  // exact, for sweeps
+  if (gx_env) G = (uint32_t)gx_env;
+  if (e->shape[kind].G) G = e->shape[kind].G;
+  if (G > (uint32_t)T::MAX_WORKERS) G = T::MAX_WORKERS;
+  const int smem = T::smem_bytes((int)G);
+  LaunchParams p = {};
+  p.iq = iq;
+  p.ch_stride = ch_stride;
+  p.n_samples = n_samples;
+  p.fmt = fmt;
+  p.chan_ids = e->d_list[kind];
+  p.n_list = n_list;
+  p.G = G;
+  p.state = e->d_state[kind];
+  p.state_stride = (uint32_t)WbTile::STATE_BYTES;
+  p.scale = e->d_scale[kind];
+  p.lsb = e->d_lsb;
+  p.pcm = e->d_pcm;
+  p.pcm_stride = e->pcm_stride;
+  p.lut = e->d_lut_wbfm_half;
+  static const int rec_env = getenv("SDR_WB_REC") ? atoi(getenv("SDR_WB_REC")) : -1;  // tuning override
+  p.aux = (uint32_t)((rec_env >= 0 && rec_env <= (int)G) ? rec_env : std::min((int)G, (int)T::REC_WARP));
+  p.scratch = nullptr;
+  p.allowed = e->last_gated ? e->d_allowed[e->seq & 1] : nullptr;
+  SDR_CK(e, cudaFuncSetAttribute(wbfm_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const uint32_t grid = (n_list + G - 1) / G;
+  wbfm_tile2_kernel<<<grid, 32 * T::warps_for((int)G), smem, stream>>>(p);
+  SDR_CK(e, cudaGetLastError());
+  e->launches++;
+  return SDR_OK;
+}
+
 int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples, int fmt,
                      cudaStream_t stream) {
   using T = WbTile;
   const int kind = SDR_KIND_WBFM;
   const uint32_t n_list = (uint32_t)e->list[kind].size();
   if (n_list == 0) return SDR_OK;
+  // SDR_WB_KERNEL=1 selects the first-generation kernel (table gathered from global memory)
+  static const int gen_env = getenv("SDR_WB_KERNEL") ? atoi(getenv("SDR_WB_KERNEL")) : 2;
+  if (gen_env != 1 && e->d_lut_wbfm_half) return launch_wbfm_tile2(e, iq, ch_stride, n_samples, fmt, stream);
   // one CTA per SM (the rings fill shared memory): spread the channels evenly over the waves
   const long slots = e->n_sm;
   const long W = ((long)n_list + slots * T::MAX_WORKERS - 1) / (slots * T::MAX_WORKERS);
@@ -625,6 +674,25 @@ int sdr_engine_create(uint32_t n_channels, int device, uint64_t max_bytes_per_ch
       for (int x = 0; x < 256; ++x) t[(size_t)y * 256 + x] = (float)atan2((double)y - 128, (double)x - 128);
     SDR_CK_CREATE(cudaMalloc(&e->d_lut_wbfm, t.size() * 4));
     SDR_CK_CREATE(cudaMemcpy(e->d_lut_wbfm, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+    // wbfm_tile2_kernel keeps only the half plane q >= 0 (row |q|, column (uint8_t)i) and takes
+    // theta(q < 0) = -theta(-q): true for this libm's atan2 on every entry, or the kernel is not used
+    std::vector<float> h((size_t)WbTile2::LUT_ROWS * 256);
+    bool odd = true;
+    for (int q = 0; q <= 128; ++q)
+      for (int c = 0; c < 256; ++c) {
+        const int i = (int)(int8_t)c;
+        const float v = (float)atan2((double)q, (double)i);
+        h[(size_t)q * 256 + c] = v;
+        if (q <= 127 && v != t[(size_t)(q + 128) * 256 + (i + 128)]) odd = false;
+        if (q >= 1) {
+          const float n = t[(size_t)(128 - q) * 256 + (i + 128)];  // the reference's entry for -q
+          if (memcmp(&n, &v, 4) == 0 || n != -v) odd = false;
+        }
+      }
+    if (odd) {
+      SDR_CK_CREATE(cudaMalloc(&e->d_lut_wbfm_half, h.size() * 4));
+      SDR_CK_CREATE(cudaMemcpy(e->d_lut_wbfm_half, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+    }
   }
   SDR_CK_CREATE(cudaStreamSynchronize(e->stream));
 #undef SDR_CK_CREATE
@@ -670,6 +738,7 @@ int sdr_engine_destroy(sdr_engine *e) {
   cudaFree(e->d_lut_fm);
   cudaFree(e->d_fm_tab);
   cudaFree(e->d_lut_wbfm);
+  cudaFree(e->d_lut_wbfm_half);
   cudaFree(e->d_iq);
   cudaFree(e->d_pcm);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);

@@ -41,6 +41,13 @@ SDR_DEV int dp2a_hi_su(uint32_t a, uint32_t b, int c) {
   return d;
 }
 SDR_DEV uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
+// PTX prmt in its default mode: a selector nibble with bit 3 set replicates the SIGN of the
+// selected byte (__byte_perm keeps only three bits per nibble)
+SDR_DEV uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t s) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(s));
+  return d;
+}
 
 // ---- memory ----
 SDR_DEV u32x4 ld_stream_u4(const void *p) {  // read-once input: bypass L1 allocation
@@ -94,6 +101,7 @@ SDR_DEV uint32_t byte_perm(uint32_t a, uint32_t b, uint32_t s) {
   }
   return r;
 }
+SDR_DEV uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t s) { return byte_perm(a, b, s); }
 template <class T> SDR_DEV T lds(const void *p) { T v; memcpy(&v, p, sizeof(T)); return v; }
 template <class T> SDR_DEV void sts(void *p, T v) { memcpy(p, &v, sizeof(T)); }
 SDR_DEV u32x4 ld_stream_u4(const void *p) { return lds<u32x4>(p); }

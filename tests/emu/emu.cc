@@ -95,4 +95,18 @@ int emu_run(int kind, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples,
   }
   return -1;
 }
+
+// wrap_pi_table (the FP64-free +-pi wrap the second WBFM kernel uses) against wrap_pi (the
+// reference's double arithmetic) for EVERY difference of two of the given values; returns the
+// number of mismatching pairs. vals = the distinct entries of the WBFM atan2 table.
+uint64_t emu_wrap_table_check(const float *vals, uint32_t n) {
+  uint64_t bad = 0;
+  for (uint32_t a = 0; a < n; ++a)
+    for (uint32_t b = 0; b < n; ++b) {
+      const float d = sdr::fsub(vals[a], vals[b]);
+      const float r = sdr::wrap_pi(d), t = sdr::wrap_pi_table(d);
+      bad += memcmp(&r, &t, 4) != 0;
+    }
+  return bad;
+}
 }

@@ -82,3 +82,26 @@ def test_clamp_path_switches_mid_stream(kind):
         got = bank.run(iq, E.FMT_U8)
         for c in range(n_ch):
             assert np.array_equal(got[c], chains[c].accept_u8(iq[c]))
+
+
+def test_table_wrap_without_fp64_equals_the_double_wrap_for_every_table_pair():
+    """wbfm_tile2_kernel wraps theta differences with two float subtractions (wrap_pi_table)
+    instead of the reference's double arithmetic (WbFmDemodulator.cc:472-480). Exhaustive over
+    all pairs of the atan2 table's distinct values: 39,920^2 = 1.59e9 differences."""
+    import ctypes as C
+    vals = np.unique(E.lut(E.KIND_WBFM).ravel())
+    assert vals.size == 39920
+    L = E.lib()
+    L.emu_wrap_table_check.restype = C.c_uint64
+    L.emu_wrap_table_check.argtypes = [C.c_void_p, C.c_uint32]
+    assert L.emu_wrap_table_check(vals.ctypes.data_as(C.c_void_p), vals.size) == 0
+
+
+def test_wbfm_table_is_odd_in_q():
+    """The second WBFM kernel keeps the half plane q >= 0 only: theta(-q, i) == -theta(q, i) bit for
+    bit for every entry of the reference's table (WbFmDemodulator.cc:159-170)."""
+    t = E.lut(E.KIND_WBFM)            # [q + 128][i + 128]
+    for q in range(1, 128):
+        assert np.array_equal(t[128 - q], -t[128 + q])
+        assert np.all(np.signbit(t[128 - q]) != np.signbit(t[128 + q]))
+    assert np.array_equal(t[0], -np.array([O.oracle().sdro_atan2f(128, i) for i in range(-128, 128)], dtype=np.float32))
