@@ -193,7 +193,7 @@ def bench_one(torch, R, synth, workload, channels, n_blocks, steps, warmup, sign
         per = reduce_max(torch, dist, world, device, a.elapsed_time(b) / 20)
         steps = int(min(20000, max(30, 2000.0 / max(per, 1e-3))))
     l0 = eng.launch_count
-    sampler = ClockSampler(device.index) if rank == 0 else None
+    sampler = ClockSampler(device.index) if rank == 0 and not os.environ.get("SDR_BENCH_NO_SAMPLER") else None
     barrier()
     e0, e1 = timed(steps)
     barrier()

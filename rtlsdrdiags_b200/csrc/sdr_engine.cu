@@ -40,10 +40,20 @@ struct sdr_engine {
   int smem_optin = 227 * 1024;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   // AM/SSB: the recurrence kernels run on rec_stream, one call behind the FIR kernels on
-  // `stream`; the numerators travel through scratch[kind][call parity]
+  // `stream`; the numerators travel through scratch[kind][call index % RING]
   cudaStream_t rec_stream = nullptr;
-  cudaEvent_t ev_fir[2] = {}, ev_rec[2] = {};
-  float *d_scratch[5][2] = {};
+  // RING: how many calls' numerators / gates exist at once. Two would do if call k's recurrence
+  // kernel always started beside call k+1's FIR kernel; when the FIR kernel's CTAs take every SM
+  // first, the recurrence runs one call later, and with three buffers call k+2 need not wait for it
+  // (profiles/r01v7_pacing.txt)
+  static constexpr int RING = 3;
+  cudaEvent_t ev_fir[RING] = {}, ev_rec[RING] = {};
+  // pacing: a caller that queues calls faster than the GPU retires them is held once PACE calls
+  // are in flight (see sdr_accept_iq)
+  static constexpr int PACE = 256;
+  cudaEvent_t ev_pace[PACE] = {};
+  int pace_depth = 32;
+  float *d_scratch[5][RING] = {};
   uint64_t seq = 0;        // sdr_accept_iq calls so far
   bool rec_pending = false;  // work on rec_stream that `stream` has not waited for yet
   // Mixed banks: the WBFM kernel (one long-lived CTA per SM that leaves issue slots, registers
@@ -77,7 +87,7 @@ struct sdr_engine {
   bool squelch_dirty = false, squelch_armed = false, signal_reports = false;
   int32_t *d_threshold = nullptr;
   uint32_t *d_rx_gain = nullptr, *d_magnitude = nullptr;
-  uint8_t *d_tracking = nullptr, *d_allowed[2] = {};
+  uint8_t *d_tracking = nullptr, *d_allowed[RING] = {};
   int32_t *d_db_table = nullptr;
   bool last_gated = false;  // the last accept ran the squelch kernel with the gate in force
 
@@ -158,7 +168,7 @@ float scale_of(int kind, float gain, int scaling) {
 // main stream waits for everything queued on rec_stream
 int join_streams(sdr_engine *e) {
   if (e->rec_pending) {
-    SDR_CK(e, cudaStreamWaitEvent(e->stream, e->ev_rec[(e->seq + 1) & 1], 0));
+    SDR_CK(e, cudaStreamWaitEvent(e->stream, e->ev_rec[(e->seq + sdr_engine::RING - 1) % sdr_engine::RING], 0));
     e->rec_pending = false;
   }
   if (e->wb_pending) {
@@ -174,7 +184,7 @@ int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride,
   using T = AmSsbTile<SSB>;
   const uint32_t n_list = (uint32_t)e->list[kind].size();
   if (n_list == 0) return SDR_OK;
-  const int par = (int)(e->seq & 1);
+  const int par = (int)(e->seq % sdr_engine::RING);
   const uint32_t n_tiles = (n_samples + TILE - 1) / TILE;
   if (!e->d_scratch[kind][par]) {
     const size_t max_tiles = (size_t)((e->max_bytes / 2 + TILE - 1) / TILE);
@@ -217,7 +227,7 @@ int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride,
 int launch_dc_block(sdr_engine *e, int kind, uint32_t n_samples) {
   const uint32_t n_list = (uint32_t)e->list[kind].size();
   if (n_list == 0) return SDR_OK;
-  const int par = (int)(e->seq & 1);
+  const int par = (int)(e->seq % sdr_engine::RING);
   const int nreg = kind == SDR_KIND_SSB ? AmSsbTile<true>::NREG : AmSsbTile<false>::NREG;
   LaunchParams p = {};
   p.n_samples = n_samples;
@@ -343,7 +353,7 @@ int launch_fm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_
   p.call_id = (uint32_t)(e->seq % 0x7fffffffull) + 1;
   p.tab = e->d_fm_tab;
   p.scratch = nullptr;
-  p.allowed = e->last_gated ? e->d_allowed[e->seq & 1] : nullptr;
+  p.allowed = e->last_gated ? e->d_allowed[e->seq % sdr_engine::RING] : nullptr;
   const uint32_t grid = (uint32_t)((n_warps + G - 1) / G);
   static const int minb_env = getenv("SDR_FM_MIN_CTAS") ? atoi(getenv("SDR_FM_MIN_CTAS")) : 0;
   switch (minb_env) {
@@ -392,7 +402,7 @@ int launch_wbfm_tile2(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint
   static const int rec_env = getenv("SDR_WB_REC") ? atoi(getenv("SDR_WB_REC")) : -1;  // tuning override
   p.aux = (uint32_t)((rec_env >= 0 && rec_env <= (int)G) ? rec_env : std::min((int)G, (int)T::REC_WARP));
   p.scratch = nullptr;
-  p.allowed = e->last_gated ? e->d_allowed[e->seq & 1] : nullptr;
+  p.allowed = e->last_gated ? e->d_allowed[e->seq % sdr_engine::RING] : nullptr;
   SDR_CK(e, cudaFuncSetAttribute(wbfm_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const uint32_t grid = (n_list + G - 1) / G;
   wbfm_tile2_kernel<<<grid, 32 * T::warps_for((int)G), smem, stream>>>(p);
@@ -438,7 +448,7 @@ int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint3
   static const int s3_env = getenv("SDR_WB_S3") ? atoi(getenv("SDR_WB_S3")) : 4;
   p.aux = (uint32_t)s3_env;
   p.scratch = nullptr;
-  p.allowed = e->last_gated ? e->d_allowed[e->seq & 1] : nullptr;
+  p.allowed = e->last_gated ? e->d_allowed[e->seq % sdr_engine::RING] : nullptr;
   SDR_CK(e, cudaFuncSetAttribute(wbfm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const uint32_t grid = (n_list + G - 1) / G;
   wbfm_tile_kernel<<<grid, 32 * T::warps_for((int)G, s3_env), smem, stream>>>(p);
@@ -504,8 +514,7 @@ int run_squelch(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint64_t b
       SDR_CK(e, cudaMalloc(&e->d_rx_gain, (size_t)e->n * 4));
       SDR_CK(e, cudaMalloc(&e->d_magnitude, (size_t)e->n * 4));
       SDR_CK(e, cudaMalloc(&e->d_tracking, e->n));
-      SDR_CK(e, cudaMalloc(&e->d_allowed[0], e->n));
-      SDR_CK(e, cudaMalloc(&e->d_allowed[1], e->n));
+      for (int i = 0; i < sdr_engine::RING; ++i) SDR_CK(e, cudaMalloc(&e->d_allowed[i], e->n));
       SDR_CK(e, cudaMalloc(&e->d_db_table, 128 * 4));
       // until now every block of every channel passed: the trackers are in `Tracking`
       // (SignalTracker.cc:104-145) if any block was seen, else in `NoSignal`
@@ -537,7 +546,7 @@ int run_squelch(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint64_t b
   q.threshold = e->d_threshold;
   q.gain_db = e->d_rx_gain;
   q.tracking = e->d_tracking;
-  q.allowed = e->d_allowed[e->seq & 1];
+  q.allowed = e->d_allowed[e->seq % sdr_engine::RING];
   q.magnitude = e->d_magnitude;
   q.db_table = e->d_db_table;
   squelch_kernel<<<e->n, 128, 0, e->stream>>>(q);
@@ -631,10 +640,13 @@ int sdr_engine_create(uint32_t n_channels, int device, uint64_t max_bytes_per_ch
     SDR_CK_CREATE(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
     SDR_CK_CREATE(cudaEventCreateWithFlags(&e->ev_wb, cudaEventDisableTiming));
   }
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < sdr_engine::RING; ++i) {
     SDR_CK_CREATE(cudaEventCreateWithFlags(&e->ev_fir[i], cudaEventDisableTiming));
     SDR_CK_CREATE(cudaEventCreateWithFlags(&e->ev_rec[i], cudaEventDisableTiming));
   }
+  for (int i = 0; i < sdr_engine::PACE; ++i)
+    SDR_CK_CREATE(cudaEventCreateWithFlags(&e->ev_pace[i], cudaEventDisableTiming));
+  if (getenv("SDR_PACE")) e->pace_depth = std::max(0, std::min((int)sdr_engine::PACE, atoi(getenv("SDR_PACE"))));  // 0 = off
   e->stream = e->own_stream;
 
   e->dump_on.assign(n_channels, 0);           // IqDataProcessor.cc:62
@@ -714,13 +726,14 @@ int sdr_engine_destroy(sdr_engine *e) {
   }
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_wb) cudaEventDestroy(e->ev_wb);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < sdr_engine::RING; ++i) {
     if (e->ev_fir[i]) cudaEventDestroy(e->ev_fir[i]);
     if (e->ev_rec[i]) cudaEventDestroy(e->ev_rec[i]);
   }
+  for (int i = 0; i < sdr_engine::PACE; ++i)
+    if (e->ev_pace[i]) cudaEventDestroy(e->ev_pace[i]);
   for (int k = 1; k <= 4; ++k) {
-    cudaFree(e->d_scratch[k][0]);
-    cudaFree(e->d_scratch[k][1]);
+    for (int i = 0; i < sdr_engine::RING; ++i) cudaFree(e->d_scratch[k][i]);
     cudaFree(e->d_state[k]);
     cudaFree(e->d_scale[k]);
     cudaFree(e->d_list[k]);
@@ -731,8 +744,7 @@ int sdr_engine_destroy(sdr_engine *e) {
   cudaFree(e->d_tracking);
   cudaFree(e->d_dump);
   cudaFree(e->d_dump_list);
-  cudaFree(e->d_allowed[0]);
-  cudaFree(e->d_allowed[1]);
+  for (int i = 0; i < sdr_engine::RING; ++i) cudaFree(e->d_allowed[i]);
   cudaFree(e->d_db_table);
   cudaFree(e->d_lsb);
   cudaFree(e->d_lut_fm);
@@ -850,10 +862,17 @@ int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_str
     dev_iq = e->d_iq;
     dev_stride = bytes;
   }
+  // Bounded run-ahead. With hundreds of calls queued the driver's launch queues fill up and the
+  // GPU is fed in bursts: a 15,000-call AM loop ran at 0.170 ms per call against 0.125 ms for the
+  // same loop 1,500 calls long, at full clocks (tools/probe_power.py, profiles/r01v7_pacing.txt).
+  // Holding the caller once pace_depth calls are in flight keeps the queues shallow.
+  const int slot = (int)(e->seq % (uint64_t)sdr_engine::PACE);
+  if (e->pace_depth > 0 && e->seq >= (uint64_t)e->pace_depth)
+    SDR_CK(e, cudaEventSynchronize(e->ev_pace[(int)((e->seq - (uint64_t)e->pace_depth) % (uint64_t)sdr_engine::PACE)]));
   const int fmt = (flags & SDR_IQ_S8_ROTATED) ? FMT_S8_ROTATED : FMT_U8_OFFSET_ROTATE;
   const uint32_t n_samples = (uint32_t)(bytes / 2);
   const bool have_rec = !e->list[SDR_KIND_AM].empty() || !e->list[SDR_KIND_SSB].empty();
-  const int par = (int)(e->seq & 1);
+  const int par = (int)(e->seq % sdr_engine::RING);
   // scratch[par] and allowed[par] were last read by the recurrence kernels of the call
   // before the previous one
   if (have_rec || e->squelch_armed || e->signal_reports || e->squelch_dirty)
@@ -885,6 +904,7 @@ int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_str
   e->rec_pending = true;
   if ((rc = launch_fm_tile(e, dev_iq, dev_stride, n_samples, fmt))) return rc;
   if (!wb_beside && (rc = launch_wbfm_tile(e, dev_iq, dev_stride, n_samples, fmt, e->stream))) return rc;
+  SDR_CK(e, cudaEventRecord(e->ev_pace[slot], e->stream));
   e->seq++;
   e->last_samples = (uint32_t)(bytes / 64);
   return SDR_OK;
@@ -903,7 +923,7 @@ int sdr_get_pcm(sdr_engine *e, int16_t *pcm, uint32_t *counts) {
   std::vector<uint8_t> gate;
   if (counts && e->last_gated && e->seq > 0) {
     gate.resize(e->n);
-    SDR_CK(e, cudaMemcpyAsync(gate.data(), e->d_allowed[(e->seq + 1) & 1], e->n, cudaMemcpyDeviceToHost, e->stream));
+    SDR_CK(e, cudaMemcpyAsync(gate.data(), e->d_allowed[(e->seq + sdr_engine::RING - 1) % sdr_engine::RING], e->n, cudaMemcpyDeviceToHost, e->stream));
   }
   SDR_CK(e, cudaStreamSynchronize(e->stream));
   if (counts)
@@ -945,7 +965,7 @@ int sdr_get_signal(sdr_engine *e, uint8_t *allowed, uint32_t *magnitude) {
   if (!e->last_gated || e->seq == 0) return fail(e, SDR_E_ARG, "no squelch result: set a threshold or enable signal reports first");
   SDR_CK(e, cudaSetDevice(e->device));
   if (allowed)
-    SDR_CK(e, cudaMemcpyAsync(allowed, e->d_allowed[(e->seq + 1) & 1], e->n, cudaMemcpyDeviceToHost, e->stream));
+    SDR_CK(e, cudaMemcpyAsync(allowed, e->d_allowed[(e->seq + sdr_engine::RING - 1) % sdr_engine::RING], e->n, cudaMemcpyDeviceToHost, e->stream));
   if (magnitude)
     SDR_CK(e, cudaMemcpyAsync(magnitude, e->d_magnitude, (size_t)e->n * 4, cudaMemcpyDeviceToHost, e->stream));
   SDR_CK(e, cudaStreamSynchronize(e->stream));
@@ -1124,7 +1144,7 @@ int sdr_ingest_commit(sdr_ingest *q, uint32_t timestamp, uint64_t bytes, uint32_
   SDR_CK(e, cudaMemcpy2DAsync(s.h_pcm, row, e->d_pcm, e->pcm_stride * 2, row, e->n, cudaMemcpyDeviceToHost, q->d2h));
   s.gated = e->last_gated;
   if (s.gated)
-    SDR_CK(e, cudaMemcpyAsync(s.h_gate, e->d_allowed[(e->seq + 1) & 1], e->n, cudaMemcpyDeviceToHost, q->d2h));
+    SDR_CK(e, cudaMemcpyAsync(s.h_gate, e->d_allowed[(e->seq + sdr_engine::RING - 1) % sdr_engine::RING], e->n, cudaMemcpyDeviceToHost, q->d2h));
   SDR_CK(e, cudaEventRecord(s.ev_done, q->d2h));
   s.timestamp = timestamp;
   s.bytes = bytes;
