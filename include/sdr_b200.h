@@ -133,7 +133,9 @@ int sdr_iq_dump_device(sdr_engine *e, int8_t **rows, uint64_t *row_stride, uint3
 /* One block for every channel: iq is [n_channels][channel_stride] bytes of
  * interleaved I,Q of which the first bytes_per_channel are consumed.
  * bytes_per_channel must be a multiple of 64 (one PCM sample); pointers and
- * stride multiples of 16. Asynchronous: returns once the work is queued. Each
+ * stride multiples of 16. Asynchronous: returns once the work is queued; a caller
+ * that queues faster than the GPU retires is held while 32 calls are in flight
+ * (environment SDR_PACE = 0..256 changes the bound, 0 removes it). Each
  * channel is demodulated by the mode it is in, exactly as the reference's
  * switch does; channels in mode None produce nothing. Filter state carries
  * over to the next call. */
