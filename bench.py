@@ -124,7 +124,7 @@ class ClockSampler:
         return out
 
 
-def run_cpu_reference(workload, modes_np, n_blocks, seconds_target=6.0, signal="tone"):
+def run_cpu_reference(workload, modes_np, n_blocks, seconds_target=6.0, signal="tone", check_gpu=False):
     """The reference's CPU chain on this box's host cores over a bounded sample of the
     workload. Returns (Msamples/s, descriptor dict). Uses oracle/_ref (the unmodified
     reference) when it was built, else the oracle port."""
@@ -151,9 +151,19 @@ def run_cpu_reference(workload, modes_np, n_blocks, seconds_target=6.0, signal="
         done += n_ch * nbytes // 2
         reps += 1
     msps = done / elapsed / 1e6
-    return msps, {"value": round(msps, 3), "unit": "Msamples/s", "cores": cores, "kind": kind,
-                  "sample": "%d channels x %d blocks of the %s workload, %d repetitions, %d host threads"
-                            % (n_ch, t_blocks, workload, reps, cores)}
+    desc = {"value": round(msps, 3), "unit": "Msamples/s", "cores": cores, "kind": kind,
+            "sample": "%d channels x %d blocks of the %s workload, %d repetitions, %d host threads"
+                      % (n_ch, t_blocks, workload, reps, cores)}
+    if check_gpu:
+        # the GPU's PCM for this very sample against the PCM the CPU chain just produced
+        import rtlsdrdiags_b200 as R
+        ref_pcm, _ = (O.ref_bank if use_ref else O.oracle_bank)(modes, iq, BLOCK_BYTES, cores, want_pcm=True)
+        eng = R.Engine(n_ch, 0, BLOCK_BYTES)
+        eng.set_modes(modes)
+        got, _ = eng.demodulate(iq)  # one reference-sized block per call, state carried
+        eng.close()
+        desc["gpu_pcm_identical"] = bool(np.array_equal(got, ref_pcm))
+    return msps, desc
 
 
 def bench_one(torch, R, synth, workload, channels, n_blocks, steps, warmup, signal, device, rank, world,
@@ -377,7 +387,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         modes = synth.modes_for(args.workload, channels).numpy()
-        _, cpu = run_cpu_reference(args.workload, modes, n_blocks, seconds_target=12.0, signal=args.signal)
+        _, cpu = run_cpu_reference(args.workload, modes, n_blocks, seconds_target=12.0, signal=args.signal, check_gpu=True)
 
     if rank == 0:
         line = {
