@@ -239,3 +239,31 @@ def test_fm_tensor_core_tuner_and_clipping_fallback(fmt):
             want = chains[ch].accept_u8(piece[ch])
             assert counts[ch] == want.size
             assert np.array_equal(pcm[ch][:counts[ch]], want), (fmt, a, ch)
+
+
+def test_first_generation_wbfm_kernel_still_matches_the_oracle():
+    """wbfm_tile_kernel (atan2 gathered from global memory) is the fallback when the host libm's
+    atan2 is not odd in q; SDR_WB_KERNEL=1 selects it. The choice is read once per process, so the
+    check runs in a child process."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "tests")
+import _oracle as O, _signals as S
+import rtlsdrdiags_b200 as R
+n, nbytes = 21, 32768 * 2 + 4096
+e = R.Engine(n, 0, 32768)
+e.set_modes(np.full(n, 3, dtype=np.uint8))
+iq = np.concatenate([S.noise(7, nbytes, seed=3), S.tone_bank([3] * 14, nbytes, seed=4)])
+pcm, counts = e.demodulate(iq)
+for ch in range(n):
+    c = O.OracleChain(); c.set_mode(3)
+    assert np.array_equal(pcm[ch], c.accept_u8(iq[ch])), ch
+print("ok")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, SDR_WB_KERNEL="1"),
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
