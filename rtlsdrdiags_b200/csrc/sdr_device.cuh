@@ -76,11 +76,13 @@ SDR_DEV float wrap_pi(float d) {
   return dadd_to_f(d, off);
 }
 
-// The same wrap without FP64, for differences of WBFM atan2-TABLE values only: 2 pi = HI + LO
-// with HI = (float)(2 pi); d - HI is exact (Sterbenz), and subtracting LO in float rounds to the
-// value the reference's double subtraction rounds to for every pair of the table's 39,920
-// distinct values (checked exhaustively, 1.59e9 pairs: tests/test_emu_parity.py). Not valid
-// for arbitrary floats (NBFM's per-sample atan2 of wider operands keeps wrap_pi).
+// The same wrap without FP64, for differences of two atan2-TABLE values only (both kernels take
+// theta from a table: WBFM 256x256, WbFmDemodulator.cc:159-170; NBFM 280x280 over the tuner's
+// output range): 2 pi = HI + LO with HI = (float)(2 pi); d - HI is exact (Sterbenz), and
+// subtracting LO in float rounds to the value the reference's double subtraction rounds to for
+// EVERY pair of distinct table values -- checked exhaustively, 39,920^2 = 1.59e9 pairs of the WBFM
+// table and 47,808^2 = 2.29e9 of the NBFM table (tests/test_emu_parity.py). Not valid for
+// arbitrary floats.
 SDR_DEV float wrap_pi_table(float d) {
   const float PI_F = 3.14159274101257324f;
   const uint32_t s = f2u(d) & 0x80000000u;

@@ -825,7 +825,7 @@ struct FmTile {
     int d[8];
     if (wraps || patch) {  // warp-uniform: a real branch, so the quiet path executes none of it
 #pragma unroll
-      for (int m = 0; m < 8; ++m) d[m] = f2i16_wrap(fmul(k, wrap_pi(df[m])));
+      for (int m = 0; m < 8; ++m) d[m] = f2i16_wrap(fmul(k, wrap_pi_table(df[m])));  // df: a difference of two table values
     } else {
 #pragma unroll
       for (int m = 0; m < 8; ++m) d[m] = (int)(int16_t)f2i_rz(fmul(k, df[m]));

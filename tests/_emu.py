@@ -24,7 +24,7 @@ def build(defines=()):
            [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
     if os.path.exists(out) and not defines and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in srcs):
         return out
-    cmd = ["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fno-fast-math", "-DSDR_EMU", "-fPIC",
+    cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-DSDR_EMU", "-fPIC",
            "-shared", "-I", CSRC, "-I", EMU_DIR, "-o", out, os.path.join(EMU_DIR, "emu.cc")] + ["-D" + d for d in defines]
     subprocess.run(cmd, check=True)
     return out

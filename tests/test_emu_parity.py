@@ -89,12 +89,14 @@ def test_table_wrap_without_fp64_equals_the_double_wrap_for_every_table_pair():
     instead of the reference's double arithmetic (WbFmDemodulator.cc:472-480). Exhaustive over
     all pairs of the atan2 table's distinct values: 39,920^2 = 1.59e9 differences."""
     import ctypes as C
-    vals = np.unique(E.lut(E.KIND_WBFM).ravel())
-    assert vals.size == 39920
     L = E.lib()
     L.emu_wrap_table_check.restype = C.c_uint64
     L.emu_wrap_table_check.argtypes = [C.c_void_p, C.c_uint32]
-    assert L.emu_wrap_table_check(vals.ctypes.data_as(C.c_void_p), vals.size) == 0
+    # ... and of the NBFM kernel's 280 x 280 table (fm_tile_kernel's discriminator): 47,808^2 = 2.29e9
+    for kind, distinct in ((E.KIND_WBFM, 39920), (E.KIND_FM, 47808)):
+        vals = np.unique(E.lut(kind).ravel())
+        assert vals.size == distinct
+        assert L.emu_wrap_table_check(vals.ctypes.data_as(C.c_void_p), vals.size) == 0
 
 
 def test_wbfm_table_is_odd_in_q():
