@@ -240,6 +240,36 @@ SDR_DEV int fir_s16_exact_range(const uint32_t (&w)[NW], int acc) {
     return acc;
   }
 }
+// The middle taps WITHOUT the clamp, keeping the largest and smallest prefix sum: if every prefix
+// stayed inside [-2^30, 2^30-1] the reference's clamps changed nothing and the plain sum is its
+// result. One dependent IMAD per tap instead of IMAD -> min -> max. (No int32 overflow can hide a
+// violation: up to the first prefix outside the range every |prefix| <= 2^30 and a term is below
+// 2^29, and hi / lo never forget that first violation.)
+template <class F, int P, int NW, int K, int KEND>
+SDR_DEV void fir_s16_prefix_range(const uint32_t (&w)[NW], int &acc, int &hi, int &lo) {
+  if constexpr (K < KEND) {
+    constexpr int pos = P - K;
+    constexpr int t = F::tap(K);
+    if constexpr (pos >= 0 && pos < 2 * NW) {
+      const int x = (pos & 1) ? ((int)w[pos / 2] >> 16) : (int)(int16_t)(w[pos / 2] & 0xffffu);
+      acc += t * x;
+      hi = acc > hi ? acc : hi;
+      lo = acc < lo ? acc : lo;
+    }
+    fir_s16_prefix_range<F, P, NW, K + 1, KEND>(w, acc, hi, lo);
+  }
+}
+// head + unclamped middle; clean = no prefix of the middle left the clamp range
+template <class F, int P, int NW>
+SDR_DEV int fir_s16_guard_mid_plain(const uint32_t (&w)[NW], bool &clean) {
+  static_assert(F::N <= 64, "a term t * x must stay below 2^29");
+  int h = 0, l = 1 << 14;
+  fir_s16_acc<TapRange<F, 0, Guard<F>::HEAD>, P, NW>(w, h, l);
+  int acc = (h << 8) + l, hi = acc, lo = acc;
+  fir_s16_prefix_range<F, P, NW, Guard<F>::HEAD, Guard<F>::TAIL>(w, acc, hi, lo);
+  clean = hi <= 0x3fffffff && lo >= -0x40000000;
+  return acc;
+}
 // head + clamped middle; the caller decides about the tail (warp-uniformly on the GPU)
 template <class F, int P, int NW>
 SDR_DEV int fir_s16_guard_mid(const uint32_t (&w)[NW]) {

@@ -870,7 +870,11 @@ struct FmTile {
     if (!exact_b) {
       acc = fir_s16_fast<taps::AUDIO40, 39, 20>(ee);
     } else {
-      acc = fir_s16_guard_mid<taps::AUDIO40, 39, 20>(ee);
+      // middle taps first without the clamp; only if some lane's prefix sums left the clamp range
+      // does the warp redo them in the reference's clamped order
+      bool clean;
+      acc = fir_s16_guard_mid_plain<taps::AUDIO40, 39, 20>(ee, clean);
+      if (__any_sync(FULL, !clean)) acc = fir_s16_guard_mid<taps::AUDIO40, 39, 20>(ee);
       const bool clamped = __any_sync(FULL, !fir_s16_guard_tail_is_free<taps::AUDIO40>(acc));
       acc = fir_s16_guard_tail<taps::AUDIO40, 39, 20>(ee, acc, clamped);
     }
