@@ -249,12 +249,21 @@ int sdr_filter_bank_run(sdr_filter_bank *b, const void *in, uint64_t in_stride, 
     case 4: FB_LAUNCH(T, false, 4); break;    \
     default: FB_LAUNCH(T, false, 0); break;   \
   }
+#define FB_LAUNCH_INT(T)                      \
+  switch (b->F) {                             \
+    case 2: FB_LAUNCH(T, true, 2); break;     \
+    case 3: FB_LAUNCH(T, true, 3); break;     \
+    case 4: FB_LAUNCH(T, true, 4); break;     \
+    case 8: FB_LAUNCH(T, true, 8); break;     \
+    default: FB_LAUNCH(T, true, 0); break;    \
+  }
   switch (b->kind) {
     case SDR_FILTER_DECIMATOR_F32: FB_LAUNCH_DEC(float); break;
-    case SDR_FILTER_INTERPOLATOR_F32: FB_LAUNCH(float, true, 0); break;
+    case SDR_FILTER_INTERPOLATOR_F32: FB_LAUNCH_INT(float); break;
     case SDR_FILTER_DECIMATOR_I16: FB_LAUNCH_DEC(int16_t); break;
-    case SDR_FILTER_INTERPOLATOR_I16: FB_LAUNCH(int16_t, true, 0); break;
+    case SDR_FILTER_INTERPOLATOR_I16: FB_LAUNCH_INT(int16_t); break;
   }
+#undef FB_LAUNCH_INT
 #undef FB_LAUNCH_DEC
 #undef FB_LAUNCH
   FB_CK(b, cudaGetLastError());

@@ -82,6 +82,61 @@ __device__ __forceinline__ void fb_compute(const FilterBankParams &p, const type
   using tap_t = typename A::tap_t;
   using acc_t = typename A::acc_t;
   T *out_row = reinterpret_cast<T *>(p.out) + (uint64_t)row * p.out_stride;
+  if constexpr (INTERP && MT > 0) {
+    // Interpolator with the factor known at compile time: a thread owns INPUT samples (n, n + 256)
+    // and all L outputs of each. Per tap index k it loads the L taps h[kL .. kL+L-1] with one or two
+    // vector loads (the same for every lane) and one input per owned sample: 2 L multiply-adds for
+    // 3 shared-memory loads instead of 2 loads per multiply-add. Every output still accumulates
+    // its own taps h[i], h[i+L], ... in that order (Interpolator.cc filterData).
+    constexpr int L = MT, RN = 2;
+    const uint32_t n_tile = p.tile_out / L;  // inputs per tile
+    for (uint32_t n0 = threadIdx.x; n0 < n_tile; n0 += RN * FB_THREADS) {
+      if (o0 + (uint64_t)n0 * L >= p.n_out) break;
+      acc_t acc[RN][L];
+      const T *xp[RN];
+#pragma unroll
+      for (int j = 0; j < RN; ++j) {
+        xp[j] = X + min(n0 + j * FB_THREADS, n_tile - 1) + (p.q - 1);  // newest input, span index
+#pragma unroll
+        for (int i = 0; i < L; ++i) acc[j][i] = A::init();
+      }
+      for (uint32_t k = 0; k < p.q; ++k) {
+        tap_t hk[L];
+        if constexpr (L % 4 == 0) {
+#pragma unroll
+          for (int v = 0; v < L / 4; ++v) {
+            const uint4 t4 = *reinterpret_cast<const uint4 *>(h + k * L + 4 * v);
+            memcpy(&hk[4 * v], &t4, 16);
+          }
+        } else if constexpr (L % 2 == 0) {
+#pragma unroll
+          for (int v = 0; v < L / 2; ++v) {
+            const uint2 t2 = *reinterpret_cast<const uint2 *>(h + k * L + 2 * v);
+            memcpy(&hk[2 * v], &t2, 8);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < L; ++i) hk[i] = h[k * L + i];
+        }
+#pragma unroll
+        for (int j = 0; j < RN; ++j) {
+          const T x = *(xp[j] - k);
+#pragma unroll
+          for (int i = 0; i < L; ++i) acc[j][i] = A::mac(acc[j][i], hk[i], x);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < RN; ++j) {
+        const uint32_t n = n0 + j * FB_THREADS;
+        const uint64_t o = o0 + (uint64_t)n * L;
+        if (n < n_tile && o < p.n_out) {
+#pragma unroll
+          for (int i = 0; i < L; ++i) out_row[o + i] = A::done(acc[j][i]);
+        }
+      }
+    }
+    return;
+  }
   // R outputs per thread and pass (t, t + 256, ..): one tap load serves R accumulators. Outputs
   // past the tile or the row read staged zeros / neighbours and are simply not stored.
   constexpr int R = 4;

@@ -267,13 +267,28 @@ __global__ void __launch_bounds__(32 * (WbTile2::MAX_WORKERS + 1), 1) wbfm_tile2
         // and every shared address is base + immediate -- the warp issues nothing but the loads,
         // the chain and the stores. (Fetching the next row early was measured twice and lost 4-13 %:
         // the extra loads in flight land between the chain's dependent instructions.)
+        u32x4 first = lds_u4(ring);  // row 0, chunk 0 ^ 0
         for (int row0 = 0; row0 < 32; row0 += 8) {
           char *base = ring + 128 * row0;
 #pragma unroll
           for (int rr = 0; rr < 8; ++rr) {
+            // only the row's FIRST chunk is fetched ahead (in the middle of the row before): it is
+            // what the chain needs first, the other seven arrive while its four steps run
             u32x4 v[8];
-            T::chain_load(base + 128 * rr, rr, v);
-            T::chain_run(base + 128 * rr, rr, v, a1, y1);
+            char *row = base + 128 * rr;
+            v[0] = first;
+#pragma unroll
+            for (int j = 1; j < 8; ++j) v[j] = lds_u4(row + 16 * (j ^ rr));
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float y0 = fsub(u2f(v[j].x), fmul(a1, y1));
+              const float y2 = fsub(u2f(v[j].y), fmul(a1, y0));
+              const float y3 = fsub(u2f(v[j].z), fmul(a1, y2));
+              y1 = fsub(u2f(v[j].w), fmul(a1, y3));
+              sts_u4(row + 16 * (j ^ rr), u32x4{f2u(y0), f2u(y2), f2u(y3), f2u(y1)});
+              // next row's chunk 0 (row 32 = the pad behind the slot for the last row: read, never used)
+              if (j == 3) first = lds_u4(row + 128 + 16 * ((rr + 1) & 7));
+            }
           }
         }
       } else {
