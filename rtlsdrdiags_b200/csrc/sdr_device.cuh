@@ -49,7 +49,23 @@ struct LaunchParams {
   const uint8_t *allowed;    // [n_channels] squelch gate of this call, or nullptr = all open
   uint32_t call_id;          // AM/SSB/FM: 31-bit id of this call, never 0 (versions the carry buffers)
   const uint32_t *tab;       // FM: tensor-core tuner tables (fm_mma_table in sdr_engine.cu)
+  unsigned long long *trace; // SDR_TRACE=1 only: [0] = earliest CTA start, [1] = latest CTA end of this launch (globaltimer ns)
 };
+
+#if SDR_DEVICE_BUILD
+// launch timeline for tools/probe_timeline.py (engine built as usual, SDR_TRACE=1 in the environment)
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_begin(const LaunchParams &p) {
+  if (p.trace && threadIdx.x == 0) atomicMin(p.trace, trace_now());
+}
+__device__ __forceinline__ void trace_end(const LaunchParams &p) {
+  if (p.trace && threadIdx.x == 0) atomicMax(p.trace + 1, trace_now());
+}
+#endif
 
 // ---------------------------------------------------------------------------
 // C-semantics helpers

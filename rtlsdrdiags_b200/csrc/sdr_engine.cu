@@ -46,14 +46,15 @@ struct sdr_engine {
   // kernel always started beside call k+1's FIR kernel; when the FIR kernel's CTAs take every SM
   // first, the recurrence runs one call later, and with three buffers call k+2 need not wait for it
   // (profiles/r01v7_pacing.txt)
-  static constexpr int RING = 3;
-  cudaEvent_t ev_fir[RING] = {}, ev_rec[RING] = {};
+  static constexpr int RING_MAX = 8;
+  int ring = 3;  // buffers in use (SDR_RING)
+  cudaEvent_t ev_fir[RING_MAX] = {}, ev_rec[RING_MAX] = {};
   // pacing: a caller that queues calls faster than the GPU retires them is held once PACE calls
   // are in flight (see sdr_accept_iq)
   static constexpr int PACE = 256;
   cudaEvent_t ev_pace[PACE] = {};
   int pace_depth = 32;
-  float *d_scratch[5][RING] = {};
+  float *d_scratch[5][RING_MAX] = {};
   uint64_t seq = 0;        // sdr_accept_iq calls so far
   bool rec_pending = false;  // work on rec_stream that `stream` has not waited for yet
   // Mixed banks: the WBFM kernel (one long-lived CTA per SM that leaves issue slots, registers
@@ -87,7 +88,7 @@ struct sdr_engine {
   bool squelch_dirty = false, squelch_armed = false, signal_reports = false;
   int32_t *d_threshold = nullptr;
   uint32_t *d_rx_gain = nullptr, *d_magnitude = nullptr;
-  uint8_t *d_tracking = nullptr, *d_allowed[RING] = {};
+  uint8_t *d_tracking = nullptr, *d_allowed[RING_MAX] = {};
   int32_t *d_db_table = nullptr;
   bool last_gated = false;  // the last accept ran the squelch kernel with the gate in force
 
@@ -100,6 +101,9 @@ struct sdr_engine {
   size_t dump_rows = 0;       // rows d_dump holds
   uint64_t dump_bytes = 0;    // bytes per channel of the last dump (0 = none)
 
+  // SDR_TRACE=1: per call [FIR start, FIR end, dc_block start, dc_block end] in globaltimer ns (tools/probe_timeline.py)
+  unsigned long long *d_trace = nullptr;
+  static constexpr uint64_t TRACE_CALLS = 4096;
   Shape shape[5];
   uint32_t last_samples = 0;  // PCM samples per channel of the last accept
   uint64_t launches = 0;
@@ -168,7 +172,7 @@ float scale_of(int kind, float gain, int scaling) {
 // main stream waits for everything queued on rec_stream
 int join_streams(sdr_engine *e) {
   if (e->rec_pending) {
-    SDR_CK(e, cudaStreamWaitEvent(e->stream, e->ev_rec[(e->seq + sdr_engine::RING - 1) % sdr_engine::RING], 0));
+    SDR_CK(e, cudaStreamWaitEvent(e->stream, e->ev_rec[(e->seq + (uint64_t)e->ring - 1) % (uint64_t)e->ring], 0));
     e->rec_pending = false;
   }
   if (e->wb_pending) {
@@ -184,7 +188,7 @@ int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride,
   using T = AmSsbTile<SSB>;
   const uint32_t n_list = (uint32_t)e->list[kind].size();
   if (n_list == 0) return SDR_OK;
-  const int par = (int)(e->seq % sdr_engine::RING);
+  const int par = (int)(e->seq % (uint64_t)e->ring);
   const uint32_t n_tiles = (n_samples + TILE - 1) / TILE;
   if (!e->d_scratch[kind][par]) {
     const size_t max_tiles = (size_t)((e->max_bytes / 2 + TILE - 1) / TILE);
@@ -218,6 +222,7 @@ int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride,
   p.call_id = (uint32_t)(e->seq % 0x7fffffffull) + 1;
   p.scratch = e->d_scratch[kind][par];
   p.allowed = e->last_gated ? e->d_allowed[par] : nullptr;
+  p.trace = e->d_trace ? e->d_trace + 4 * (e->seq % sdr_engine::TRACE_CALLS) : nullptr;
   amssb_fir_kernel<SSB><<<(uint32_t)((n_warps + 3) / 4), 128, 4 * 2 * TILE_BYTES, e->stream>>>(p);
   SDR_CK(e, cudaGetLastError());
   e->launches++;
@@ -227,7 +232,7 @@ int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride,
 int launch_dc_block(sdr_engine *e, int kind, uint32_t n_samples) {
   const uint32_t n_list = (uint32_t)e->list[kind].size();
   if (n_list == 0) return SDR_OK;
-  const int par = (int)(e->seq % sdr_engine::RING);
+  const int par = (int)(e->seq % (uint64_t)e->ring);
   const int nreg = kind == SDR_KIND_SSB ? AmSsbTile<true>::NREG : AmSsbTile<false>::NREG;
   LaunchParams p = {};
   p.n_samples = n_samples;
@@ -241,13 +246,18 @@ int launch_dc_block(sdr_engine *e, int kind, uint32_t n_samples) {
   p.aux = (uint32_t)nreg * 256;  // byte offset of the IIR tail in the state blob (after both carry buffers)
   p.scratch = e->d_scratch[kind][par];
   p.allowed = e->last_gated ? e->d_allowed[par] : nullptr;
+  p.trace = e->d_trace ? e->d_trace + 4 * (e->seq % sdr_engine::TRACE_CALLS) + 2 : nullptr;
   // Small banks: few CTAs, so each gets seven helper warps and the chain warp is never kept
   // waiting; large banks: three helpers, so the many CTAs leave the FIR kernel its registers.
   static const int helpers_env = getenv("SDR_DC_HELPERS") ? atoi(getenv("SDR_DC_HELPERS")) : 0;
   const int helpers = helpers_env ? helpers_env : (n_list <= 32u * (uint32_t)e->n_sm ? 7 : 3);
   if (helpers > 3) {
     SDR_CK(e, cudaFuncSetAttribute(dc_block_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM_BYTES));
-    dc_block_kernel<7><<<(n_list + 31) / 32, 32 * 8, DC_SMEM_BYTES, e->rec_stream>>>(p);
+    // extra (unused) shared memory keeps the FIR kernel's CTAs off the few SMs that host a recurrence CTA
+    static const int pad_env = getenv("SDR_DC_PAD_KB") ? atoi(getenv("SDR_DC_PAD_KB")) : 0;
+    const int smem7 = DC_SMEM_BYTES + 1024 * pad_env;
+    SDR_CK(e, cudaFuncSetAttribute(dc_block_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem7));
+    dc_block_kernel<7><<<(n_list + 31) / 32, 32 * 8, smem7, e->rec_stream>>>(p);
   } else {
     SDR_CK(e, cudaFuncSetAttribute(dc_block_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM_BYTES));
     dc_block_kernel<3><<<(n_list + 31) / 32, 32 * 4, DC_SMEM_BYTES, e->rec_stream>>>(p);
@@ -353,7 +363,7 @@ int launch_fm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_
   p.call_id = (uint32_t)(e->seq % 0x7fffffffull) + 1;
   p.tab = e->d_fm_tab;
   p.scratch = nullptr;
-  p.allowed = e->last_gated ? e->d_allowed[e->seq % sdr_engine::RING] : nullptr;
+  p.allowed = e->last_gated ? e->d_allowed[e->seq % (uint64_t)e->ring] : nullptr;
   const uint32_t grid = (uint32_t)((n_warps + G - 1) / G);
   static const int minb_env = getenv("SDR_FM_MIN_CTAS") ? atoi(getenv("SDR_FM_MIN_CTAS")) : 0;
   switch (minb_env) {
@@ -402,7 +412,7 @@ int launch_wbfm_tile2(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint
   static const int rec_env = getenv("SDR_WB_REC") ? atoi(getenv("SDR_WB_REC")) : -1;  // tuning override
   p.aux = (uint32_t)((rec_env >= 0 && rec_env <= (int)G) ? rec_env : std::min((int)G, (int)T::REC_WARP));
   p.scratch = nullptr;
-  p.allowed = e->last_gated ? e->d_allowed[e->seq % sdr_engine::RING] : nullptr;
+  p.allowed = e->last_gated ? e->d_allowed[e->seq % (uint64_t)e->ring] : nullptr;
   SDR_CK(e, cudaFuncSetAttribute(wbfm_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const uint32_t grid = (n_list + G - 1) / G;
   wbfm_tile2_kernel<<<grid, 32 * T::warps_for((int)G), smem, stream>>>(p);
@@ -448,7 +458,7 @@ int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint3
   static const int s3_env = getenv("SDR_WB_S3") ? atoi(getenv("SDR_WB_S3")) : 4;
   p.aux = (uint32_t)s3_env;
   p.scratch = nullptr;
-  p.allowed = e->last_gated ? e->d_allowed[e->seq % sdr_engine::RING] : nullptr;
+  p.allowed = e->last_gated ? e->d_allowed[e->seq % (uint64_t)e->ring] : nullptr;
   SDR_CK(e, cudaFuncSetAttribute(wbfm_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const uint32_t grid = (n_list + G - 1) / G;
   wbfm_tile_kernel<<<grid, 32 * T::warps_for((int)G, s3_env), smem, stream>>>(p);
@@ -514,7 +524,7 @@ int run_squelch(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint64_t b
       SDR_CK(e, cudaMalloc(&e->d_rx_gain, (size_t)e->n * 4));
       SDR_CK(e, cudaMalloc(&e->d_magnitude, (size_t)e->n * 4));
       SDR_CK(e, cudaMalloc(&e->d_tracking, e->n));
-      for (int i = 0; i < sdr_engine::RING; ++i) SDR_CK(e, cudaMalloc(&e->d_allowed[i], e->n));
+      for (int i = 0; i < sdr_engine::RING_MAX; ++i) SDR_CK(e, cudaMalloc(&e->d_allowed[i], e->n));
       SDR_CK(e, cudaMalloc(&e->d_db_table, 128 * 4));
       // until now every block of every channel passed: the trackers are in `Tracking`
       // (SignalTracker.cc:104-145) if any block was seen, else in `NoSignal`
@@ -546,7 +556,7 @@ int run_squelch(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint64_t b
   q.threshold = e->d_threshold;
   q.gain_db = e->d_rx_gain;
   q.tracking = e->d_tracking;
-  q.allowed = e->d_allowed[e->seq % sdr_engine::RING];
+  q.allowed = e->d_allowed[e->seq % (uint64_t)e->ring];
   q.magnitude = e->d_magnitude;
   q.db_table = e->d_db_table;
   squelch_kernel<<<e->n, 128, 0, e->stream>>>(q);
@@ -640,12 +650,19 @@ int sdr_engine_create(uint32_t n_channels, int device, uint64_t max_bytes_per_ch
     SDR_CK_CREATE(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
     SDR_CK_CREATE(cudaEventCreateWithFlags(&e->ev_wb, cudaEventDisableTiming));
   }
-  for (int i = 0; i < sdr_engine::RING; ++i) {
+  for (int i = 0; i < sdr_engine::RING_MAX; ++i) {
     SDR_CK_CREATE(cudaEventCreateWithFlags(&e->ev_fir[i], cudaEventDisableTiming));
     SDR_CK_CREATE(cudaEventCreateWithFlags(&e->ev_rec[i], cudaEventDisableTiming));
   }
   for (int i = 0; i < sdr_engine::PACE; ++i)
     SDR_CK_CREATE(cudaEventCreateWithFlags(&e->ev_pace[i], cudaEventDisableTiming));
+  if (getenv("SDR_TRACE") && atoi(getenv("SDR_TRACE"))) {
+    std::vector<unsigned long long> init(4 * sdr_engine::TRACE_CALLS);
+    for (size_t i = 0; i < init.size(); ++i) init[i] = (i & 1) ? 0ull : ~0ull;
+    SDR_CK_CREATE(cudaMalloc(&e->d_trace, init.size() * 8));
+    SDR_CK_CREATE(cudaMemcpy(e->d_trace, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+  }
+  if (getenv("SDR_RING")) e->ring = std::max(2, std::min((int)sdr_engine::RING_MAX, atoi(getenv("SDR_RING"))));
   if (getenv("SDR_PACE")) e->pace_depth = std::max(0, std::min((int)sdr_engine::PACE, atoi(getenv("SDR_PACE"))));  // 0 = off
   e->stream = e->own_stream;
 
@@ -726,14 +743,14 @@ int sdr_engine_destroy(sdr_engine *e) {
   }
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_wb) cudaEventDestroy(e->ev_wb);
-  for (int i = 0; i < sdr_engine::RING; ++i) {
+  for (int i = 0; i < sdr_engine::RING_MAX; ++i) {
     if (e->ev_fir[i]) cudaEventDestroy(e->ev_fir[i]);
     if (e->ev_rec[i]) cudaEventDestroy(e->ev_rec[i]);
   }
   for (int i = 0; i < sdr_engine::PACE; ++i)
     if (e->ev_pace[i]) cudaEventDestroy(e->ev_pace[i]);
   for (int k = 1; k <= 4; ++k) {
-    for (int i = 0; i < sdr_engine::RING; ++i) cudaFree(e->d_scratch[k][i]);
+    for (int i = 0; i < sdr_engine::RING_MAX; ++i) cudaFree(e->d_scratch[k][i]);
     cudaFree(e->d_state[k]);
     cudaFree(e->d_scale[k]);
     cudaFree(e->d_list[k]);
@@ -744,13 +761,14 @@ int sdr_engine_destroy(sdr_engine *e) {
   cudaFree(e->d_tracking);
   cudaFree(e->d_dump);
   cudaFree(e->d_dump_list);
-  for (int i = 0; i < sdr_engine::RING; ++i) cudaFree(e->d_allowed[i]);
+  for (int i = 0; i < sdr_engine::RING_MAX; ++i) cudaFree(e->d_allowed[i]);
   cudaFree(e->d_db_table);
   cudaFree(e->d_lsb);
   cudaFree(e->d_lut_fm);
   cudaFree(e->d_fm_tab);
   cudaFree(e->d_lut_wbfm);
   cudaFree(e->d_lut_wbfm_half);
+  cudaFree(e->d_trace);
   cudaFree(e->d_iq);
   cudaFree(e->d_pcm);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -840,6 +858,16 @@ int sdr_set_launch_shape(sdr_engine *e, int kind, uint32_t G, uint32_t NT) {
 
 uint64_t sdr_launch_count(const sdr_engine *e) { return e ? e->launches : 0; }
 
+// Diagnostics (not part of include/sdr_b200.h): the launch timeline recorded under SDR_TRACE=1,
+// [call % 4096][FIR start, FIR end, dc_block start, dc_block end] in globaltimer ns.
+int sdr_debug_read_trace(sdr_engine *e, unsigned long long *out, uint64_t n_calls) {
+  if (!e || !e->d_trace || !out || n_calls > sdr_engine::TRACE_CALLS) return SDR_E_ARG;
+  SDR_CK(e, cudaSetDevice(e->device));
+  SDR_CK(e, cudaDeviceSynchronize());
+  SDR_CK(e, cudaMemcpy(out, e->d_trace, n_calls * 32, cudaMemcpyDeviceToHost));
+  return SDR_OK;
+}
+
 int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_stride, uint32_t flags) {
   if (!e || !iq) return SDR_E_ARG;
   if (bytes == 0 || bytes % 64) return fail(e, SDR_E_ARG, "bytes_per_channel must be a positive multiple of 64");
@@ -872,7 +900,7 @@ int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_str
   const int fmt = (flags & SDR_IQ_S8_ROTATED) ? FMT_S8_ROTATED : FMT_U8_OFFSET_ROTATE;
   const uint32_t n_samples = (uint32_t)(bytes / 2);
   const bool have_rec = !e->list[SDR_KIND_AM].empty() || !e->list[SDR_KIND_SSB].empty();
-  const int par = (int)(e->seq % sdr_engine::RING);
+  const int par = (int)(e->seq % (uint64_t)e->ring);
   // scratch[par] and allowed[par] were last read by the recurrence kernels of the call
   // before the previous one
   if (have_rec || e->squelch_armed || e->signal_reports || e->squelch_dirty)
@@ -923,7 +951,7 @@ int sdr_get_pcm(sdr_engine *e, int16_t *pcm, uint32_t *counts) {
   std::vector<uint8_t> gate;
   if (counts && e->last_gated && e->seq > 0) {
     gate.resize(e->n);
-    SDR_CK(e, cudaMemcpyAsync(gate.data(), e->d_allowed[(e->seq + sdr_engine::RING - 1) % sdr_engine::RING], e->n, cudaMemcpyDeviceToHost, e->stream));
+    SDR_CK(e, cudaMemcpyAsync(gate.data(), e->d_allowed[(e->seq + (uint64_t)e->ring - 1) % (uint64_t)e->ring], e->n, cudaMemcpyDeviceToHost, e->stream));
   }
   SDR_CK(e, cudaStreamSynchronize(e->stream));
   if (counts)
@@ -965,7 +993,7 @@ int sdr_get_signal(sdr_engine *e, uint8_t *allowed, uint32_t *magnitude) {
   if (!e->last_gated || e->seq == 0) return fail(e, SDR_E_ARG, "no squelch result: set a threshold or enable signal reports first");
   SDR_CK(e, cudaSetDevice(e->device));
   if (allowed)
-    SDR_CK(e, cudaMemcpyAsync(allowed, e->d_allowed[(e->seq + sdr_engine::RING - 1) % sdr_engine::RING], e->n, cudaMemcpyDeviceToHost, e->stream));
+    SDR_CK(e, cudaMemcpyAsync(allowed, e->d_allowed[(e->seq + (uint64_t)e->ring - 1) % (uint64_t)e->ring], e->n, cudaMemcpyDeviceToHost, e->stream));
   if (magnitude)
     SDR_CK(e, cudaMemcpyAsync(magnitude, e->d_magnitude, (size_t)e->n * 4, cudaMemcpyDeviceToHost, e->stream));
   SDR_CK(e, cudaStreamSynchronize(e->stream));
@@ -1144,7 +1172,7 @@ int sdr_ingest_commit(sdr_ingest *q, uint32_t timestamp, uint64_t bytes, uint32_
   SDR_CK(e, cudaMemcpy2DAsync(s.h_pcm, row, e->d_pcm, e->pcm_stride * 2, row, e->n, cudaMemcpyDeviceToHost, q->d2h));
   s.gated = e->last_gated;
   if (s.gated)
-    SDR_CK(e, cudaMemcpyAsync(s.h_gate, e->d_allowed[(e->seq + sdr_engine::RING - 1) % sdr_engine::RING], e->n, cudaMemcpyDeviceToHost, q->d2h));
+    SDR_CK(e, cudaMemcpyAsync(s.h_gate, e->d_allowed[(e->seq + (uint64_t)e->ring - 1) % (uint64_t)e->ring], e->n, cudaMemcpyDeviceToHost, q->d2h));
   SDR_CK(e, cudaEventRecord(s.ev_done, q->d2h));
   s.timestamp = timestamp;
   s.bytes = bytes;

@@ -327,6 +327,7 @@ __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n_warps = p.aux;  // worker warps of the whole grid
   const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;
+  trace_begin(p);
   if (gw >= n_warps) return;
   const uint32_t n_tiles = (p.n_samples + TILE - 1) / TILE;
   // The launch is one sequence of n_list * n_tiles tiles (channel-major); warp gw takes the
@@ -415,6 +416,7 @@ __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant
       if (lane == 0) *reinterpret_cast<volatile uint32_t *>(version) = (nxt << 31) | p.call_id;
     }
   }
+  if (p.trace && lane == 0) atomicMax(p.trace + 1, trace_now());
 }
 
 // y[n] = fl(d[n] - fl(-0.95f * y[n-1])), pcm[n] = (int16_t)(gain * y[n])
@@ -435,6 +437,7 @@ constexpr int DC_SMEM_BYTES = (DC_STAGES + 2) * DC_STAGE_BYTES + 32 * 16;  // + 
 
 template <int DC_HELPERS>
 __global__ void __launch_bounds__(32 * (1 + DC_HELPERS), DC_HELPERS > 3 ? 4 : 6) dc_block_kernel(const __grid_constant__ LaunchParams p) {
+  trace_begin(p);
   extern __shared__ uint4 smem_raw[];
   char *ring = reinterpret_cast<char *>(smem_raw);            // DC_STAGES numerator tiles
   char *ybuf = ring + DC_STAGES * DC_STAGE_BYTES;             // two tiles of y
@@ -572,6 +575,7 @@ __global__ void __launch_bounds__(32 * (1 + DC_HELPERS), DC_HELPERS > 3 ? 4 : 6)
     __syncthreads();
   }
   if (active) tail[1] = y1;
+  trace_end(p);
 }
 
 
