@@ -44,10 +44,10 @@ struct sdr_engine {
   cudaStream_t rec_stream = nullptr;
   // RING: how many calls' numerators / gates exist at once. Two would do if call k's recurrence
   // kernel always started beside call k+1's FIR kernel; when the FIR kernel's CTAs take every SM
-  // first, the recurrence runs one call later, and with three buffers call k+2 need not wait for it
+  // first, the recurrence runs one or two calls later; with two buffers call k+2 had to wait for it
   // (profiles/r01v7_pacing.txt)
   static constexpr int RING_MAX = 8;
-  int ring = 3;  // buffers in use (SDR_RING)
+  int ring = 6;  // buffers in use (SDR_RING): slack for the recurrence kernel to lag the FIR kernel by a few calls
   cudaEvent_t ev_fir[RING_MAX] = {}, ev_rec[RING_MAX] = {};
   // pacing: a caller that queues calls faster than the GPU retires them is held once PACE calls
   // are in flight (see sdr_accept_iq)
