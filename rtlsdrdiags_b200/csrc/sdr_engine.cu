@@ -191,8 +191,11 @@ int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride,
   const int par = (int)(e->seq % (uint64_t)e->ring);
   const uint32_t n_tiles = (n_samples + TILE - 1) / TILE;
   if (!e->d_scratch[kind][par]) {
+    // every buffer of the ring at the kind's first call: no allocation may fall into a later call
     const size_t max_tiles = (size_t)((e->max_bytes / 2 + TILE - 1) / TILE);
-    SDR_CK(e, cudaMalloc(&e->d_scratch[kind][par], (size_t)e->n * max_tiles * 32 * sizeof(float)));
+    for (int i = 0; i < e->ring; ++i)
+      if (!e->d_scratch[kind][i])
+        SDR_CK(e, cudaMalloc(&e->d_scratch[kind][i], (size_t)e->n * max_tiles * 32 * sizeof(float)));
   }
   // The launch's tiles are dealt out in equal shares to 48 worker warps per SM (12 CTAs of 4
   // warps, of which 4-5 are resident at a time): shares small enough that SMs which also host
