@@ -114,3 +114,19 @@ def test_squelch_matches_golden_vectors():
             out[i].append(pcm[i][:counts[i]])
     for i in range(n):
         assert np.array_equal(np.concatenate(out[i]), g["pcm_%d" % i])
+
+
+@pytest.mark.parametrize("ring,pace", [(2, 1), (3, 0), (8, 256)])
+def test_squelch_and_recurrence_buffers_at_other_ring_depths(ring, pace):
+    """The scratch / gate / event ring depth (SDR_RING) and the run-ahead bound (SDR_PACE) are read
+    once per engine: the squelch test above, run in a child process at the extremes."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, 'tests'); import test_gpu_squelch as T; "
+            "T.test_squelch_matches_oracle(4096); T.test_arming_after_open_blocks_and_reports_only(); print('ok')")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root,
+                       env=dict(os.environ, SDR_RING=str(ring), SDR_PACE=str(pace)), capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
