@@ -230,13 +230,25 @@ int sdr_filter_bank_run(sdr_filter_bank *b, const void *in, uint64_t in_stride, 
     p.pitch = p.span;
   } else {
     tile = 2048;
-    while (tile > 32 && (uint64_t)M * (tile - 1) + b->N + 2 * 32 * M > budget) tile /= 2;
+    while (tile > 32 && (uint64_t)M * (tile - 1) + b->N + 3 * 32 * M > budget) tile /= 2;
     p.span = M * (tile - 1) + b->N;
-    // phases land in different banks when the staging loop writes 32 consecutive samples
-    p.pitch = ((p.span + M - 1) / M + 31) / 32 * 32 + ((32 % M) == 0 && M > 1 ? 32 / M : (M > 1 ? 1 : 0));
+    // phases land in different banks when the staging loop writes 32 consecutive samples; the eight
+    // extra words are what the 16-byte window loads of the float M = 2, 4 path may read past the data
+    p.pitch = ((p.span + M - 1) / M + 8 + 31) / 32 * 32 + ((32 % M) == 0 && M > 1 ? 32 / M : (M > 1 ? 1 : 0));
   }
+  // float decimators with M = 2, 4: taps above the highest full block of four a-values (see the kernel)
+  p.kp = 0;
+  p.hoff = 0;
+  if (!b->interp && !b->i16 && (M == 2 || M == 4)) {
+    const uint32_t a_top = (b->N - 1) / M, ph_top = (b->N - 1) % M;
+    const int a_full = (ph_top == M - 1) ? (int)a_top : (int)a_top - 1;  // largest a with every phase present
+    const int n_blocks = a_full >= 3 ? (a_full + 1) / 4 : 0;
+    p.kp = b->N - (uint32_t)n_blocks * 4 * M;
+    p.hoff = (4 - p.kp % 4) % 4;
+  }
+  p.np = (p.hoff + b->N + 3) / 4 * 4;
   p.tile_out = tile;
-  const size_t smem = (size_t)4 * b->N + (size_t)(b->interp ? p.span : (size_t)M * p.pitch) * b->esize + 16;
+  const size_t smem = (size_t)4 * p.np + (size_t)(b->interp ? p.span : (size_t)M * p.pitch) * b->esize + 16;
   if (smem > 48 * 1024) return fb_fail(b, SDR_E_ARG, "tile does not fit in shared memory");
   const uint64_t tiles = n_out ? (n_out + tile - 1) / tile : 1;
   if (tiles > 0x7fffffffull) return fb_fail(b, SDR_E_TOO_LONG, "too many tiles");

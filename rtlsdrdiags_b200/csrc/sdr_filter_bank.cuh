@@ -43,6 +43,8 @@ struct FilterBankParams {
   uint32_t span;          // input samples a full tile needs
   uint32_t pitch;         // words per phase row of X
   uint32_t sum_abs_taps;  // Q15 kinds: sum |q[k]|
+  uint32_t hoff, np;      // taps sit at word hoff of the tap area (so that tap blocks are 16-byte aligned), X at word np
+  uint32_t kp;            // float decimators with M = 2, 4: taps before the first full block of 4 M
 };
 
 // CLAMP = false: the tile's samples are small enough that no partial sum can reach the Q15
@@ -137,6 +139,58 @@ __device__ __forceinline__ void fb_compute(const FilterBankParams &p, const type
     }
     return;
   }
+  if constexpr (!INTERP && (MT == 2 || MT == 4) && sizeof(T) == 4 && sizeof(tap_t) == 4) {
+    // Float decimator, M = 2 or 4: a thread owns FOUR CONSECUTIVE outputs t0 .. t0+3. Tap k meets the
+    // sample at X[ph][t + a] with a = (N-1-k) / M, ph = (N-1-k) % M; four consecutive values of a
+    // for four consecutive outputs touch seven consecutive words of a phase row, i.e. two aligned
+    // 16-byte loads (t0 and the block's lowest a are multiples of 4), and the block's 4 M taps are
+    // consecutive in k: 2 M + M loads of 16 bytes feed 16 M multiply-adds, against one load per
+    // multiply-add. Each output still adds its taps in the reference's order k = 0, 1, ...
+    // (Decimator.cc:168-209): the kp taps above the highest full block one by one, then the blocks
+    // from the highest a down, within a block a descending and ph descending.
+    constexpr int M_ = MT;
+    const int n_blocks = (int)((p.N - p.kp) / (4 * M_));
+    for (uint32_t t0 = 4 * threadIdx.x; t0 < p.tile_out; t0 += 4 * FB_THREADS) {
+      if (o0 + t0 >= p.n_out) break;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      for (uint32_t k = 0; k < p.kp; ++k) {
+        const uint32_t r = p.N - 1 - k;
+        const float hk = h[k];
+        const float *xr = X + (r % M_) * p.pitch + t0 + r / M_;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] = fadd(acc[j], fmul(hk, xr[j]));
+      }
+      const float *hb = h + p.kp;
+      for (int m = n_blocks - 1; m >= 0; --m, hb += 4 * M_) {
+        float tp[4 * M_];
+#pragma unroll
+        for (int v = 0; v < M_; ++v) {
+          const uint4 t4 = *reinterpret_cast<const uint4 *>(hb + 4 * v);
+          memcpy(&tp[4 * v], &t4, 16);
+        }
+        float W[M_][8];
+#pragma unroll
+        for (int ph = 0; ph < M_; ++ph) {
+          const uint4 lo = *reinterpret_cast<const uint4 *>(X + ph * p.pitch + t0 + 4 * m);
+          const uint4 hi = *reinterpret_cast<const uint4 *>(X + ph * p.pitch + t0 + 4 * m + 4);
+          memcpy(&W[ph][0], &lo, 16);
+          memcpy(&W[ph][4], &hi, 16);
+        }
+#pragma unroll
+        for (int g = 3; g >= 0; --g)
+#pragma unroll
+          for (int ph = M_ - 1; ph >= 0; --ph) {
+            const float hk = tp[(3 - g) * M_ + (M_ - 1 - ph)];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] = fadd(acc[j], fmul(hk, W[ph][j + g]));
+          }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (t0 + j < p.tile_out && o0 + t0 + j < p.n_out) out_row[o0 + t0 + j] = acc[j];
+    }
+    return;
+  }
   // R outputs per thread and pass (t, t + 256, ..): one tap load serves R accumulators. Outputs
   // past the tile or the row read staged zeros / neighbours and are simply not stored.
   constexpr int R = 4;
@@ -194,8 +248,8 @@ template <class T, bool INTERP, int MT>
 __global__ void __launch_bounds__(FB_THREADS) filter_bank_kernel(const __grid_constant__ FilterBankParams p) {
   using tap_t = typename FbAcc<T, true>::tap_t;
   extern __shared__ uint4 fb_smem_raw[];
-  tap_t *h = reinterpret_cast<tap_t *>(fb_smem_raw);
-  T *X = reinterpret_cast<T *>(h + p.N);
+  tap_t *h = reinterpret_cast<tap_t *>(fb_smem_raw) + p.hoff;
+  T *X = reinterpret_cast<T *>(reinterpret_cast<tap_t *>(fb_smem_raw) + p.np);
   const uint32_t row = blockIdx.y;
   const T *in_row = reinterpret_cast<const T *>(p.in) + (uint64_t)row * p.in_stride;
   const T *carry_row = reinterpret_cast<const T *>(p.carry_in) + (uint64_t)row * p.C;

@@ -117,3 +117,20 @@ def test_argument_checks():
     assert b.out_count(1) == 1
     got = b.run(np.ones((2, 1), dtype=f32))
     assert got.shape == (2, 1) and got[0, 0] == 1.0
+
+
+@pytest.mark.parametrize("factor", [2, 4])
+def test_float_decimator_block_path_edges(factor):
+    """Float decimators with M = 2, 4 take the path with 16-byte window loads: tap counts around the
+    block size (4 M), with and without taps above the highest full block, short and ragged streams."""
+    rng = np.random.default_rng(900 + factor)
+    for n_taps in (1, 3, 4, 5, 4 * factor - 1, 4 * factor, 4 * factor + 1, 15, 16, 17, 37, 80, 81, 83, 127):
+        taps = rng.normal(0, 0.3, n_taps).astype(f32)
+        rows, n = 5, int(rng.integers(1, 6000))
+        x = (rng.normal(0, 3000, (rows, n))).astype(f32)
+        b = _bank(1, rows, taps, factor)
+        cut = int(rng.integers(0, n))
+        got = np.concatenate([b.run(x[:, :cut]), b.run(x[:, cut:])], axis=1) if cut else b.run(x)
+        for r in range(rows):
+            exp = O.Multirate(1, taps, factor).run(x[r])
+            assert got[r].tobytes() == exp.tobytes(), (factor, n_taps, r)
