@@ -236,10 +236,10 @@ int sdr_filter_bank_run(sdr_filter_bank *b, const void *in, uint64_t in_stride, 
     // extra words are what the 16-byte window loads of the float M = 2, 4 path may read past the data
     p.pitch = ((p.span + M - 1) / M + 8 + 31) / 32 * 32 + ((32 % M) == 0 && M > 1 ? 32 / M : (M > 1 ? 1 : 0));
   }
-  // float decimators with M = 2, 4: taps above the highest full block of four a-values (see the kernel)
+  // decimators with M = 2, 4: taps above the highest full block of four a-values (see the kernel)
   p.kp = 0;
   p.hoff = 0;
-  if (!b->interp && !b->i16 && (M == 2 || M == 4)) {
+  if (!b->interp && (M == 2 || M == 4)) {
     const uint32_t a_top = (b->N - 1) / M, ph_top = (b->N - 1) % M;
     const int a_full = (ph_top == M - 1) ? (int)a_top : (int)a_top - 1;  // largest a with every phase present
     const int n_blocks = a_full >= 3 ? (a_full + 1) / 4 : 0;

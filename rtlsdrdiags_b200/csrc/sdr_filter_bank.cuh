@@ -139,7 +139,8 @@ __device__ __forceinline__ void fb_compute(const FilterBankParams &p, const type
     }
     return;
   }
-  if constexpr (!INTERP && (MT == 2 || MT == 4) && sizeof(T) == 4 && sizeof(tap_t) == 4) {
+  // (filters shorter than one block of 4 M taps stay on the generic path below)
+  if constexpr (!INTERP && (MT == 2 || MT == 4) && sizeof(T) == 4 && sizeof(tap_t) == 4) if (p.N > p.kp) {
     // Float decimator, M = 2 or 4: a thread owns FOUR CONSECUTIVE outputs t0 .. t0+3. Tap k meets the
     // sample at X[ph][t + a] with a = (N-1-k) / M, ph = (N-1-k) % M; four consecutive values of a
     // for four consecutive outputs touch seven consecutive words of a phase row, i.e. two aligned
@@ -188,6 +189,51 @@ __device__ __forceinline__ void fb_compute(const FilterBankParams &p, const type
 #pragma unroll
       for (int j = 0; j < 4; ++j)
         if (t0 + j < p.tile_out && o0 + t0 + j < p.n_out) out_row[o0 + t0 + j] = acc[j];
+    }
+    return;
+  }
+  if constexpr (!INTERP && (MT == 2 || MT == 4) && sizeof(T) == 2 && !CLAMP) if (p.N > p.kp) {
+    // Q15 decimator, M = 2 or 4, in a tile whose samples cannot reach the clamp: the same blocking as
+    // the float path above (four consecutive outputs per thread, blocks of four a-values), the window of
+    // a phase row as two 8-byte loads of four int16 each. Without the clamp the sum is an exact integer,
+    // so the order of the multiply-adds is free.
+    constexpr int M_ = MT;
+    const int n_blocks = (int)((p.N - p.kp) / (4 * M_));
+    for (uint32_t t0 = 4 * threadIdx.x; t0 < p.tile_out; t0 += 4 * FB_THREADS) {
+      if (o0 + t0 >= p.n_out) break;
+      int acc[4] = {1 << 14, 1 << 14, 1 << 14, 1 << 14};
+      for (uint32_t k = 0; k < p.kp; ++k) {
+        const uint32_t r = p.N - 1 - k;
+        const int hk = h[k];
+        const T *xr = X + (r % M_) * p.pitch + t0 + r / M_;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[j] += hk * (int)xr[j];
+      }
+      const int *hb = h + p.kp;
+      for (int m = n_blocks - 1; m >= 0; --m, hb += 4 * M_) {
+        int tp[4 * M_];
+#pragma unroll
+        for (int v = 0; v < M_; ++v) {
+          const uint4 t4 = *reinterpret_cast<const uint4 *>(hb + 4 * v);
+          memcpy(&tp[4 * v], &t4, 16);
+        }
+#pragma unroll
+        for (int ph = M_ - 1; ph >= 0; --ph) {
+          const uint2 lo = *reinterpret_cast<const uint2 *>(X + ph * p.pitch + t0 + 4 * m);
+          const uint2 hi = *reinterpret_cast<const uint2 *>(X + ph * p.pitch + t0 + 4 * m + 4);
+          const int W[8] = {(int)(int16_t)lo.x, (int)lo.x >> 16, (int)(int16_t)lo.y, (int)lo.y >> 16,
+                            (int)(int16_t)hi.x, (int)hi.x >> 16, (int)(int16_t)hi.y, (int)hi.y >> 16};
+#pragma unroll
+          for (int g = 3; g >= 0; --g) {
+            const int hk = tp[(3 - g) * M_ + (M_ - 1 - ph)];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j] += hk * W[j + g];
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (t0 + j < p.tile_out && o0 + t0 + j < p.n_out) out_row[o0 + t0 + j] = (int16_t)(acc[j] >> 15);
     }
     return;
   }

@@ -134,3 +134,21 @@ def test_float_decimator_block_path_edges(factor):
         for r in range(rows):
             exp = O.Multirate(1, taps, factor).run(x[r])
             assert got[r].tobytes() == exp.tobytes(), (factor, n_taps, r)
+
+
+@pytest.mark.parametrize("factor", [2, 4])
+def test_q15_decimator_block_path_edges(factor):
+    """Q15 decimators with M = 2, 4 take the blocked path in tiles whose samples cannot reach the clamp
+    (moderate amplitude here), the per-tap clamp path otherwise (one full-scale row per case)."""
+    rng = np.random.default_rng(950 + factor)
+    for n_taps in (1, 3, 4, 5, 4 * factor - 1, 4 * factor, 4 * factor + 1, 16, 17, 37, 80, 83):
+        taps = (rng.normal(0, 0.3, n_taps) / max(1.0, np.sqrt(n_taps) / 3)).astype(f32)
+        rows, n = 5, int(rng.integers(1, 7000))
+        x = rng.integers(-3000, 3000, (rows, n)).astype(np.int16)
+        x[4] = rng.integers(-32768, 32768, n).astype(np.int16)   # this row's tiles keep the clamp
+        b = _bank(3, rows, taps, factor)
+        cut = int(rng.integers(0, n))
+        got = np.concatenate([b.run(x[:, :cut]), b.run(x[:, cut:])], axis=1) if cut else b.run(x)
+        for r in range(rows):
+            exp = O.Multirate(3, taps, factor).run(x[r])
+            assert got[r].tobytes() == exp.tobytes(), (factor, n_taps, r)
