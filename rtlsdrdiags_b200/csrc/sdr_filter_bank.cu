@@ -104,6 +104,14 @@ int sdr_filter_bank_create(int device, int kind, uint32_t n_rows, const float *t
     q32[i] = b->q15[i];
     b->sum_abs_q15 += (uint32_t)abs((int)b->q15[i]);
   }
+  if (interp) {  // an output only meets the taps of its own phase: the largest phase sum bounds it
+    b->sum_abs_q15 = 0;
+    for (uint32_t ph = 0; ph < factor; ++ph) {
+      uint32_t s = 0;
+      for (uint32_t k = ph; k < n_taps; k += factor) s += (uint32_t)abs((int)b->q15[k]);
+      b->sum_abs_q15 = s > b->sum_abs_q15 ? s : b->sum_abs_q15;
+    }
+  }
   const void *src = b->i16 ? (const void *)q32.data() : (const void *)taps;
   const size_t cbytes = (size_t)(b->C ? b->C : 1) * n_rows * b->esize;
   if ((ce = cudaMalloc(&b->d_taps, 4 * (size_t)n_taps)) != cudaSuccess ||
