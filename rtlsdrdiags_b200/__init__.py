@@ -87,6 +87,9 @@ def load_library(build_if_missing=True):
     L.sdr_last_error.argtypes = [vp]
     L.sdr_last_error.restype = C.c_char_p
     L.sdr_version.restype = C.c_char_p
+    # diagnostics, not part of include/sdr_b200.h
+    L.sdr_debug_set_dc_shape.argtypes = [vp, u32, u32]
+    L.sdr_debug_dc_redo_count.argtypes = [vp, C.POINTER(u32)]
     L.sdr_filter_bank_create.argtypes = [i32, i32, u32, vp, u32, u32, C.POINTER(vp)]
     L.sdr_filter_bank_destroy.argtypes = [vp]
     L.sdr_filter_bank_set_stream.argtypes = [vp, vp]
@@ -237,6 +240,18 @@ class Engine:
     @property
     def launch_count(self):
         return int(self.L.sdr_launch_count(self.h))
+
+    # ---- diagnostics (tests, tuning) ----
+    def debug_set_dc_shape(self, seg_count=0, warm_rows=32):
+        """Segmentation of the AM/SSB recurrence kernel: seg_count 0 = per call; warm_rows = rows of
+        32 PCM samples a segment warms up on."""
+        self._ck(self.L.sdr_debug_set_dc_shape(self.h, int(seg_count), int(warm_rows)))
+
+    def debug_dc_redo_count(self):
+        """Segments the recurrence kernel had to redo serially since the engine was created."""
+        n = C.c_uint32()
+        self._ck(self.L.sdr_debug_dc_redo_count(self.h, C.byref(n)))
+        return n.value
 
     def demodulate(self, iq, fmt=IQ_U8_OFFSET):
         """Convenience: one accept + get_pcm on host arrays. Long streams are cut into

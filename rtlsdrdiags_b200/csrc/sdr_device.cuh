@@ -50,6 +50,10 @@ struct LaunchParams {
   uint32_t call_id;          // AM/SSB/FM: 31-bit id of this call, never 0 (versions the carry buffers)
   const uint32_t *tab;       // FM: tensor-core tuner tables (fm_mma_table in sdr_engine.cu)
   unsigned long long *trace; // SDR_TRACE=1 only: [0] = earliest CTA start, [1] = latest CTA end of this launch (globaltimer ns)
+  // dc_block_kernel: a call's rows (32 PCM samples each) are cut into seg_count segments of
+  // seg_rows rows per channel; a segment warms up on the warm_rows rows before it
+  uint32_t seg_count, seg_rows, warm_rows;
+  uint32_t *counters;        // [0] = segments dc_block_kernel had to redo serially (diagnostics)
 };
 
 #if SDR_DEVICE_BUILD

@@ -42,19 +42,20 @@ struct sdr_engine {
   // AM/SSB: the recurrence kernels run on rec_stream, one call behind the FIR kernels on
   // `stream`; the numerators travel through scratch[kind][call index % RING]
   cudaStream_t rec_stream = nullptr;
-  // RING: how many calls' numerators / gates exist at once. Two would do if call k's recurrence
-  // kernel always started beside call k+1's FIR kernel; when the FIR kernel's CTAs take every SM
-  // first, the recurrence runs one or two calls later; with two buffers call k+2 had to wait for it
-  // (profiles/r01v7_pacing.txt)
-  static constexpr int RING_MAX = 8;
-  int ring = 6;  // buffers in use (SDR_RING): slack for the recurrence kernel to lag the FIR kernel by a few calls
+  // RING: how many calls' numerators / gates exist at once. Call k's recurrence kernel runs beside
+  // call k+1's FIR kernel and is a small fraction of its length (segment-parallel, see
+  // dc_block_kernel), so call k+2 never waits for it; the third buffer is slack.
+  static constexpr int RING_MAX = 3;
+  static constexpr int ring = RING_MAX;
   cudaEvent_t ev_fir[RING_MAX] = {}, ev_rec[RING_MAX] = {};
-  // pacing: a caller that queues calls faster than the GPU retires them is held once PACE calls
-  // are in flight (see sdr_accept_iq)
-  static constexpr int PACE = 256;
+  // bounded run-ahead: a caller that queues calls faster than the GPU retires them is held once
+  // RUN_AHEAD calls are in flight (see sdr_accept_iq)
+  static constexpr int RUN_AHEAD = 32, PACE = 2 * RUN_AHEAD;
   cudaEvent_t ev_pace[PACE] = {};
-  int pace_depth = 32;
   float *d_scratch[5][RING_MAX] = {};
+  // dc_block_kernel's segmentation (0 = chosen per call) and its redo counter
+  uint32_t dc_seg_count = 0, dc_warm_rows = 32;
+  uint32_t *d_counters = nullptr;
   uint64_t seq = 0;        // sdr_accept_iq calls so far
   bool rec_pending = false;  // work on rec_stream that `stream` has not waited for yet
   // Mixed banks: the WBFM kernel (one long-lived CTA per SM that leaves issue slots, registers
@@ -91,6 +92,9 @@ struct sdr_engine {
   uint8_t *d_tracking = nullptr, *d_allowed[RING_MAX] = {};
   int32_t *d_db_table = nullptr;
   bool last_gated = false;  // the last accept ran the squelch kernel with the gate in force
+  // blocks were accepted without the squelch kernel after d_tracking came to exist: every one of
+  // them passed, so the reference's trackers all stand in `Tracking` (SignalTracker.cc:104-145)
+  bool tracking_stale = false;
 
   // IQ dump (IqDataProcessor::enableIqDump): channels whose converted block is kept
   std::vector<uint8_t> dump_on;
@@ -232,6 +236,21 @@ int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride,
   return SDR_OK;
 }
 
+// Segmentation of one call's recurrence (dc_block_kernel): rows of 32 PCM samples, segments of
+// at least 16 rows, at most 32 segments per channel (the lanes of one warp), none for short calls
+// (a warm-up of 32 rows would cost more than it saves).
+void dc_segments(const sdr_engine *e, uint32_t n_rows, uint32_t *seg_count, uint32_t *seg_rows) {
+  uint32_t S = 1;
+  if (e->dc_seg_count) {
+    S = e->dc_seg_count;
+  } else if (n_rows >= 64) {
+    while (S < 16 && n_rows / (2 * S) >= 16) S *= 2;
+  }
+  while (S > 1 && (n_rows + S - 1) / S * (S - 1) >= n_rows) S /= 2;  // no empty segments in the middle
+  *seg_count = S;
+  *seg_rows = (n_rows + S - 1) / S;
+}
+
 int launch_dc_block(sdr_engine *e, int kind, uint32_t n_samples) {
   const uint32_t n_list = (uint32_t)e->list[kind].size();
   if (n_list == 0) return SDR_OK;
@@ -250,21 +269,11 @@ int launch_dc_block(sdr_engine *e, int kind, uint32_t n_samples) {
   p.scratch = e->d_scratch[kind][par];
   p.allowed = e->last_gated ? e->d_allowed[par] : nullptr;
   p.trace = e->d_trace ? e->d_trace + 4 * (e->seq % sdr_engine::TRACE_CALLS) + 2 : nullptr;
-  // Small banks: few CTAs, so each gets seven helper warps and the chain warp is never kept
-  // waiting; large banks: three helpers, so the many CTAs leave the FIR kernel its registers.
-  static const int helpers_env = getenv("SDR_DC_HELPERS") ? atoi(getenv("SDR_DC_HELPERS")) : 0;
-  const int helpers = helpers_env ? helpers_env : (n_list <= 32u * (uint32_t)e->n_sm ? 7 : 3);
-  if (helpers > 3) {
-    SDR_CK(e, cudaFuncSetAttribute(dc_block_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM_BYTES));
-    // extra (unused) shared memory keeps the FIR kernel's CTAs off the few SMs that host a recurrence CTA
-    static const int pad_env = getenv("SDR_DC_PAD_KB") ? atoi(getenv("SDR_DC_PAD_KB")) : 0;
-    const int smem7 = DC_SMEM_BYTES + 1024 * pad_env;
-    SDR_CK(e, cudaFuncSetAttribute(dc_block_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem7));
-    dc_block_kernel<7><<<(n_list + 31) / 32, 32 * 8, smem7, e->rec_stream>>>(p);
-  } else {
-    SDR_CK(e, cudaFuncSetAttribute(dc_block_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_SMEM_BYTES));
-    dc_block_kernel<3><<<(n_list + 31) / 32, 32 * 4, DC_SMEM_BYTES, e->rec_stream>>>(p);
-  }
+  dc_segments(e, (n_samples + TILE - 1) / TILE, &p.seg_count, &p.seg_rows);
+  p.warm_rows = e->dc_warm_rows;
+  p.counters = e->d_counters;
+  const uint64_t lanes = (uint64_t)n_list * p.seg_count;
+  dc_block_kernel<<<(uint32_t)((lanes + 127) / 128), 128, 0, e->rec_stream>>>(p);
   SDR_CK(e, cudaGetLastError());
   e->launches++;
   return SDR_OK;
@@ -519,7 +528,7 @@ int run_iq_dump(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint64_t b
 int run_squelch(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint64_t bytes, int fmt) {
   e->last_gated = false;
   if (e->squelch_dirty) {
-    bool armed = e->squelch_armed;
+    bool armed = false;
     for (uint32_t ch = 0; ch < e->n && !armed; ++ch)
       armed = (int64_t)e->threshold[ch] > -42 - (int64_t)e->rx_gain_db[ch];
     if ((armed || e->signal_reports) && !e->d_tracking) {
@@ -550,7 +559,14 @@ int run_squelch(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint64_t b
     e->squelch_armed = armed;
     e->squelch_dirty = false;
   }
-  if (!e->squelch_armed && !e->signal_reports) return SDR_OK;
+  if (!e->squelch_armed && !e->signal_reports) {
+    if (e->d_tracking) e->tracking_stale = true;
+    return SDR_OK;
+  }
+  if (e->tracking_stale) {
+    SDR_CK(e, cudaMemsetAsync(e->d_tracking, 1, e->n, e->stream));
+    e->tracking_stale = false;
+  }
   SquelchParams q;
   q.iq = iq;
   q.ch_stride = ch_stride;
@@ -665,8 +681,8 @@ int sdr_engine_create(uint32_t n_channels, int device, uint64_t max_bytes_per_ch
     SDR_CK_CREATE(cudaMalloc(&e->d_trace, init.size() * 8));
     SDR_CK_CREATE(cudaMemcpy(e->d_trace, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
   }
-  if (getenv("SDR_RING")) e->ring = std::max(2, std::min((int)sdr_engine::RING_MAX, atoi(getenv("SDR_RING"))));
-  if (getenv("SDR_PACE")) e->pace_depth = std::max(0, std::min((int)sdr_engine::PACE, atoi(getenv("SDR_PACE"))));  // 0 = off
+  SDR_CK_CREATE(cudaMalloc(&e->d_counters, 16));
+  SDR_CK_CREATE(cudaMemset(e->d_counters, 0, 16));
   e->stream = e->own_stream;
 
   e->dump_on.assign(n_channels, 0);           // IqDataProcessor.cc:62
@@ -772,6 +788,7 @@ int sdr_engine_destroy(sdr_engine *e) {
   cudaFree(e->d_lut_wbfm);
   cudaFree(e->d_lut_wbfm_half);
   cudaFree(e->d_trace);
+  cudaFree(e->d_counters);
   cudaFree(e->d_iq);
   cudaFree(e->d_pcm);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -871,6 +888,27 @@ int sdr_debug_read_trace(sdr_engine *e, unsigned long long *out, uint64_t n_call
   return SDR_OK;
 }
 
+// Diagnostics (not part of include/sdr_b200.h): dc_block_kernel's segmentation -- seg_count 0 =
+// chosen per call, else a power of two <= 32; warm_rows = rows of 32 PCM samples a segment warms
+// up on -- and how many segments it had to redo serially so far. Tests shrink the warm-up to
+// force the redo path.
+int sdr_debug_set_dc_shape(sdr_engine *e, uint32_t seg_count, uint32_t warm_rows) {
+  if (!e || seg_count > 32 || (seg_count & (seg_count - 1))) return SDR_E_ARG;
+  e->dc_seg_count = seg_count;
+  e->dc_warm_rows = warm_rows;
+  return SDR_OK;
+}
+
+int sdr_debug_dc_redo_count(sdr_engine *e, uint32_t *count) {
+  if (!e || !count) return SDR_E_ARG;
+  SDR_CK(e, cudaSetDevice(e->device));
+  int rc = join_streams(e);
+  if (rc) return rc;
+  SDR_CK(e, cudaMemcpyAsync(count, e->d_counters, 4, cudaMemcpyDeviceToHost, e->stream));
+  SDR_CK(e, cudaStreamSynchronize(e->stream));
+  return SDR_OK;
+}
+
 int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_stride, uint32_t flags) {
   if (!e || !iq) return SDR_E_ARG;
   if (bytes == 0 || bytes % 64) return fail(e, SDR_E_ARG, "bytes_per_channel must be a positive multiple of 64");
@@ -894,18 +932,16 @@ int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_str
     dev_stride = bytes;
   }
   // Bounded run-ahead. With hundreds of calls queued the driver's launch queues fill up and the
-  // GPU is fed in bursts: a 15,000-call AM loop ran at 0.170 ms per call against 0.125 ms for the
-  // same loop 1,500 calls long, at full clocks (tools/probe_power.py, profiles/r01v7_pacing.txt).
-  // Holding the caller once pace_depth calls are in flight keeps the queues shallow.
+  // GPU is fed in bursts (profiles/r01v7_pacing.txt); holding the caller once RUN_AHEAD calls are
+  // in flight keeps the queues shallow.
   const int slot = (int)(e->seq % (uint64_t)sdr_engine::PACE);
-  if (e->pace_depth > 0 && e->seq >= (uint64_t)e->pace_depth)
-    SDR_CK(e, cudaEventSynchronize(e->ev_pace[(int)((e->seq - (uint64_t)e->pace_depth) % (uint64_t)sdr_engine::PACE)]));
+  if (e->seq >= (uint64_t)sdr_engine::RUN_AHEAD)
+    SDR_CK(e, cudaEventSynchronize(e->ev_pace[(int)((e->seq - (uint64_t)sdr_engine::RUN_AHEAD) % (uint64_t)sdr_engine::PACE)]));
   const int fmt = (flags & SDR_IQ_S8_ROTATED) ? FMT_S8_ROTATED : FMT_U8_OFFSET_ROTATE;
   const uint32_t n_samples = (uint32_t)(bytes / 2);
   const bool have_rec = !e->list[SDR_KIND_AM].empty() || !e->list[SDR_KIND_SSB].empty();
   const int par = (int)(e->seq % (uint64_t)e->ring);
-  // scratch[par] and allowed[par] were last read by the recurrence kernels of the call
-  // before the previous one
+  // scratch[par] and allowed[par] were last read by the recurrence kernels RING calls ago
   if (have_rec || e->squelch_armed || e->signal_reports || e->squelch_dirty)
     SDR_CK(e, cudaStreamWaitEvent(e->stream, e->ev_rec[par], 0));
   if ((rc = run_iq_dump(e, dev_iq, dev_stride, bytes, fmt))) return rc;
