@@ -7,9 +7,16 @@
 
 A "step" is one pass of the hot path over one batch of synthetic IQ: every channel
 of the bank gets T reference blocks (T x 32768 bytes = T x 64 ms of signal) and comes
-out as T x 512 PCM samples. Channels shard across ranks with no data-path collective
-(weak scaling: the per-GPU bank is fixed); torch.distributed is used for the barrier
-and the max-over-ranks of the device-timed region only.
+out as T x 512 PCM samples. Channels shard across ranks with no data-path collective;
+torch.distributed is used for the barrier, the max-over-ranks of the device-timed region
+and the gather of the per-rank parity flags only.
+
+Without --workload the run is BASELINE.json's configuration for N GPUs:
+    N = 1     AM envelope demod, 1024 channels                      (configs[1], the headline)
+    N = 2, 4  LSB/USB SSB demod, 16384 channels across the GPUs     (configs[3]; strong scaling 2 -> 4)
+    N = 8     mixed AM/FM/WBFM/LSB/USB bank, 65536 channels         (configs[4])
+and, for N > 1, a second short run of the headline AM bank per GPU (`am_weak`), so the 1 -> N
+weak-scaling curve of the headline exists next to the named configurations.
 
 Prints ONE JSON line (rank 0). `value` is whole-job complex-IQ Msamples/s with the
 input already resident in HBM; `e2e` is the same metric through the C ABI with host
@@ -35,9 +42,12 @@ METRIC = "aggregate_iq_msamples_per_s"
 # (dc_block_kernel) runs one step behind on a second stream and is inside the timed region.
 KERNELS = {"am": "amssb_fir_kernel<false> (+ dc_block_kernel overlapped on the second stream)",
            "ssb": "amssb_fir_kernel<true> (+ dc_block_kernel overlapped on the second stream)",
-           "fm": "fm_tile_kernel", "wbfm": "wbfm_tile_kernel",
+           "fm": "fm_tile_kernel", "wbfm": "wbfm_tile2_kernel",
            "mixed": "amssb_fir_kernel<false> + amssb_fir_kernel<true> + 2 x dc_block_kernel + fm_tile_kernel + "
-                    "wbfm_tile_kernel"}
+                    "wbfm_tile2_kernel (the step is timed as a whole)"}
+# BASELINE.json configs per GPU count: (workload, total channels, scaling label)
+BASELINE_CONFIGS = {1: ("am", 1024, "weak"), 2: ("ssb", 16384, "strong"), 4: ("ssb", 16384, "strong"),
+                    8: ("mixed", 65536, "weak")}
 
 
 def parse_args():
@@ -45,7 +55,8 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=0, help="timed steps (0 = enough for ~2 s of device time)")
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="am", choices=["am", "fm", "wbfm", "ssb", "mixed"])
+    ap.add_argument("--workload", default=None, choices=["am", "fm", "wbfm", "ssb", "mixed"],
+                    help="default: BASELINE.json's configuration for --gpus N (see the module docstring)")
     ap.add_argument("--signal", default="tone", choices=["tone", "noise"])
     ap.add_argument("--blocks", type=int, default=0, help="reference blocks per channel per step (0 = auto)")
     ap.add_argument("--channels", type=int, default=0, help="channels per GPU (0 = the workload's)")
@@ -124,6 +135,12 @@ class ClockSampler:
         return out
 
 
+def _cpu_chain(O, use_ref, modes, iq, cores, want_pcm):
+    if use_ref:
+        return O.ref_bank(modes, iq, BLOCK_BYTES, cores, want_pcm=want_pcm)
+    return O.oracle_bank(modes, iq, BLOCK_BYTES, cores, want_pcm=want_pcm)
+
+
 def run_cpu_reference(workload, modes_np, n_blocks, seconds_target=6.0, signal="tone", check_gpu=False):
     """The reference's CPU chain on this box's host cores over a bounded sample of the
     workload. Returns (Msamples/s, descriptor dict). Uses oracle/_ref (the unmodified
@@ -143,10 +160,7 @@ def run_cpu_reference(workload, modes_np, n_blocks, seconds_target=6.0, signal="
     kind = "reference" if use_ref else "port"
     done, elapsed, reps = 0, 0.0, 0
     while elapsed < seconds_target and reps < 1000:
-        if use_ref:
-            _, secs = O.ref_bank(modes, iq, BLOCK_BYTES, cores, want_pcm=False)
-        else:
-            _, secs = O.oracle_bank(modes, iq, BLOCK_BYTES, cores, want_pcm=False)
+        _, secs = _cpu_chain(O, use_ref, modes, iq, cores, False)
         elapsed += secs
         done += n_ch * nbytes // 2
         reps += 1
@@ -157,7 +171,7 @@ def run_cpu_reference(workload, modes_np, n_blocks, seconds_target=6.0, signal="
     if check_gpu:
         # the GPU's PCM for this very sample against the PCM the CPU chain just produced
         import rtlsdrdiags_b200 as R
-        ref_pcm, _ = (O.ref_bank if use_ref else O.oracle_bank)(modes, iq, BLOCK_BYTES, cores, want_pcm=True)
+        ref_pcm, _ = _cpu_chain(O, use_ref, modes, iq, cores, True)
         eng = R.Engine(n_ch, 0, BLOCK_BYTES)
         eng.set_modes(modes)
         got, _ = eng.demodulate(iq)  # one reference-sized block per call, state carried
@@ -166,13 +180,42 @@ def run_cpu_reference(workload, modes_np, n_blocks, seconds_target=6.0, signal="
     return msps, desc
 
 
+def shard_parity(R, synth, workload, channels, first_channel, n_blocks, device_index, signal, seed):
+    """This rank's shard against the CPU chain (oracle/_ref, the compiled reference, when it was
+    built): a sample of the shard's channels, two passes of the bench's own call shape (n_blocks
+    reference blocks per call, so the carried state and the segmented recurrence are exercised as
+    timed), PCM compared bit for bit. The CPU chain sees the same bytes in 32768-byte blocks."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_binding as O
+    use_ref = O.ref("radiodiags") is not None
+    n_s = min(channels, 20)
+    pick = np.unique(np.linspace(0, channels - 1, n_s).astype(np.int64))  # spread over the shard
+    modes = synth.modes_for(workload, channels, first_channel=first_channel)[pick]
+    blocks = min(n_blocks, 4)
+    nbytes = blocks * BLOCK_BYTES
+    iq = synth.make_bank(signal, modes, 2 * nbytes, seed, "cpu").numpy()
+    eng = R.Engine(int(pick.size), device_index, nbytes)
+    eng.set_modes(modes.numpy())
+    got, _ = eng.demodulate(iq)
+    eng.close()
+    cores = min(os.cpu_count() or 1, int(pick.size))
+    exp, _ = _cpu_chain(O, use_ref, modes.numpy(), iq, cores, True)
+    return bool(np.array_equal(got, exp)), {
+        "checker": "oracle/_ref (the reference compiled in place)" if use_ref else "oracle port",
+        "sample": "%d channels spread over the shard x 2 calls of %d blocks (%s)" % (pick.size, blocks, signal)}
+
+
 def bench_one(torch, R, synth, workload, channels, n_blocks, steps, warmup, signal, device, rank, world,
-              dist, want_e2e=True):
+              dist, want_e2e=True, first_channel=None):
     """Times `steps` passes of one workload on this rank. Returns a dict of local results."""
-    modes = synth.modes_for(workload, channels, first_channel=rank * channels)
+    first = rank * channels if first_channel is None else first_channel
+    modes = synth.modes_for(workload, channels, first_channel=first)
     nbytes = n_blocks * BLOCK_BYTES
     eng = R.Engine(channels, device.index, nbytes)
     eng.set_modes(modes.numpy())
+    if os.environ.get("SDR_BENCH_TILE_LOADER") == "cpasync":  # A/B runs: AM/SSB tiles by cp.async instead of TMA
+        eng.debug_set_tile_loader(False)
     # a dedicated (non-default) stream: the kernels are launched on it and the CUDA
     # events that time them are recorded on it
     stream = torch.cuda.Stream(device)
@@ -210,6 +253,7 @@ def bench_one(torch, R, synth, workload, channels, n_blocks, steps, warmup, sign
     clocks = sampler.stop() if sampler else None
     ms = e0.elapsed_time(e1)
     launches = eng.launch_count - l0
+    redo = eng.debug_dc_redo_count()
     if clocks is not None:
         clocks["sampled"] = "timed region"
         if clocks["samples"] < 5:  # region too short for nvidia-smi: soak the same call for 1.5 s
@@ -222,20 +266,26 @@ def bench_one(torch, R, synth, workload, channels, n_blocks, steps, warmup, sign
             clocks["sampled"] = "1.5 s soak of the same launch right after the timed region (region too short)"
     res = {"ms_total": ms, "launches": launches, "clocks": clocks, "steps": steps,
            "samples_per_step": channels * nbytes // 2, "h2d": channels * nbytes,
-           "d2h": channels * (nbytes // 64) * 2}
+           "d2h": channels * (nbytes // 64) * 2, "dc_redo": redo}
+    eng.set_stream(0)
+    eng.close()
 
     # ---- end to end through the C ABI: pinned host IQ in, host PCM out, every step ----
     if want_e2e:
         h_iq = torch.empty((channels, nbytes), dtype=torch.uint8, pin_memory=True)
         h_iq.copy_(iq)
+        del iq
         h_pcm = torch.empty((channels, nbytes // 64), dtype=torch.int16, pin_memory=True)
         torch.cuda.synchronize(device)
+        n_warm, n_e2e = 3, 10
+        # Both paths start from a fresh engine and see the same 13 ticks, so their last PCM must agree.
         # (1) one synchronous call pair per step: sdr_accept_iq(host) + sdr_get_pcm
-        for _ in range(min(warmup, 3)):
+        eng = R.Engine(channels, device.index, nbytes)
+        eng.set_modes(modes.numpy())
+        for _ in range(n_warm):
             eng.accept_iq_ptr(h_iq.data_ptr(), nbytes, nbytes, R.IQ_HOST)
             eng.get_pcm_ptr(h_pcm.data_ptr())
         barrier()
-        n_e2e = 10
         t0 = time.perf_counter()
         for _ in range(n_e2e):
             eng.accept_iq_ptr(h_iq.data_ptr(), nbytes, nbytes, R.IQ_HOST)
@@ -244,16 +294,21 @@ def bench_one(torch, R, synth, workload, channels, n_blocks, steps, warmup, sign
         res["e2e_sync_ms_total"] = (time.perf_counter() - t0) * 1e3
         sync_sum = int(h_pcm.to(torch.int64).sum().item())
         del h_pcm
+        eng.close()
         # (2) the ingest ring (the bank's DataConsumer): every step's tick is taken from a pinned
         # slot, copied to the GPU, demodulated and its PCM copied back to pinned memory; copies
-        # of neighbouring ticks overlap. A step is complete when its tick has been retired.
+        # of neighbouring ticks overlap. A step is complete when its tick has been retired. The
+        # producer writes in place: sdr_ingest_acquire hands it the pinned slot, so no host copy
+        # is part of a step (sdr_ingest_accept, which copies like DataConsumer.cc:246-248, is
+        # timed separately below).
+        eng = R.Engine(channels, device.index, nbytes)
+        eng.set_modes(modes.numpy())
         ring = R.Ingest(eng, 3, nbytes)
-        for _ in range(3):                     # fill the three pinned slots with the workload
+        for _ in range(n_warm):                # fill the three pinned slots with the workload
             ring.acquire()[:] = h_iq.numpy()
             ring.commit(0)
-        for _ in range(3):
+        for _ in range(n_warm):
             ring.retire(copy=False)
-        del h_iq
         barrier()
         t0 = time.perf_counter()
         acc = 0
@@ -271,10 +326,24 @@ def bench_one(torch, R, synth, workload, channels, n_blocks, steps, warmup, sign
         ring_sum = int(torch.from_numpy(pcm.copy()).to(torch.int64).sum().item())
         res["pcm_checksum"] = ring_sum
         res["e2e_paths_agree"] = ring_sum == sync_sum
+        # (3) the copying entry: sdr_ingest_accept memcpy's the caller's block into the slot first
+        n_copy = 3
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(n_copy):
+            ring.accept(k, h_iq.numpy())
+            if k >= 2:
+                ring.retire(copy=False)
+        for _ in range(min(2, n_copy)):
+            ring.retire(copy=False)
+        torch.cuda.synchronize(device)
+        res["e2e_copy_ms_total"] = (time.perf_counter() - t0) * 1e3
+        res["e2e_copy_steps"] = n_copy
         ring.close()
-    eng.set_stream(0)
-    eng.close()
-    del iq
+        eng.close()
+        del h_iq
+    else:
+        del iq
     torch.cuda.empty_cache()
     return res
 
@@ -287,6 +356,37 @@ def reduce_max(torch, dist, world, device, x):
     return float(t.item())
 
 
+def gather_flags(torch, dist, world, device, flag):
+    if world == 1:
+        return [bool(flag)]
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device)
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [bool(int(x.item())) for x in out]
+
+
+def traffic_for(workload):
+    """DRAM bytes per launch of the workload's dominant kernel from this round's ncu --set full
+    capture (profiles/ncu_traffic.json), with the label of the build it was captured on."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            d = json.load(f)
+        return d.get(workload), d.get("_captured")
+    except Exception:
+        return None, None
+
+
+def config_of(workload, wl_desc, signal, channels, world, n_blocks):
+    """The `config` object of the JSON line: identical for the B200 arm and the reference arm."""
+    per_gpu = channels * n_blocks * BLOCK_BYTES
+    return {"workload": workload, "description": wl_desc, "signal": signal,
+            "channels_per_gpu": channels, "channels_total": channels * world,
+            "blocks_per_channel_per_step": n_blocks,
+            "block_bytes": BLOCK_BYTES, "iq_bytes_per_gpu_per_step": per_gpu,
+            "l2": "input per step (%d MiB) exceeds the 126 MB L2; no flush needed" % (per_gpu >> 20),
+            "sharding": "contiguous channel ranges per rank, no data-path collective"}
+
+
 def main():
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -295,21 +395,33 @@ def main():
 
     import numpy as np
     from rtlsdrdiags_b200 import synth
-    wl_channels, _, wl_desc = synth.WORKLOADS[args.workload]
-    channels = args.channels or wl_channels
-    n_blocks = args.blocks or default_blocks(args.workload, channels)
+    n_gpus = world if args.impl != "reference" else max(args.gpus, 1)
+    scaling = "weak"
+    total_channels = None
+    if args.workload is None:
+        workload, total_channels, scaling = BASELINE_CONFIGS.get(n_gpus, ("am", 1024 * n_gpus, "weak"))
+        channels = args.channels or total_channels // n_gpus
+        if n_gpus == 1:
+            total_channels = None
+    else:
+        workload = args.workload
+        channels = args.channels or synth.WORKLOADS[workload][0]
+    wl_desc = synth.WORKLOADS[workload][2] if total_channels is None else \
+        "%s (%d channels in total, %d per GPU on %d GPUs)" % (synth.WORKLOADS[workload][2], total_channels,
+                                                               channels, n_gpus)
+    n_blocks = args.blocks or default_blocks(workload, channels)
 
     if args.impl == "reference":
         # the reference's own CPU implementation of the path, all host threads; rank 0 only
         if rank != 0:
             return 0
-        modes = synth.modes_for(args.workload, channels).numpy()
+        modes = synth.modes_for(workload, channels).numpy()
         vals = []
         desc = None
         t_begin = time.time()
         n_steps = args.steps if args.steps > 0 else 5
         for i in range(args.warmup + n_steps):
-            v, desc = run_cpu_reference(args.workload, modes, n_blocks, seconds_target=1.0, signal=args.signal)
+            v, desc = run_cpu_reference(workload, modes, n_blocks, seconds_target=1.0, signal=args.signal)
             if i >= args.warmup:
                 vals.append(v)
             if time.time() - t_begin > 150:
@@ -318,10 +430,11 @@ def main():
         desc["value"] = round(value, 3)
         line = {"impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Msamples/s",
                 "n_gpus": args.gpus, "steps": len(vals), "warmup": args.warmup,
-                "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": None, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
                 "dtype": "q15 int32 + f32", "data": "synthetic",
-                "config": {"workload": args.workload, "description": wl_desc, "signal": args.signal,
-                           "channels_per_gpu": channels, "blocks_per_channel_per_step": n_blocks},
+                "config": config_of(workload, wl_desc, args.signal, channels, n_gpus, n_blocks),
+                "note": "each step times a bounded sample of this workload on the host cores (see "
+                        "cpu_baseline.sample); the CPU arm does not scale with --gpus",
                 "realtime_channels": round(value / 0.256, 1), "cpu_baseline": desc,
                 "e2e": {"value": round(value, 3), "unit": "Msamples/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0},
@@ -342,10 +455,11 @@ def main():
     if world != args.gpus and rank == 0:
         print("note: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE" % (args.gpus, world), file=sys.stderr)
 
-    res = bench_one(torch, R, synth, args.workload, channels, n_blocks, args.steps, args.warmup, args.signal,
+    res = bench_one(torch, R, synth, workload, channels, n_blocks, args.steps, args.warmup, args.signal,
                     device, rank, world, dist, want_e2e=not args.no_e2e)
     if args.no_e2e:
-        res.update(e2e_ms_total=float("inf"), e2e_sync_ms_total=float("inf"), e2e_steps=0, e2e_paths_agree=None)
+        res.update(e2e_ms_total=float("inf"), e2e_sync_ms_total=float("inf"), e2e_copy_ms_total=float("inf"),
+                   e2e_steps=0, e2e_copy_steps=0, e2e_paths_agree=None)
     ms_total = reduce_max(torch, dist, world, device, res["ms_total"])
     e2e_ms_total = reduce_max(torch, dist, world, device, res["e2e_ms_total"])
     total_samples_step = res["samples_per_step"] * world
@@ -354,22 +468,37 @@ def main():
     e2e_value = total_samples_step * res["e2e_steps"] / (e2e_ms_total * 1e-3) / 1e6
     e2e_sync_ms = reduce_max(torch, dist, world, device, res["e2e_sync_ms_total"])
     e2e_sync_value = total_samples_step * res["e2e_steps"] / (e2e_sync_ms * 1e-3) / 1e6
+    e2e_copy_ms = reduce_max(torch, dist, world, device, res["e2e_copy_ms_total"])
+    e2e_copy_value = total_samples_step * res["e2e_copy_steps"] / (e2e_copy_ms * 1e-3) / 1e6
+    paths_agree = gather_flags(torch, dist, world, device, bool(res["e2e_paths_agree"]))
     peak, peak_src = peaks()
     # the dominant kernel: one launch per demodulator kind per step; for single-mode
-    # workloads that is the only kernel in the timed region
+    # workloads that is the only kernel in the timed region besides the small recurrence kernel
     kernel_ms = res["ms_total"] / steps
     achieved = res["samples_per_step"] * ALGO_BYTES_PER_SAMPLE / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get(args.workload)
-    except Exception:
-        pass
+    traffic, traffic_label = traffic_for(workload)
+
+    # every rank: a sample of ITS shard against the compiled reference
+    ok, parity_desc = shard_parity(R, synth, workload, channels, rank * channels, n_blocks, device.index,
+                                   args.signal, 4321 + rank)
+    per_rank = gather_flags(torch, dist, world, device, ok)
+
+    # N > 1: the headline AM bank per GPU as well, so its weak-scaling curve exists
+    am_weak = None
+    if world > 1 and workload != "am" and not args.no_extras:
+        ch = synth.WORKLOADS["am"][0]
+        nb = default_blocks("am", ch)
+        r = bench_one(torch, R, synth, "am", ch, nb, 200, 5, args.signal, device, rank, world, dist, want_e2e=False)
+        ms_am = reduce_max(torch, dist, world, device, r["ms_total"])
+        v = r["samples_per_step"] * world * r["steps"] / (ms_am * 1e-3) / 1e6
+        am_weak = {"value": round(v, 1), "unit": "Msamples/s", "channels_per_gpu": ch, "blocks": nb, "steps": r["steps"],
+                   "ms_per_step": round(ms_am / r["steps"], 4), "scaling": "weak",
+                   "roofline_frac": round(v * 1e6 * ALGO_BYTES_PER_SAMPLE / 1e9 / (peak * world), 4)}
 
     extras = {}
     if rank == 0 and world == 1 and not args.no_extras:
         for wl in ["fm", "wbfm", "ssb", "mixed", "am"]:
-            if wl == args.workload:
+            if wl == workload:
                 continue
             ch = synth.WORKLOADS[wl][0]
             nb = default_blocks(wl, ch)
@@ -378,44 +507,54 @@ def main():
             extras[wl] = {"value": round(v, 1), "unit": "Msamples/s", "channels": ch, "blocks": nb,
                           "realtime_channels": round(v / 0.256),
                           "roofline_frac": round(v * 1e6 * ALGO_BYTES_PER_SAMPLE / 1e9 / peak, 4)}
+            if not args.no_cpu:  # the reference's CPU chain on the same workload, bounded sample
+                _, c = run_cpu_reference(wl, synth.modes_for(wl, ch).numpy(), nb, seconds_target=2.0,
+                                         signal=args.signal, check_gpu=True)
+                extras[wl]["cpu_baseline"] = c
         if args.signal == "tone":
-            r = bench_one(torch, R, synth, args.workload, channels, n_blocks, 40, 3, "noise", device, 0, 1,
+            r = bench_one(torch, R, synth, workload, channels, n_blocks, 40, 3, "noise", device, 0, 1,
                           None, want_e2e=False)
             v = r["samples_per_step"] * r["steps"] / (r["ms_total"] * 1e-3) / 1e6
-            extras[args.workload + "_noise_input"] = {"value": round(v, 1), "unit": "Msamples/s"}
+            extras[workload + "_noise_input"] = {"value": round(v, 1), "unit": "Msamples/s"}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        modes = synth.modes_for(args.workload, channels).numpy()
-        _, cpu = run_cpu_reference(args.workload, modes, n_blocks, seconds_target=12.0, signal=args.signal, check_gpu=True)
+    if rank == 0 and not args.no_cpu:
+        modes = synth.modes_for(workload, channels).numpy()
+        _, cpu = run_cpu_reference(workload, modes, n_blocks, seconds_target=12.0 if world == 1 else 4.0,
+                                   signal=args.signal, check_gpu=True)
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "Msamples/s",
             "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": round(ms_total / steps, 4), "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": round(ms_total / steps, 4), "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "q15 int32 + f32", "data": "synthetic",
-            "config": {"workload": args.workload, "description": wl_desc, "signal": args.signal,
-                       "channels_per_gpu": channels, "blocks_per_channel_per_step": n_blocks,
-                       "block_bytes": BLOCK_BYTES, "iq_bytes_per_gpu_per_step": res["h2d"],
-                       "l2": "input per step (%d MiB) exceeds the 126 MB L2; no flush needed" % (res["h2d"] >> 20),
-                       "sharding": "contiguous channel ranges per rank, no data-path collective"},
+            "config": config_of(workload, wl_desc, args.signal, channels, world, n_blocks),
             "realtime_channels": round(value / 0.256),
             "realtime_channels_per_gpu": round(value / 0.256 / world),
             "clocks": res["clocks"],
             "e2e": {"value": round(e2e_value, 2), "unit": "Msamples/s", "h2d_bytes_per_step": res["h2d"] * world,
                     "d2h_bytes_per_step": res["d2h"] * world, "steps": res["e2e_steps"],
-                    "api": "sdr_ingest_commit + sdr_ingest_retire: 3-slot pinned ring, every tick copied "
-                           "host->device, demodulated, PCM copied device->host; neighbouring ticks overlap",
+                    "api": "sdr_ingest_acquire/commit + sdr_ingest_retire: 3-slot pinned ring the producer writes "
+                           "in place, every tick copied host->device, demodulated, PCM copied device->host; "
+                           "neighbouring ticks overlap",
                     "synchronous_value": round(e2e_sync_value, 2),
                     "synchronous_api": "sdr_accept_iq(SDR_IQ_HOST) + sdr_get_pcm per step, pinned host buffers",
-                    "paths_agree": res["e2e_paths_agree"]},
+                    "copying_value": round(e2e_copy_value, 2),
+                    "copying_api": "sdr_ingest_accept: the caller's block is first memcpy'd into the pinned slot "
+                                   "by one host thread (DataConsumer.cc:246-248), then as above",
+                    "paths_agree": all(paths_agree)},
             "gpu_launches": res["launches"],
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                         "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                         "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_capture": traffic_label,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE,
-                         "kernel_ms": round(kernel_ms, 4), "kernel": KERNELS[args.workload]},
+                         "kernel_ms": round(kernel_ms, 4), "kernel": KERNELS[workload],
+                         "frac_of_box": round(value * 1e6 * ALGO_BYTES_PER_SAMPLE / 1e9 / (peak * world), 4)},
+            "parity": {"gpu_pcm_identical": all(per_rank), "per_rank": per_rank, **parity_desc,
+                       "recurrence_segments_redone_in_timed_region": res["dc_redo"]},
             "cpu_baseline": cpu,
+            "am_weak": am_weak,
             "other_workloads": extras,
         }
         print(json.dumps(line))

@@ -90,6 +90,7 @@ def load_library(build_if_missing=True):
     # diagnostics, not part of include/sdr_b200.h
     L.sdr_debug_set_dc_shape.argtypes = [vp, u32, u32]
     L.sdr_debug_dc_redo_count.argtypes = [vp, C.POINTER(u32)]
+    L.sdr_debug_set_tile_loader.argtypes = [vp, i32]
     L.sdr_filter_bank_create.argtypes = [i32, i32, u32, vp, u32, u32, C.POINTER(vp)]
     L.sdr_filter_bank_destroy.argtypes = [vp]
     L.sdr_filter_bank_set_stream.argtypes = [vp, vp]
@@ -246,6 +247,10 @@ class Engine:
         """Segmentation of the AM/SSB recurrence kernel: seg_count 0 = per call; warm_rows = rows of
         32 PCM samples a segment warms up on."""
         self._ck(self.L.sdr_debug_set_dc_shape(self.h, int(seg_count), int(warm_rows)))
+
+    def debug_set_tile_loader(self, tma=True):
+        """AM/SSB FIR kernel: full tiles by TMA (cp.async.bulk.tensor, the default) or by cp.async."""
+        self._ck(self.L.sdr_debug_set_tile_loader(self.h, int(bool(tma))))
 
     def debug_dc_redo_count(self):
         """Segments the recurrence kernel had to redo serially since the engine was created."""

@@ -9,6 +9,7 @@
 //     mode-uniform), the two atan2 tables, an IQ staging buffer and the PCM buffer.
 // sdr_accept_iq queues one launch per demodulator kind that has channels (AM and SSB: a FIR
 // kernel plus a recurrence kernel on a second stream). No CPU path exists.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
@@ -53,6 +54,12 @@ struct sdr_engine {
   static constexpr int RUN_AHEAD = 32, PACE = 2 * RUN_AHEAD;
   cudaEvent_t ev_pace[PACE] = {};
   float *d_scratch[5][RING_MAX] = {};
+  // AM/SSB FIR kernel: full tiles by TMA (cp.async.bulk.tensor through a tensor map of the caller's
+  // IQ array, rebuilt when pointer, stride or length change) or by cp.async
+  bool use_tma = true;
+  CUtensorMap tmap;
+  const void *tmap_iq = nullptr;
+  uint64_t tmap_stride = 0, tmap_rows = 0;
   // dc_block_kernel's segmentation (0 = chosen per call) and its redo counter
   uint32_t dc_seg_count = 0, dc_warm_rows = 32;
   uint32_t *d_counters = nullptr;
@@ -186,6 +193,46 @@ int join_streams(sdr_engine *e) {
   return SDR_OK;
 }
 
+// The IQ array as the TMA sees it: uint8 [n_channels][rows of 128 bytes][128], of which only the
+// rows of FULL tiles (16 rows = 2048 bytes) are ever asked for, so the map never reaches past
+// a channel's valid bytes. The boxes are {128, 16, 1} with the hardware's 128-byte swizzle.
+typedef CUresult (*TensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                         const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                         CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                         CUtensorMapFloatOOBfill);
+int iq_tensor_map(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples) {
+  const uint64_t rows = (uint64_t)(n_samples / TILE) * (TILE_BYTES / 128);
+  if (e->tmap_iq == iq && e->tmap_stride == ch_stride && e->tmap_rows == rows) return SDR_OK;
+  static TensorMapEncodeTiled encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    SDR_CK(e, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+    if (!fn || qr != cudaDriverEntryPointSuccess) return fail(e, SDR_E_CUDA, "the driver has no cuTensorMapEncodeTiled");
+    encode = (TensorMapEncodeTiled)fn;
+  }
+  if (rows == 0) {  // no full tile in this call: the kernel issues no TMA; keep any valid map
+    memset(&e->tmap, 0, sizeof e->tmap);
+  } else {
+    const cuuint64_t dims[3] = {128, rows, e->n};
+    const cuuint64_t strides[2] = {128, ch_stride};
+    const cuuint32_t box[3] = {128, TILE_BYTES / 128, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(&e->tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(iq), dims, strides, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      char msg[96];
+      snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+      return fail(e, SDR_E_CUDA, msg);
+    }
+  }
+  e->tmap_iq = iq;
+  e->tmap_stride = ch_stride;
+  e->tmap_rows = rows;
+  return SDR_OK;
+}
+
 // AM / SSB: FIR kernel on the engine's stream, recurrence kernel on rec_stream.
 template <bool SSB>
 int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples, int fmt) {
@@ -230,7 +277,14 @@ int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride,
   p.scratch = e->d_scratch[kind][par];
   p.allowed = e->last_gated ? e->d_allowed[par] : nullptr;
   p.trace = e->d_trace ? e->d_trace + 4 * (e->seq % sdr_engine::TRACE_CALLS) : nullptr;
-  amssb_fir_kernel<SSB><<<(uint32_t)((n_warps + 3) / 4), 128, 4 * 2 * TILE_BYTES, e->stream>>>(p);
+  const uint32_t grid = (uint32_t)((n_warps + 3) / 4);
+  if (e->use_tma) {
+    const int rc = iq_tensor_map(e, iq, ch_stride, n_samples);
+    if (rc) return rc;
+    amssb_fir_kernel<SSB, true><<<grid, 128, 4 * 2 * TILE_BYTES, e->stream>>>(p, e->tmap);
+  } else {
+    amssb_fir_kernel<SSB, false><<<grid, 128, 4 * 2 * TILE_BYTES, e->stream>>>(p, e->tmap);
+  }
   SDR_CK(e, cudaGetLastError());
   e->launches++;
   return SDR_OK;
@@ -896,6 +950,13 @@ int sdr_debug_set_dc_shape(sdr_engine *e, uint32_t seg_count, uint32_t warm_rows
   if (!e || seg_count > 32 || (seg_count & (seg_count - 1))) return SDR_E_ARG;
   e->dc_seg_count = seg_count;
   e->dc_warm_rows = warm_rows;
+  return SDR_OK;
+}
+
+// how the AM/SSB FIR kernel fetches full tiles: 1 = TMA (default), 0 = cp.async (for A/B runs)
+int sdr_debug_set_tile_loader(sdr_engine *e, int tma) {
+  if (!e) return SDR_E_ARG;
+  e->use_tma = tma != 0;
   return SDR_OK;
 }
 

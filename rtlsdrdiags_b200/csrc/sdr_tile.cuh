@@ -23,6 +23,7 @@
 #include "sdr_device.cuh"
 
 #if SDR_DEVICE_BUILD
+#include <cuda.h>  // CUtensorMap
 namespace sdr {
 
 constexpr int TILE = 1024;             // complex samples per tile
@@ -120,6 +121,77 @@ struct TileIo {
       asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                    : "=r"(w[4 * j]), "=r"(w[4 * j + 1]), "=r"(w[4 * j + 2]), "=r"(w[4 * j + 3])
                    : "r"(rd[j] + buf)
+                   : "memory");
+  }
+};
+
+// ---------------------------------------------------------------------------
+// TMA tile loader. A full tile (2048 contiguous bytes of one channel) is a box of 16 rows x 128
+// bytes of the 3-D view [channel][row of 128 B][128] of the caller's IQ array; ONE lane issues
+// one cp.async.bulk.tensor per tile and the copy engine lands it in the warp's slot with the
+// hardware's 128-byte swizzle (16-byte chunk c of row r sits at chunk c ^ (r & 7)), which makes
+// the per-lane read of 64 consecutive bytes bank-conflict free exactly like the hand swizzle of
+// TileIo: lanes 2r and 2r+1 share row r, and a quarter-warp's eight 16-byte reads fall on eight
+// different chunk columns. Completion is an mbarrier per slot buffer (expect_tx = 2048 bytes).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_tile(uint32_t dst, const CUtensorMap *map, uint32_t row, uint32_t ch, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(0), "r"(row), "r"(ch), "r"(bar)
+      : "memory");
+}
+struct TmaIo {
+  uint32_t slot;    // shared address of slot buffer 0 (1024-byte aligned); buffer 1 follows at + TILE_BYTES
+  uint32_t bar;     // shared address of the two mbarriers (8 bytes each)
+  uint32_t rd[4];   // shared addresses of the lane's four 16-byte chunks in buffer 0
+  uint32_t phase;   // bit b = parity the next wait on buffer b's barrier expects
+  __device__ __forceinline__ void init(const char *slots, uint64_t *bars, int lane) {
+    slot = (uint32_t)__cvta_generic_to_shared(slots);
+    bar = (uint32_t)__cvta_generic_to_shared(bars);
+    const uint32_t r = (uint32_t)lane >> 1, c0 = 4u * ((uint32_t)lane & 1u);
+#pragma unroll
+    for (uint32_t j = 0; j < 4; ++j) rd[j] = slot + 128u * r + 16u * ((c0 + j) ^ (r & 7u));
+    phase = 0;
+    if (lane == 0) {
+      mbar_init(bar, 1);
+      mbar_init(bar + 8, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
+  // one lane: arm buffer b's barrier and start the copy of tile `t` of channel `ch`
+  __device__ __forceinline__ void issue(uint32_t b, const CUtensorMap *map, uint32_t t, uint32_t ch) const {
+    mbar_expect_tx(bar + 8 * b, TILE_BYTES);
+    tma_load_tile(slot + b * TILE_BYTES, map, t * (TILE_BYTES / 128), ch, bar + 8 * b);
+  }
+  __device__ __forceinline__ void wait(uint32_t b) {
+    mbar_wait(bar + 8 * b, (phase >> b) & 1u);
+    phase ^= 1u << b;
+  }
+  __device__ __forceinline__ void read(uint32_t b, uint32_t (&w)[16]) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                   : "=r"(w[4 * j]), "=r"(w[4 * j + 1]), "=r"(w[4 * j + 2]), "=r"(w[4 * j + 3])
+                   : "r"(rd[j] + b * TILE_BYTES)
                    : "memory");
   }
 };
@@ -319,11 +391,15 @@ struct AmSsbTile {
 // dc_block_kernel: the sequential recurrence, lane == channel, over the numerators the FIR
 // kernel left in `scratch`. The engine launches it on a second stream, so it overlaps the
 // next call's FIR kernel.
-template <bool SSB>
-__global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant__ LaunchParams p) {
+// TMA = true: full tiles arrive by cp.async.bulk.tensor (TmaIo), one instruction of one lane per
+// tile; false: by four cp.async per lane (TileIo). A partial last tile takes cp.async either way.
+template <bool SSB, bool TMA>
+__global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant__ LaunchParams p,
+                                                           const __grid_constant__ CUtensorMap tmap) {
   using T = AmSsbTile<SSB>;
   constexpr uint32_t WARMUP = T::WARMUP_TILES;
-  extern __shared__ uint4 smem_raw[];
+  extern __shared__ __align__(1024) uint4 smem_raw[];
+  __shared__ uint64_t s_bar[4][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n_warps = p.aux;  // worker warps of the whole grid
   const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -338,7 +414,9 @@ __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant
 
   char *slots = reinterpret_cast<char *>(smem_raw) + warp * 2 * TILE_BYTES;
   TileIo io;
-  io.init(slots, lane);
+  TmaIo tio;
+  if constexpr (TMA) tio.init(slots, s_bar[warp], lane);
+  else io.init(slots, lane);
   PrevMasks pm;
   pm.init(lane);
   const int fmt = p.fmt;
@@ -377,31 +455,45 @@ __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant
     const uint8_t *g = src + (uint64_t)tw * TILE_BYTES + 16 * lane;  // the lane's chunk 0 of the tile to fetch next
     // the scratch row of tile tw; rows of warm-up tiles are walked over but not written
     float *sp = p.scratch + ((uint64_t)tw * p.n_list + li) * 32 + lane;
-    uint32_t buf = 0;
+    uint32_t buf = 0;  // 0 or 1
     __syncwarp();  // the previous piece's last reads of the slot buffers are done
-    if (tw < tf) io.fill_full(buf, g);
-    else tile_fill(slots + buf, g - 16 * lane, lane, (int)(p.n_samples - tw * TILE) >> 3);
+    if (tw < tf) {
+      if constexpr (TMA) { if (lane == 0) tio.issue(0, &tmap, tw, ch); }
+      else io.fill_full(0, g);
+    } else {
+      tile_fill(slots, g - 16 * lane, lane, (int)(p.n_samples - tw * TILE) >> 3);
+    }
     cp_async_commit();
     for (uint32_t t = tw; t < tf; ++t) {
       g += TILE_BYTES;
-      if (t + 1 < tf) io.fill_full(buf ^ TILE_BYTES, g);
-      else if (partial) tile_fill(slots + (buf ^ TILE_BYTES), g - 16 * lane, lane, (int)(p.n_samples - (t + 1) * TILE) >> 3);
-      cp_async_commit();
-      cp_async_wait<1>();
-      __syncwarp();
+      if (t + 1 < tf) {
+        if constexpr (TMA) { if (lane == 0) tio.issue(buf ^ 1u, &tmap, t + 1, ch); }
+        else io.fill_full((buf ^ 1u) * TILE_BYTES, g);
+      } else if (partial) {
+        tile_fill(slots + (buf ^ 1u) * TILE_BYTES, g - 16 * lane, lane, (int)(p.n_samples - (t + 1) * TILE) >> 3);
+      }
       uint32_t w[16];
-      io.read(buf, w);
+      if constexpr (TMA) {
+        if (partial) cp_async_commit();
+        tio.wait(buf);
+        tio.read(buf, w);
+      } else {
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        io.read(buf * TILE_BYTES, w);
+      }
       __syncwarp();  // this buffer may be refilled (tile t+2) once every lane has read it
       const uint32_t d = T::template tile<true>(w, fmt, lsb, pv, lane, 32, pm);
       if (t >= t0) *sp = u2f(d);
       sp += sp_step;
-      buf ^= TILE_BYTES;
+      buf ^= 1u;
     }
     if (partial) {
       cp_async_wait<0>();
       __syncwarp();
       uint32_t w[16];
-      tile_read(slots + buf, lane, w);
+      tile_read(slots + buf * TILE_BYTES, lane, w);
       const int r = (int)(p.n_samples - tf * TILE) >> 5;
       const uint32_t d = T::template tile<false>(w, fmt, lsb, pv, lane, r, pm);
       if (lane < r) *sp = u2f(d);  // tf >= t0 always

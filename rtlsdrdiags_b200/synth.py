@@ -16,9 +16,9 @@ WORKLOADS = {
     "am": (1024, [MODE_AM], "AM envelope demod, batch of 1024 synthetic 256 kS/s IQ channels on 1xB200"),
     "fm": (8192, [MODE_FM], "NBFM, 8192 channels per GPU (north-star real-time target mode)"),
     "wbfm": (8192, [MODE_WBFM], "WBFM broadcast (discriminator + de-emphasis), 8192 channels on 1xB200"),
-    "ssb": (8192, [MODE_LSB, MODE_USB], "LSB/USB SSB demod, 16384 channels across 2 B200 (8192 per GPU)"),
+    "ssb": (8192, [MODE_LSB, MODE_USB], "LSB/USB SSB demod with the phasing network and sideband selection (BASELINE config 4: 16384 channels across 2/4 B200)"),
     "mixed": (8192, [MODE_AM, MODE_FM, MODE_WBFM, MODE_LSB, MODE_USB],
-              "mixed-mode AM/FM/WBFM/SSB bank, 65536 streams across 8 B200 (8192 per GPU)"),
+              "mixed-mode AM/FM/WBFM/LSB/USB bank (BASELINE config 5: 65536 streams across 8 B200)"),
 }
 
 

@@ -13,6 +13,9 @@ done
 timeout 300 python bench.py --steps 2000 --warmup 5 --no-extras --no-cpu --no-e2e 2>&1 | tail -1 | python -c "
 import sys, json
 d = json.loads(sys.stdin.read()); print('am steps2000', d['value'], 'frac', d['roofline']['frac'], 'ms', d['ms_per_step'], d['clocks'])" | tee -a gpurun_out/r02a_am.txt
+SDR_BENCH_TILE_LOADER=cpasync timeout 300 python bench.py --steps 2000 --warmup 5 --no-extras --no-cpu --no-e2e 2>&1 | tail -1 | python -c "
+import sys, json
+d = json.loads(sys.stdin.read()); print('am steps2000 cp.async loader', d['value'], 'frac', d['roofline']['frac'], 'ms', d['ms_per_step'], d['clocks'])" | tee -a gpurun_out/r02a_am.txt
 for wl in ssb mixed; do
 timeout 300 python bench.py --workload $wl --steps 50 --warmup 5 --no-extras --no-cpu --no-e2e 2>&1 | tail -1 | python -c "
 import sys, json
