@@ -214,8 +214,10 @@ def bench_one(torch, R, synth, workload, channels, n_blocks, steps, warmup, sign
     nbytes = n_blocks * BLOCK_BYTES
     eng = R.Engine(channels, device.index, nbytes)
     eng.set_modes(modes.numpy())
-    if os.environ.get("SDR_BENCH_TILE_LOADER") == "cpasync":  # A/B runs: AM/SSB tiles by cp.async instead of TMA
-        eng.debug_set_tile_loader(False)
+    if os.environ.get("SDR_BENCH_TILE_LOADER"):  # A/B runs: AM/SSB tiles by cp.async (0) or TMA with 2..4 buffers
+        eng.debug_set_tile_loader(int(os.environ["SDR_BENCH_TILE_LOADER"]))
+    if os.environ.get("SDR_BENCH_DC_SHAPE"):     # A/B runs: "segments,warm-up rows" of the recurrence kernel
+        eng.debug_set_dc_shape(*[int(x) for x in os.environ["SDR_BENCH_DC_SHAPE"].split(",")])
     # a dedicated (non-default) stream: the kernels are launched on it and the CUDA
     # events that time them are recorded on it
     stream = torch.cuda.Stream(device)

@@ -34,6 +34,10 @@
  *     (IqDataProcessor.cc:756-760, UdpClient.cc:173-241)
  *   DataConsumer::acceptData(ts, buf, n) + consumer thread  sdr_ingest_accept / _acquire+_commit,
  *     (src_diags/DataConsumer.cc:220-261, 318-352)           sdr_ingest_retire, sdr_ingest_stats
+ *   Radio's demodulator objects, one set per radio, and    sdr_bank_create, sdr_bank_set_mode(s),
+ *     one DataConsumer feeding them (Radio.cc:150-187,       sdr_bank_acquire + sdr_bank_commit,
+ *     DataConsumer.cc:220-352) -- for radios spread over     sdr_bank_retire
+ *     several GPUs of one box
  *   new Decimator / Interpolator / Decimator_int16 /        sdr_filter_bank_create
  *     Interpolator_int16 (N, taps, factor)
  *     (Filters/Decimator.cc:41-76, Filters/Interpolator.cc:39-61, Filters/Int16/*.cc)
@@ -134,8 +138,7 @@ int sdr_iq_dump_device(sdr_engine *e, int8_t **rows, uint64_t *row_stride, uint3
  * interleaved I,Q of which the first bytes_per_channel are consumed.
  * bytes_per_channel must be a multiple of 64 (one PCM sample); pointers and
  * stride multiples of 16. Asynchronous: returns once the work is queued; a caller
- * that queues faster than the GPU retires is held while 32 calls are in flight
- * (environment SDR_PACE = 0..256 changes the bound, 0 removes it). Each
+ * that queues faster than the GPU retires is held while 32 calls are in flight. Each
  * channel is demodulated by the mode it is in, exactly as the reference's
  * switch does; channels in mode None produce nothing. Filter state carries
  * over to the next call. */
@@ -146,7 +149,8 @@ int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes_per_channel,
  * in mode None), rows are samples_per_row = bytes_per_channel/64 apart.
  * Synchronises. Either pointer may be NULL. */
 int sdr_get_pcm(sdr_engine *e, int16_t *pcm, uint32_t *counts);
-/* Device-resident PCM of the last call: [n_channels][*stride] int16. */
+/* Device-resident PCM of the last call: [n_channels][*stride] int16. The engine alternates
+ * between two buffers, so ask again after every sdr_accept_iq. */
 int sdr_pcm_device(sdr_engine *e, int16_t **pcm, uint64_t *stride);
 int sdr_sync(sdr_engine *e);
 /* The engine runs part of its work on a second, internal stream. sdr_join makes the
@@ -182,6 +186,41 @@ int sdr_ingest_retire(sdr_ingest *q, uint32_t *timestamp, const int16_t **pcm, u
 /* lastTimeStamp and shortBlockCount (DataConsumer.cc:282-283), ticks committed, ticks in flight */
 int sdr_ingest_stats(const sdr_ingest *q, uint32_t *last_timestamp, uint32_t *short_block_count, uint64_t *ticks,
                      uint32_t *in_flight);
+
+/* ---- multi-device bank ----
+ * n_channels radios over several GPUs of one box: device i of `devices` owns the contiguous
+ * channels [n i / G, n (i + 1) / G) with an engine and an ingest ring of its own; nothing is
+ * exchanged between devices. A tick is one block of every channel, written by the producer into
+ * ONE pinned array [n_channels][block_bytes] (sdr_bank_acquire); sdr_bank_commit queues, per
+ * device, the host->device copy of its slab, the demodulation and the copy of its PCM rows into
+ * ONE pinned array [n_channels][bytes / 64] that sdr_bank_retire hands out once every device is
+ * done. All calls only queue work, so one host thread drives the whole box. Calls on one bank
+ * must be serialised by the caller. Setters not mirrored here go through the shard's engine
+ * (sdr_bank_shard) with the channel index made local (channel - first_channel). */
+typedef struct sdr_bank sdr_bank;
+int sdr_bank_create(uint32_t n_channels, const int *devices, uint32_t n_devices, uint64_t block_bytes,
+                    uint32_t n_slots /* 2..64 */, sdr_bank **out);
+int sdr_bank_destroy(sdr_bank *b);
+uint32_t sdr_bank_device_count(const sdr_bank *b);
+/* Shard i: its CUDA device, first channel, channel count and engine; any pointer may be NULL. */
+int sdr_bank_shard(const sdr_bank *b, uint32_t i, int *device, uint32_t *first_channel, uint32_t *n_channels,
+                   sdr_engine **engine);
+int sdr_bank_set_mode(sdr_bank *b, uint32_t channel, int mode);
+int sdr_bank_set_modes(sdr_bank *b, const uint8_t *modes /* [n_channels] */);
+int sdr_bank_set_gain(sdr_bank *b, uint32_t channel, int kind, float gain);
+int sdr_bank_reset(sdr_bank *b, uint32_t channel, int kind);
+int sdr_bank_set_squelch_threshold(sdr_bank *b, uint32_t channel, int32_t threshold_dbfs);
+/* The next free tick array, [n_channels][*channel_stride] bytes of pinned host memory. */
+int sdr_bank_acquire(sdr_bank *b, void **iq, uint64_t *channel_stride);
+/* Queue the acquired tick on every device (flags: SDR_IQ_U8_OFFSET or SDR_IQ_S8_ROTATED). A tick
+ * longer than block_bytes is clipped, a shorter one counts as a short block on every shard. */
+int sdr_bank_commit(sdr_bank *b, uint32_t timestamp, uint64_t bytes_per_channel, uint32_t flags);
+/* Waits for the oldest tick in flight on every device: its PCM [n_channels][*samples_per_row]
+ * (pinned host memory, valid until the slot is acquired again) and counts[n_channels]. */
+int sdr_bank_retire(sdr_bank *b, uint32_t *timestamp, const int16_t **pcm, uint32_t *samples_per_row,
+                    const uint32_t **counts);
+/* Text of the last error on this bank (or of the last failed create if b is NULL). */
+const char *sdr_bank_last_error(const sdr_bank *b);
 
 /* ---- batched multirate filter banks ----
  * The reference's generic filter classes that the IQ->PCM path does not instantiate itself.

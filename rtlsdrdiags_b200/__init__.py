@@ -28,6 +28,9 @@ ABI_SYMBOLS = ["sdr_engine_create", "sdr_engine_destroy", "sdr_set_stream", "sdr
                "sdr_set_receive_gain_db", "sdr_enable_signal_reports", "sdr_get_signal", "sdr_set_iq_dump",
                "sdr_get_iq_dump", "sdr_iq_dump_device", "sdr_ingest_create", "sdr_ingest_destroy",
                "sdr_ingest_accept", "sdr_ingest_acquire", "sdr_ingest_commit", "sdr_ingest_retire", "sdr_ingest_stats",
+               "sdr_bank_create", "sdr_bank_destroy", "sdr_bank_device_count", "sdr_bank_shard", "sdr_bank_set_mode",
+               "sdr_bank_set_modes", "sdr_bank_set_gain", "sdr_bank_reset", "sdr_bank_set_squelch_threshold",
+               "sdr_bank_acquire", "sdr_bank_commit", "sdr_bank_retire", "sdr_bank_last_error",
                "sdr_filter_bank_create", "sdr_filter_bank_destroy", "sdr_filter_bank_set_stream",
                "sdr_filter_bank_reset", "sdr_filter_bank_out_count", "sdr_filter_bank_run", "sdr_filter_bank_sync",
                "sdr_filter_bank_taps_q15", "sdr_filter_bank_launch_count", "sdr_filter_bank_last_error"]
@@ -91,6 +94,21 @@ def load_library(build_if_missing=True):
     L.sdr_debug_set_dc_shape.argtypes = [vp, u32, u32]
     L.sdr_debug_dc_redo_count.argtypes = [vp, C.POINTER(u32)]
     L.sdr_debug_set_tile_loader.argtypes = [vp, i32]
+    L.sdr_bank_create.argtypes = [u32, C.POINTER(i32), u32, u64, u32, C.POINTER(vp)]
+    L.sdr_bank_destroy.argtypes = [vp]
+    L.sdr_bank_device_count.argtypes = [vp]
+    L.sdr_bank_device_count.restype = u32
+    L.sdr_bank_shard.argtypes = [vp, u32, C.POINTER(i32), C.POINTER(u32), C.POINTER(u32), C.POINTER(vp)]
+    L.sdr_bank_set_mode.argtypes = [vp, u32, i32]
+    L.sdr_bank_set_modes.argtypes = [vp, vp]
+    L.sdr_bank_set_gain.argtypes = [vp, u32, i32, C.c_float]
+    L.sdr_bank_reset.argtypes = [vp, u32, i32]
+    L.sdr_bank_set_squelch_threshold.argtypes = [vp, u32, C.c_int32]
+    L.sdr_bank_acquire.argtypes = [vp, C.POINTER(vp), C.POINTER(u64)]
+    L.sdr_bank_commit.argtypes = [vp, u32, u64, u32]
+    L.sdr_bank_retire.argtypes = [vp, C.POINTER(u32), C.POINTER(vp), C.POINTER(u32), C.POINTER(vp)]
+    L.sdr_bank_last_error.argtypes = [vp]
+    L.sdr_bank_last_error.restype = C.c_char_p
     L.sdr_filter_bank_create.argtypes = [i32, i32, u32, vp, u32, u32, C.POINTER(vp)]
     L.sdr_filter_bank_destroy.argtypes = [vp]
     L.sdr_filter_bank_set_stream.argtypes = [vp, vp]
@@ -248,9 +266,10 @@ class Engine:
         32 PCM samples a segment warms up on."""
         self._ck(self.L.sdr_debug_set_dc_shape(self.h, int(seg_count), int(warm_rows)))
 
-    def debug_set_tile_loader(self, tma=True):
-        """AM/SSB FIR kernel: full tiles by TMA (cp.async.bulk.tensor, the default) or by cp.async."""
-        self._ck(self.L.sdr_debug_set_tile_loader(self.h, int(bool(tma))))
+    def debug_set_tile_loader(self, loader=True):
+        """AM/SSB FIR kernel: full tiles by TMA (cp.async.bulk.tensor; True / 1 = default depth, 2..4 =
+        that many slot buffers per warp) or by cp.async (False / 0)."""
+        self._ck(self.L.sdr_debug_set_tile_loader(self.h, int(loader)))
 
     def debug_dc_redo_count(self):
         """Segments the recurrence kernel had to redo serially since the engine was created."""
@@ -326,6 +345,79 @@ class Ingest:
         self.e._ck(self.L.sdr_ingest_stats(self.q, C.byref(ts), C.byref(short), C.byref(ticks), C.byref(fl)))
         return {"last_timestamp": ts.value, "short_blocks": short.value, "ticks": ticks.value,
                 "in_flight": fl.value}
+
+
+class Bank:
+    """n_channels radios over several GPUs of one box (sdr_bank_*): contiguous channel shards, one
+    pinned tick array and one pinned PCM array per slot shared by all devices."""
+
+    def __init__(self, n_channels, devices, block_bytes=BLOCK_BYTES, n_slots=3):
+        self.L = load_library()
+        self.n, self.block_bytes = int(n_channels), int(block_bytes)
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        b = C.c_void_p()
+        rc = self.L.sdr_bank_create(self.n, devs, len(devices), self.block_bytes, int(n_slots), C.byref(b))
+        if rc != 0:
+            raise SdrError("sdr_bank_create failed (%d): %s" % (rc, self.L.sdr_bank_last_error(None).decode()))
+        self.b = b
+
+    def close(self):
+        if getattr(self, "b", None):
+            self.L.sdr_bank_destroy(self.b)
+            self.b = None
+
+    __del__ = close
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise SdrError("sdr error %d: %s" % (rc, self.L.sdr_bank_last_error(self.b).decode()))
+
+    def shards(self):
+        """[(device, first_channel, n_channels)] per shard."""
+        out = []
+        for i in range(self.L.sdr_bank_device_count(self.b)):
+            d, f, n = C.c_int(), C.c_uint32(), C.c_uint32()
+            self._ck(self.L.sdr_bank_shard(self.b, i, C.byref(d), C.byref(f), C.byref(n), None))
+            out.append((d.value, f.value, n.value))
+        return out
+
+    def set_mode(self, channel, mode):
+        self._ck(self.L.sdr_bank_set_mode(self.b, channel, mode))
+
+    def set_modes(self, modes):
+        m = np.ascontiguousarray(modes, dtype=np.uint8)
+        if m.size != self.n:
+            raise SdrError("modes must have one entry per channel")
+        self._ck(self.L.sdr_bank_set_modes(self.b, m.ctypes.data_as(C.c_void_p)))
+
+    def set_gain(self, channel, kind, gain):
+        self._ck(self.L.sdr_bank_set_gain(self.b, channel, kind, float(gain)))
+
+    def reset(self, channel, kind):
+        self._ck(self.L.sdr_bank_reset(self.b, channel, kind))
+
+    def set_squelch_threshold(self, channel, dbfs):
+        self._ck(self.L.sdr_bank_set_squelch_threshold(self.b, channel, int(dbfs)))
+
+    def acquire(self):
+        """The next free tick as a writable [n_channels][block_bytes] uint8 view of pinned memory."""
+        p, stride = C.c_void_p(), C.c_uint64()
+        self._ck(self.L.sdr_bank_acquire(self.b, C.byref(p), C.byref(stride)))
+        buf = (C.c_uint8 * (self.n * stride.value)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.uint8).reshape(self.n, stride.value)
+
+    def commit(self, timestamp, bytes_per_channel=None, fmt=IQ_U8_OFFSET):
+        self._ck(self.L.sdr_bank_commit(self.b, int(timestamp) & 0xFFFFFFFF,
+                                        self.block_bytes if bytes_per_channel is None else int(bytes_per_channel), fmt))
+
+    def retire(self, copy=True):
+        """(timestamp, pcm [n_channels][samples], counts [n_channels]) of the oldest tick in flight."""
+        ts, samples, p, c = C.c_uint32(), C.c_uint32(), C.c_void_p(), C.c_void_p()
+        self._ck(self.L.sdr_bank_retire(self.b, C.byref(ts), C.byref(p), C.byref(samples), C.byref(c)))
+        pcm = np.frombuffer((C.c_int16 * (self.n * samples.value)).from_address(p.value), dtype=np.int16)
+        counts = np.frombuffer((C.c_uint32 * self.n).from_address(c.value), dtype=np.uint32)
+        pcm = pcm.reshape(self.n, samples.value)
+        return ts.value, (pcm.copy() if copy else pcm), (counts.copy() if copy else counts)
 
 
 FILTER_DECIMATOR_F32, FILTER_INTERPOLATOR_F32, FILTER_DECIMATOR_I16, FILTER_INTERPOLATOR_I16 = 1, 2, 3, 4

@@ -44,8 +44,8 @@ struct LaunchParams {
   uint64_t pcm_stride;       // int16 elements between channels
   const float *lut;          // atan2 table of this mode (FM 280x280, WBFM 256x256)
   uint32_t aux;              // kernel-specific word (WBFM: scheduler sharing; AM/SSB FIR: worker warps; dc_block: tail offset)
-  float *scratch;            // AM/SSB: IIR numerators between the FIR and the recurrence kernel,
-                             // [tile][list index][32 lanes]
+  int16_t *scratch;          // AM/SSB: IIR numerators between the FIR and the recurrence kernel,
+                             // [list index][row = tile][32 lanes] (exact small integers)
   const uint8_t *allowed;    // [n_channels] squelch gate of this call, or nullptr = all open
   uint32_t call_id;          // AM/SSB/FM: 31-bit id of this call, never 0 (versions the carry buffers)
   const uint32_t *tab;       // FM: tensor-core tuner tables (fm_mma_table in sdr_engine.cu)

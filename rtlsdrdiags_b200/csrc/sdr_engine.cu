@@ -53,15 +53,15 @@ struct sdr_engine {
   // RUN_AHEAD calls are in flight (see sdr_accept_iq)
   static constexpr int RUN_AHEAD = 32, PACE = 2 * RUN_AHEAD;
   cudaEvent_t ev_pace[PACE] = {};
-  float *d_scratch[5][RING_MAX] = {};
+  int16_t *d_scratch[5][RING_MAX] = {};
   // AM/SSB FIR kernel: full tiles by TMA (cp.async.bulk.tensor through a tensor map of the caller's
   // IQ array, rebuilt when pointer, stride or length change) or by cp.async
-  bool use_tma = true;
+  int tile_loader = 4;  // 0 = cp.async (two slot buffers), 2 / 3 / 4 = TMA with that many slot buffers
   CUtensorMap tmap;
   const void *tmap_iq = nullptr;
   uint64_t tmap_stride = 0, tmap_rows = 0;
   // dc_block_kernel's segmentation (0 = chosen per call) and its redo counter
-  uint32_t dc_seg_count = 0, dc_warm_rows = 32;
+  uint32_t dc_seg_count = 0, dc_warm_rows = 28;  // 896 steps: beyond the latest merge seen (807)
   uint32_t *d_counters = nullptr;
   uint64_t seq = 0;        // sdr_accept_iq calls so far
   bool rec_pending = false;  // work on rec_stream that `stream` has not waited for yet
@@ -87,8 +87,11 @@ struct sdr_engine {
   float *d_lut_wbfm_half = nullptr;  // q >= 0 half plane for wbfm_tile2_kernel, [129][256]
   uint32_t *d_fm_tab = nullptr;  // tensor-core tuner tables, fm_mma_table()
   uint8_t *d_iq = nullptr;
-  int16_t *d_pcm = nullptr;
+  // two PCM buffers, used by alternate calls: the read-back of call k (sdr_get_pcm, the ingest
+  // ring's device->host copy) does not hold up the kernels of call k+1
+  int16_t *d_pcm2[2] = {nullptr, nullptr};
   uint64_t pcm_stride = 0;
+  int16_t *pcm_of(uint64_t call) const { return d_pcm2[call & 1]; }
 
   // squelch (IqDataProcessor's Squelch object, one per channel)
   std::vector<int32_t> threshold;   // dBFS, -200 = the reference's always-open default
@@ -246,7 +249,7 @@ int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride,
     const size_t max_tiles = (size_t)((e->max_bytes / 2 + TILE - 1) / TILE);
     for (int i = 0; i < e->ring; ++i)
       if (!e->d_scratch[kind][i])
-        SDR_CK(e, cudaMalloc(&e->d_scratch[kind][i], (size_t)e->n * max_tiles * 32 * sizeof(float)));
+        SDR_CK(e, cudaMalloc(&e->d_scratch[kind][i], (size_t)e->n * max_tiles * 32 * sizeof(int16_t)));
   }
   // The launch's tiles are dealt out in equal shares to 48 worker warps per SM (12 CTAs of 4
   // warps, of which 4-5 are resident at a time): shares small enough that SMs which also host
@@ -269,7 +272,7 @@ int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride,
   p.state_stride = (uint32_t)T::STATE_BYTES;
   p.scale = e->d_scale[kind];
   p.lsb = e->d_lsb;
-  p.pcm = e->d_pcm;
+  p.pcm = e->pcm_of(e->seq);
   p.pcm_stride = e->pcm_stride;
   p.lut = nullptr;
   p.aux = (uint32_t)n_warps;
@@ -278,12 +281,14 @@ int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride,
   p.allowed = e->last_gated ? e->d_allowed[par] : nullptr;
   p.trace = e->d_trace ? e->d_trace + 4 * (e->seq % sdr_engine::TRACE_CALLS) : nullptr;
   const uint32_t grid = (uint32_t)((n_warps + 3) / 4);
-  if (e->use_tma) {
+  if (e->tile_loader == 0) {
+    amssb_fir_kernel<SSB, false, 2><<<grid, 128, 4 * 2 * TILE_BYTES, e->stream>>>(p, e->tmap);
+  } else {
     const int rc = iq_tensor_map(e, iq, ch_stride, n_samples);
     if (rc) return rc;
-    amssb_fir_kernel<SSB, true><<<grid, 128, 4 * 2 * TILE_BYTES, e->stream>>>(p, e->tmap);
-  } else {
-    amssb_fir_kernel<SSB, false><<<grid, 128, 4 * 2 * TILE_BYTES, e->stream>>>(p, e->tmap);
+    if (e->tile_loader == 2) amssb_fir_kernel<SSB, true, 2><<<grid, 128, 4 * 2 * TILE_BYTES, e->stream>>>(p, e->tmap);
+    else if (e->tile_loader == 3) amssb_fir_kernel<SSB, true, 3><<<grid, 128, 4 * 3 * TILE_BYTES, e->stream>>>(p, e->tmap);
+    else amssb_fir_kernel<SSB, true, 4><<<grid, 128, 4 * 4 * TILE_BYTES, e->stream>>>(p, e->tmap);
   }
   SDR_CK(e, cudaGetLastError());
   e->launches++;
@@ -291,14 +296,14 @@ int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride,
 }
 
 // Segmentation of one call's recurrence (dc_block_kernel): rows of 32 PCM samples, segments of
-// at least 16 rows, at most 32 segments per channel (the lanes of one warp), none for short calls
-// (a warm-up of 32 rows would cost more than it saves).
+// at least 32 rows (so the warm-up rows, which are read a second time, stay below the segment's
+// own), at most 32 segments per channel (the lanes of one warp), none for short calls.
 void dc_segments(const sdr_engine *e, uint32_t n_rows, uint32_t *seg_count, uint32_t *seg_rows) {
   uint32_t S = 1;
   if (e->dc_seg_count) {
     S = e->dc_seg_count;
   } else if (n_rows >= 64) {
-    while (S < 16 && n_rows / (2 * S) >= 16) S *= 2;
+    while (S < 32 && n_rows / (2 * S) >= 32) S *= 2;
   }
   while (S > 1 && (n_rows + S - 1) / S * (S - 1) >= n_rows) S /= 2;  // no empty segments in the middle
   *seg_count = S;
@@ -317,7 +322,7 @@ int launch_dc_block(sdr_engine *e, int kind, uint32_t n_samples) {
   p.state = e->d_state[kind];
   p.state_stride = (uint32_t)state_bytes(kind);
   p.scale = e->d_scale[kind];
-  p.pcm = e->d_pcm;
+  p.pcm = e->pcm_of(e->seq);
   p.pcm_stride = e->pcm_stride;
   p.aux = (uint32_t)nreg * 256;  // byte offset of the IIR tail in the state blob (after both carry buffers)
   p.scratch = e->d_scratch[kind][par];
@@ -327,7 +332,7 @@ int launch_dc_block(sdr_engine *e, int kind, uint32_t n_samples) {
   p.warm_rows = e->dc_warm_rows;
   p.counters = e->d_counters;
   const uint64_t lanes = (uint64_t)n_list * p.seg_count;
-  dc_block_kernel<<<(uint32_t)((lanes + 127) / 128), 128, 0, e->rec_stream>>>(p);
+  dc_block_kernel<<<(uint32_t)((lanes + 31) / 32), 32, 0, e->rec_stream>>>(p);
   SDR_CK(e, cudaGetLastError());
   e->launches++;
   return SDR_OK;
@@ -422,7 +427,7 @@ int launch_fm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_
   p.state_stride = (uint32_t)FmTile::STATE_BYTES;
   p.scale = e->d_scale[kind];
   p.lsb = e->d_lsb;
-  p.pcm = e->d_pcm;
+  p.pcm = e->pcm_of(e->seq);
   p.pcm_stride = e->pcm_stride;
   p.lut = e->d_lut_fm;
   p.aux = (uint32_t)n_warps;
@@ -472,7 +477,7 @@ int launch_wbfm_tile2(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint
   p.state_stride = (uint32_t)WbTile::STATE_BYTES;
   p.scale = e->d_scale[kind];
   p.lsb = e->d_lsb;
-  p.pcm = e->d_pcm;
+  p.pcm = e->pcm_of(e->seq);
   p.pcm_stride = e->pcm_stride;
   p.lut = e->d_lut_wbfm_half;
   static const int rec_env = getenv("SDR_WB_REC") ? atoi(getenv("SDR_WB_REC")) : -1;  // tuning override
@@ -517,7 +522,7 @@ int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint3
   p.state_stride = (uint32_t)T::STATE_BYTES;
   p.scale = e->d_scale[kind];
   p.lsb = e->d_lsb;
-  p.pcm = e->d_pcm;
+  p.pcm = e->pcm_of(e->seq);
   p.pcm_stride = e->pcm_stride;
   p.lut = e->d_lut_wbfm;
   // workers allowed on the recurrence warp's scheduler (tunable: SDR_WB_S3)
@@ -755,8 +760,10 @@ int sdr_engine_create(uint32_t n_channels, int device, uint64_t max_bytes_per_ch
   }
   SDR_CK_CREATE(cudaMalloc(&e->d_lsb, n_channels));
   e->pcm_stride = (max_bytes_per_channel / 64 + 7) & ~7ull;  // rows stay 16-byte aligned
-  SDR_CK_CREATE(cudaMalloc(&e->d_pcm, (size_t)n_channels * e->pcm_stride * 2));
-  SDR_CK_CREATE(cudaMemsetAsync(e->d_pcm, 0, (size_t)n_channels * e->pcm_stride * 2, e->stream));
+  for (int i = 0; i < 2; ++i) {
+    SDR_CK_CREATE(cudaMalloc(&e->d_pcm2[i], (size_t)n_channels * e->pcm_stride * 2));
+    SDR_CK_CREATE(cudaMemsetAsync(e->d_pcm2[i], 0, (size_t)n_channels * e->pcm_stride * 2, e->stream));
+  }
 
   // atan2 tables, built with the host libm exactly as the reference builds its
   // WBFM table (WbFmDemodulator.cc:159-170). NBFM calls atan2 per sample on
@@ -844,7 +851,8 @@ int sdr_engine_destroy(sdr_engine *e) {
   cudaFree(e->d_trace);
   cudaFree(e->d_counters);
   cudaFree(e->d_iq);
-  cudaFree(e->d_pcm);
+  cudaFree(e->d_pcm2[0]);
+  cudaFree(e->d_pcm2[1]);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
   return SDR_OK;
@@ -953,10 +961,11 @@ int sdr_debug_set_dc_shape(sdr_engine *e, uint32_t seg_count, uint32_t warm_rows
   return SDR_OK;
 }
 
-// how the AM/SSB FIR kernel fetches full tiles: 1 = TMA (default), 0 = cp.async (for A/B runs)
-int sdr_debug_set_tile_loader(sdr_engine *e, int tma) {
-  if (!e) return SDR_E_ARG;
-  e->use_tma = tma != 0;
+// how the AM/SSB FIR kernel fetches full tiles: 0 = cp.async with two slot buffers per warp,
+// 2 / 3 / 4 = TMA with that many (1 = the default TMA depth); for A/B runs
+int sdr_debug_set_tile_loader(sdr_engine *e, int loader) {
+  if (!e || loader < 0 || loader > 4) return SDR_E_ARG;
+  e->tile_loader = loader == 1 ? 4 : loader;
   return SDR_OK;
 }
 
@@ -1046,7 +1055,7 @@ int sdr_get_pcm(sdr_engine *e, int16_t *pcm, uint32_t *counts) {
     if (rc) return rc;
   }
   if (pcm && e->last_samples)
-    SDR_CK(e, cudaMemcpy2DAsync(pcm, (size_t)e->last_samples * 2, e->d_pcm, e->pcm_stride * 2,
+    SDR_CK(e, cudaMemcpy2DAsync(pcm, (size_t)e->last_samples * 2, e->pcm_of(e->seq - 1), e->pcm_stride * 2,
                                 (size_t)e->last_samples * 2, e->n, cudaMemcpyDeviceToHost, e->stream));
   std::vector<uint8_t> gate;
   if (counts && e->last_gated && e->seq > 0) {
@@ -1062,7 +1071,7 @@ int sdr_get_pcm(sdr_engine *e, int16_t *pcm, uint32_t *counts) {
 
 int sdr_pcm_device(sdr_engine *e, int16_t **pcm, uint64_t *stride) {
   if (!e) return SDR_E_ARG;
-  if (pcm) *pcm = e->d_pcm;
+  if (pcm) *pcm = e->pcm_of(e->seq ? e->seq - 1 : 0);  // the buffer of the last accept
   if (stride) *stride = e->pcm_stride;
   return SDR_OK;
 }
@@ -1160,6 +1169,8 @@ struct sdr_ingest {
     int16_t *h_pcm = nullptr;
     uint8_t *h_gate = nullptr;
     cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_done = nullptr;
+    bool own_host = true;        // false: h_iq belongs to a bank's shared tick array
+    int16_t *pcm_dst = nullptr;  // where this tick's PCM was copied to (h_pcm, or a bank's shared array)
     uint32_t timestamp = 0;
     uint64_t bytes = 0;
     bool gated = false, queued = false;
@@ -1170,7 +1181,7 @@ struct sdr_ingest {
   uint64_t block_bytes = 0;
   std::vector<Slot> slot;
   uint32_t head = 0, tail = 0, in_flight = 0;
-  int prev = -1;             // slot whose PCM read-back the next demodulation has to wait for
+  int prev = -1, prev2 = -1; // the slots of the last two ticks (see sdr_ingest_commit)
   cudaStream_t h2d = nullptr, d2h = nullptr;
   uint32_t last_timestamp = 0, short_blocks = 0;
   uint64_t ticks = 0;
@@ -1183,7 +1194,7 @@ int sdr_ingest_destroy(sdr_ingest *q) {
   cudaStreamSynchronize(q->e->stream);
   if (q->d2h) cudaStreamSynchronize(q->d2h);
   for (auto &s : q->slot) {
-    cudaFreeHost(s.h_iq);
+    if (s.own_host) cudaFreeHost(s.h_iq);
     cudaFreeHost(s.h_pcm);
     cudaFreeHost(s.h_gate);
     cudaFree(s.d_iq);
@@ -1197,7 +1208,25 @@ int sdr_ingest_destroy(sdr_ingest *q) {
   return SDR_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// host_iq: null, or n_slots pointers to pinned [n_channels][block_bytes] arrays the slots use instead
+// of their own (a bank's shared tick arrays; then no per-slot PCM array is allocated either)
+int ingest_create(sdr_engine *e, uint32_t n_slots, uint64_t block_bytes, uint8_t *const *host_iq, sdr_ingest **out);
+int ingest_commit(sdr_ingest *q, uint32_t timestamp, uint64_t bytes, uint32_t flags, int16_t *pcm_dst);
+}  // namespace
+
+extern "C" {
+
 int sdr_ingest_create(sdr_engine *e, uint32_t n_slots, uint64_t block_bytes, sdr_ingest **out) {
+  return ingest_create(e, n_slots, block_bytes, nullptr, out);
+}
+
+}  // extern "C"
+
+namespace {
+int ingest_create(sdr_engine *e, uint32_t n_slots, uint64_t block_bytes, uint8_t *const *host_iq, sdr_ingest **out) {
   if (!e || !out || n_slots < 2 || n_slots > 64) return SDR_E_ARG;
   if (block_bytes == 0 || block_bytes % 64 || block_bytes > e->max_bytes)
     return fail(e, SDR_E_ARG, "ingest block_bytes must be a multiple of 64 within max_bytes_per_channel");
@@ -1219,9 +1248,15 @@ int sdr_ingest_create(sdr_engine *e, uint32_t n_slots, uint64_t block_bytes, sdr
   SDR_CK_Q(cudaStreamCreateWithFlags(&q->h2d, cudaStreamNonBlocking));
   SDR_CK_Q(cudaStreamCreateWithFlags(&q->d2h, cudaStreamNonBlocking));
   const size_t iq_bytes = (size_t)e->n * block_bytes, pcm_bytes = (size_t)e->n * (block_bytes / 64) * 2;
-  for (auto &s : q->slot) {
-    SDR_CK_Q(cudaHostAlloc(&s.h_iq, iq_bytes, cudaHostAllocDefault));
-    SDR_CK_Q(cudaHostAlloc(&s.h_pcm, pcm_bytes, cudaHostAllocDefault));
+  for (uint32_t i = 0; i < n_slots; ++i) {
+    sdr_ingest::Slot &s = q->slot[i];
+    if (host_iq) {
+      s.h_iq = host_iq[i];
+      s.own_host = false;
+    } else {
+      SDR_CK_Q(cudaHostAlloc(&s.h_iq, iq_bytes, cudaHostAllocDefault));
+      SDR_CK_Q(cudaHostAlloc(&s.h_pcm, pcm_bytes, cudaHostAllocDefault));
+    }
     SDR_CK_Q(cudaHostAlloc(&s.h_gate, e->n, cudaHostAllocDefault));
     SDR_CK_Q(cudaMalloc(&s.d_iq, iq_bytes));
     SDR_CK_Q(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
@@ -1233,6 +1268,9 @@ int sdr_ingest_create(sdr_engine *e, uint32_t n_slots, uint64_t block_bytes, sdr
   *out = q;
   return SDR_OK;
 }
+}  // namespace
+
+extern "C" {
 
 int sdr_ingest_acquire(sdr_ingest *q, void **iq, uint64_t *channel_stride) {
   if (!q || !iq) return SDR_E_ARG;
@@ -1244,6 +1282,13 @@ int sdr_ingest_acquire(sdr_ingest *q, void **iq, uint64_t *channel_stride) {
 }
 
 int sdr_ingest_commit(sdr_ingest *q, uint32_t timestamp, uint64_t bytes, uint32_t flags) {
+  return ingest_commit(q, timestamp, bytes, flags, nullptr);
+}
+
+}  // extern "C"
+
+namespace {
+int ingest_commit(sdr_ingest *q, uint32_t timestamp, uint64_t bytes, uint32_t flags, int16_t *pcm_dst) {
   if (!q) return SDR_E_ARG;
   sdr_engine *e = q->e;
   sdr_ingest::Slot &s = q->slot[q->head];
@@ -1261,15 +1306,17 @@ int sdr_ingest_commit(sdr_ingest *q, uint32_t timestamp, uint64_t bytes, uint32_
                                 cudaMemcpyHostToDevice, q->h2d));
   SDR_CK(e, cudaEventRecord(s.ev_h2d, q->h2d));
   SDR_CK(e, cudaStreamWaitEvent(e->stream, s.ev_h2d, 0));
-  // the engine has one PCM buffer: wait until the previous tick's was read back
-  if (q->prev >= 0) SDR_CK(e, cudaStreamWaitEvent(e->stream, q->slot[q->prev].ev_done, 0));
+  // the engine alternates between two PCM buffers: this tick writes the one the tick before the
+  // previous one used, so that tick's read-back must be over (the previous tick's may still run)
+  if (q->prev2 >= 0) SDR_CK(e, cudaStreamWaitEvent(e->stream, q->slot[q->prev2].ev_done, 0));
   int rc = sdr_accept_iq(e, s.d_iq, bytes, q->block_bytes, SDR_IQ_DEVICE | (flags & SDR_IQ_S8_ROTATED));
   if (rc) return rc;
   if ((rc = join_streams(e))) return rc;
   SDR_CK(e, cudaEventRecord(s.ev_comp, e->stream));
   SDR_CK(e, cudaStreamWaitEvent(q->d2h, s.ev_comp, 0));
   const size_t row = (size_t)(bytes / 64) * 2;
-  SDR_CK(e, cudaMemcpy2DAsync(s.h_pcm, row, e->d_pcm, e->pcm_stride * 2, row, e->n, cudaMemcpyDeviceToHost, q->d2h));
+  s.pcm_dst = pcm_dst ? pcm_dst : s.h_pcm;
+  SDR_CK(e, cudaMemcpy2DAsync(s.pcm_dst, row, e->pcm_of(e->seq - 1), e->pcm_stride * 2, row, e->n, cudaMemcpyDeviceToHost, q->d2h));
   s.gated = e->last_gated;
   if (s.gated)
     SDR_CK(e, cudaMemcpyAsync(s.h_gate, e->d_allowed[(e->seq + (uint64_t)e->ring - 1) % (uint64_t)e->ring], e->n, cudaMemcpyDeviceToHost, q->d2h));
@@ -1278,12 +1325,16 @@ int sdr_ingest_commit(sdr_ingest *q, uint32_t timestamp, uint64_t bytes, uint32_
   s.bytes = bytes;
   s.mode = e->mode;
   s.queued = true;
+  q->prev2 = q->prev;
   q->prev = (int)q->head;
   q->head = (q->head + 1) % (uint32_t)q->slot.size();
   q->in_flight++;
   q->ticks++;
   return SDR_OK;
 }
+}  // namespace
+
+extern "C" {
 
 int sdr_ingest_accept(sdr_ingest *q, uint32_t timestamp, const void *iq, uint64_t bytes, uint64_t channel_stride,
                       uint32_t flags) {
@@ -1310,7 +1361,7 @@ int sdr_ingest_retire(sdr_ingest *q, uint32_t *timestamp, const int16_t **pcm, u
   for (uint32_t ch = 0; ch < e->n; ++ch)
     s.counts[ch] = (s.mode[ch] == SDR_MODE_NONE || (s.gated && !s.h_gate[ch])) ? 0 : samples;
   if (timestamp) *timestamp = s.timestamp;
-  if (pcm) *pcm = s.h_pcm;
+  if (pcm) *pcm = s.pcm_dst;
   if (samples_per_row) *samples_per_row = samples;
   if (counts) *counts = s.counts.data();
   s.queued = false;
@@ -1326,6 +1377,215 @@ int sdr_ingest_stats(const sdr_ingest *q, uint32_t *last_timestamp, uint32_t *sh
   if (short_block_count) *short_block_count = q->short_blocks;
   if (ticks) *ticks = q->ticks;
   if (in_flight) *in_flight = q->in_flight;
+  return SDR_OK;
+}
+
+
+// ---------------------------------------------------------------------------
+// Multi-device bank: n_channels radios over the GPUs of one box.
+// Channels are independent, so device g simply owns the contiguous range
+// [n g / G, n (g + 1) / G): one engine and one ingest ring per device, no exchange between
+// devices. What the devices share is host memory: ONE pinned tick array [n_channels][block_bytes]
+// per slot that every device host->device-copies its slab out of, and ONE pinned PCM array
+// [n_channels][bytes / 64] per slot that every device copies its slab into -- the "gather" is
+// where the copies land. One host thread drives all devices: every call below only queues work.
+// ---------------------------------------------------------------------------
+struct sdr_bank {
+  uint32_t n = 0;
+  uint64_t block_bytes = 0;
+  std::vector<int> device;
+  std::vector<uint32_t> first;  // [n_devices + 1]
+  std::vector<sdr_engine *> eng;
+  std::vector<sdr_ingest *> ing;
+  struct Slot {
+    uint8_t *h_iq = nullptr;
+    int16_t *h_pcm = nullptr;
+    std::vector<uint32_t> counts;
+    bool queued = false;
+  };
+  std::vector<Slot> slot;
+  uint32_t head = 0, tail = 0;
+  std::string err;
+};
+
+static thread_local std::string g_bank_error;
+static int bank_fail(sdr_bank *b, int code, const std::string &what) {
+  if (b) b->err = what;
+  else g_bank_error = what;
+  return code;
+}
+// error of shard i's engine, with the shard named
+static int bank_fail_shard(sdr_bank *b, int code, uint32_t i) {
+  char head[64];
+  snprintf(head, sizeof head, "device %d (shard %u): ", b->device[i], i);
+  return bank_fail(b, code, std::string(head) + sdr_last_error(b->eng[i]));
+}
+
+const char *sdr_bank_last_error(const sdr_bank *b) { return b ? b->err.c_str() : g_bank_error.c_str(); }
+
+int sdr_bank_destroy(sdr_bank *b) {
+  if (!b) return SDR_E_ARG;
+  for (size_t i = 0; i < b->eng.size(); ++i) {
+    if (i < b->ing.size() && b->ing[i]) sdr_ingest_destroy(b->ing[i]);
+    if (b->eng[i]) sdr_engine_destroy(b->eng[i]);
+  }
+  for (auto &s : b->slot) {
+    cudaFreeHost(s.h_iq);
+    cudaFreeHost(s.h_pcm);
+  }
+  delete b;
+  return SDR_OK;
+}
+
+int sdr_bank_create(uint32_t n_channels, const int *devices, uint32_t n_devices, uint64_t block_bytes,
+                    uint32_t n_slots, sdr_bank **out) {
+  if (!out) return SDR_E_ARG;
+  *out = nullptr;
+  if (!devices || n_devices == 0 || n_channels < n_devices || n_slots < 2 || n_slots > 64 || block_bytes == 0 ||
+      block_bytes % 64)
+    return bank_fail(nullptr, SDR_E_ARG, "sdr_bank_create: need 1..n_channels devices, 2..64 slots, block_bytes a multiple of 64");
+  for (uint32_t i = 0; i < n_devices; ++i)
+    for (uint32_t j = 0; j < i; ++j)
+      if (devices[i] == devices[j]) return bank_fail(nullptr, SDR_E_ARG, "sdr_bank_create: a device is listed twice");
+  sdr_bank *b = new (std::nothrow) sdr_bank();
+  if (!b) return SDR_E_NOMEM;
+  b->n = n_channels;
+  b->block_bytes = block_bytes;
+  b->device.assign(devices, devices + n_devices);
+  b->first.resize(n_devices + 1);
+  for (uint32_t i = 0; i <= n_devices; ++i) b->first[i] = (uint32_t)((uint64_t)n_channels * i / n_devices);
+  b->eng.assign(n_devices, nullptr);
+  b->ing.assign(n_devices, nullptr);
+  b->slot.resize(n_slots);
+  // the shared tick and PCM arrays: pinned for every device's context
+  for (auto &s : b->slot) {
+    cudaError_t ce = cudaHostAlloc(&s.h_iq, (size_t)n_channels * block_bytes, cudaHostAllocPortable);
+    if (ce == cudaSuccess) ce = cudaHostAlloc(&s.h_pcm, (size_t)n_channels * (block_bytes / 64) * 2, cudaHostAllocPortable);
+    if (ce != cudaSuccess) {
+      bank_fail(nullptr, SDR_E_NOMEM, std::string("sdr_bank_create: pinned host memory: ") + cudaGetErrorString(ce));
+      sdr_bank_destroy(b);
+      return ce == cudaErrorMemoryAllocation ? SDR_E_NOMEM : SDR_E_CUDA;
+    }
+    s.counts.assign(n_channels, 0);
+  }
+  for (uint32_t i = 0; i < n_devices; ++i) {
+    const uint32_t n_i = b->first[i + 1] - b->first[i];
+    int rc = sdr_engine_create(n_i, devices[i], block_bytes, &b->eng[i]);
+    if (rc) {
+      bank_fail(nullptr, rc, std::string("sdr_bank_create: ") + sdr_last_error(nullptr));
+      sdr_bank_destroy(b);
+      return rc;
+    }
+    std::vector<uint8_t *> slabs(n_slots);
+    for (uint32_t k = 0; k < n_slots; ++k) slabs[k] = b->slot[k].h_iq + (size_t)b->first[i] * block_bytes;
+    rc = ingest_create(b->eng[i], n_slots, block_bytes, slabs.data(), &b->ing[i]);
+    if (rc) {
+      bank_fail(nullptr, rc, std::string("sdr_bank_create: ") + sdr_last_error(b->eng[i]));
+      sdr_bank_destroy(b);
+      return rc;
+    }
+  }
+  *out = b;
+  return SDR_OK;
+}
+
+uint32_t sdr_bank_device_count(const sdr_bank *b) { return b ? (uint32_t)b->device.size() : 0; }
+
+int sdr_bank_shard(const sdr_bank *b, uint32_t i, int *device, uint32_t *first_channel, uint32_t *n_channels,
+                   sdr_engine **engine) {
+  if (!b || i >= b->device.size()) return SDR_E_ARG;
+  if (device) *device = b->device[i];
+  if (first_channel) *first_channel = b->first[i];
+  if (n_channels) *n_channels = b->first[i + 1] - b->first[i];
+  if (engine) *engine = b->eng[i];
+  return SDR_OK;
+}
+
+// shard of a channel: first[] is ascending
+static uint32_t bank_shard_of(const sdr_bank *b, uint32_t ch) {
+  return (uint32_t)(std::upper_bound(b->first.begin(), b->first.end(), ch) - b->first.begin()) - 1;
+}
+
+int sdr_bank_set_mode(sdr_bank *b, uint32_t channel, int mode) {
+  if (!b || channel >= b->n) return SDR_E_ARG;
+  const uint32_t i = bank_shard_of(b, channel);
+  const int rc = sdr_set_mode(b->eng[i], channel - b->first[i], mode);
+  return rc ? bank_fail(b, rc, "sdr_bank_set_mode: bad mode") : SDR_OK;
+}
+
+int sdr_bank_set_modes(sdr_bank *b, const uint8_t *modes) {
+  if (!b || !modes) return SDR_E_ARG;
+  for (size_t i = 0; i < b->eng.size(); ++i) {
+    const int rc = sdr_set_modes(b->eng[i], modes + b->first[i]);
+    if (rc) return bank_fail(b, rc, "sdr_bank_set_modes: bad mode");
+  }
+  return SDR_OK;
+}
+
+int sdr_bank_set_gain(sdr_bank *b, uint32_t channel, int kind, float gain) {
+  if (!b || channel >= b->n) return SDR_E_ARG;
+  const uint32_t i = bank_shard_of(b, channel);
+  const int rc = sdr_set_gain(b->eng[i], channel - b->first[i], kind, gain);
+  return rc ? bank_fail(b, rc, "sdr_bank_set_gain: bad kind") : SDR_OK;
+}
+
+int sdr_bank_reset(sdr_bank *b, uint32_t channel, int kind) {
+  if (!b || channel >= b->n) return SDR_E_ARG;
+  const uint32_t i = bank_shard_of(b, channel);
+  const int rc = sdr_reset(b->eng[i], channel - b->first[i], kind);
+  return rc ? bank_fail_shard(b, rc, i) : SDR_OK;
+}
+
+int sdr_bank_set_squelch_threshold(sdr_bank *b, uint32_t channel, int32_t threshold_dbfs) {
+  if (!b || channel >= b->n) return SDR_E_ARG;
+  const uint32_t i = bank_shard_of(b, channel);
+  return sdr_set_squelch_threshold(b->eng[i], channel - b->first[i], threshold_dbfs);
+}
+
+int sdr_bank_acquire(sdr_bank *b, void **iq, uint64_t *channel_stride) {
+  if (!b || !iq) return SDR_E_ARG;
+  sdr_bank::Slot &s = b->slot[b->head];
+  if (s.queued) return bank_fail(b, SDR_E_FULL, "bank ring full: retire a tick first");
+  *iq = s.h_iq;
+  if (channel_stride) *channel_stride = b->block_bytes;
+  return SDR_OK;
+}
+
+int sdr_bank_commit(sdr_bank *b, uint32_t timestamp, uint64_t bytes, uint32_t flags) {
+  if (!b) return SDR_E_ARG;
+  sdr_bank::Slot &s = b->slot[b->head];
+  if (s.queued) return bank_fail(b, SDR_E_FULL, "bank ring full: retire a tick first");
+  if (bytes == 0 || bytes % 64) return bank_fail(b, SDR_E_ARG, "bytes_per_channel must be a positive multiple of 64");
+  const uint64_t take = bytes > b->block_bytes ? b->block_bytes : bytes;  // clipped like DataConsumer.cc:232-246
+  for (size_t i = 0; i < b->eng.size(); ++i) {
+    // this device's slab of the shared PCM array, rows take / 64 samples apart
+    int16_t *dst = s.h_pcm + (size_t)b->first[i] * (take / 64);
+    const int rc = ingest_commit(b->ing[i], timestamp, bytes, flags, dst);
+    if (rc) return bank_fail_shard(b, rc, (uint32_t)i);
+  }
+  s.queued = true;
+  b->head = (b->head + 1) % (uint32_t)b->slot.size();
+  return SDR_OK;
+}
+
+int sdr_bank_retire(sdr_bank *b, uint32_t *timestamp, const int16_t **pcm, uint32_t *samples_per_row,
+                    const uint32_t **counts) {
+  if (!b) return SDR_E_ARG;
+  sdr_bank::Slot &s = b->slot[b->tail];
+  if (!s.queued) return bank_fail(b, SDR_E_EMPTY, "bank ring empty: nothing to retire");
+  uint32_t ts = 0, samples = 0;
+  for (size_t i = 0; i < b->eng.size(); ++i) {
+    const uint32_t *c = nullptr;
+    const int rc = sdr_ingest_retire(b->ing[i], &ts, nullptr, &samples, &c);
+    if (rc) return bank_fail_shard(b, rc, (uint32_t)i);
+    memcpy(s.counts.data() + b->first[i], c, (size_t)(b->first[i + 1] - b->first[i]) * 4);
+  }
+  if (timestamp) *timestamp = ts;
+  if (pcm) *pcm = s.h_pcm;
+  if (samples_per_row) *samples_per_row = samples;
+  if (counts) *counts = s.counts.data();
+  s.queued = false;
+  b->tail = (b->tail + 1) % (uint32_t)b->slot.size();
   return SDR_OK;
 }
 

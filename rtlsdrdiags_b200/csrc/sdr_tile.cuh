@@ -159,11 +159,11 @@ __device__ __forceinline__ void tma_load_tile(uint32_t dst, const CUtensorMap *m
       : "memory");
 }
 struct TmaIo {
-  uint32_t slot;    // shared address of slot buffer 0 (1024-byte aligned); buffer 1 follows at + TILE_BYTES
-  uint32_t bar;     // shared address of the two mbarriers (8 bytes each)
+  uint32_t slot;    // shared address of slot buffer 0 (1024-byte aligned); buffer b follows at + b * TILE_BYTES
+  uint32_t bar;     // shared address of the buffers' mbarriers (8 bytes each)
   uint32_t rd[4];   // shared addresses of the lane's four 16-byte chunks in buffer 0
   uint32_t phase;   // bit b = parity the next wait on buffer b's barrier expects
-  __device__ __forceinline__ void init(const char *slots, uint64_t *bars, int lane) {
+  __device__ __forceinline__ void init(const char *slots, uint64_t *bars, int lane, int n_buffers) {
     slot = (uint32_t)__cvta_generic_to_shared(slots);
     bar = (uint32_t)__cvta_generic_to_shared(bars);
     const uint32_t r = (uint32_t)lane >> 1, c0 = 4u * ((uint32_t)lane & 1u);
@@ -171,8 +171,7 @@ struct TmaIo {
     for (uint32_t j = 0; j < 4; ++j) rd[j] = slot + 128u * r + 16u * ((c0 + j) ^ (r & 7u));
     phase = 0;
     if (lane == 0) {
-      mbar_init(bar, 1);
-      mbar_init(bar + 8, 1);
+      for (int b = 0; b < n_buffers; ++b) mbar_init(bar + 8 * b, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -265,12 +264,14 @@ struct AmSsbTile {
   }
 
   // One tile of one channel. `w` = the lane's 64 input bytes. Returns what the
-  // recurrence warp consumes for this lane's PCM sample: the numerator of the DC-removal
-  // filter, fl(x[n] - x[n-1]) (float bits), where x is the AM magnitude estimate or the
-  // SSB phased sum. Updates the carry to this tile's registers rolled by r valid lanes.
+  // recurrence kernel consumes for this lane's PCM sample: the numerator of the DC-removal
+  // filter, fl(x[n] - x[n-1]), where x is the AM magnitude estimate or the SSB phased sum. Both
+  // are small integers (AM |x| <= 271, SSB <= 553 for 8-bit input: stage gains 113/128, 122/114,
+  // 181/122, Hilbert 372/181), so the float difference is exact and travels as an int16.
+  // Updates the carry to this tile's registers rolled by r valid lanes.
   // FULL_TILE: r == 32 is known at compile time (the hot loop); otherwise 1 <= r <= 32.
   template <bool FULL_TILE = false>
-  __device__ __forceinline__ static uint32_t tile(const uint32_t (&w)[16], int fmt, bool lsb, AmSsbCarry<SSB> &pv, int lane, int r,
+  __device__ __forceinline__ static int tile(const uint32_t (&w)[16], int fmt, bool lsb, AmSsbCarry<SSB> &pv, int lane, int r,
                                                   const PrevMasks &pm) {
     AmSsbCarry<SSB> cu;
     uint32_t a[8], b[8];
@@ -338,7 +339,7 @@ struct AmSsbTile {
       cu.dem = i2f(lsb ? i_delayed - q_shifted : i_delayed + q_shifted);
     }
     // numerator of the DC-removal IIR, b = {1, -1}: fl(1*x[n] + (-1)*x[n-1]) (IirFilter.cc:164)
-    const uint32_t out = f2u(fadd(cu.dem, fmul(-1.0f, shfl_prev(cu.dem, pv.dem, 1, lane))));
+    const int out = f2i_rz(fadd(cu.dem, fmul(-1.0f, shfl_prev(cu.dem, pv.dem, 1, lane))));
 
     // the last 32 lanes of the stream become the next tile's "previous" registers
     if (FULL_TILE || r == 32) {
@@ -393,13 +394,14 @@ struct AmSsbTile {
 // next call's FIR kernel.
 // TMA = true: full tiles arrive by cp.async.bulk.tensor (TmaIo), one instruction of one lane per
 // tile; false: by four cp.async per lane (TileIo). A partial last tile takes cp.async either way.
-template <bool SSB, bool TMA>
+// NST = slot buffers per warp: NST - 1 tiles are in flight while one is computed.
+template <bool SSB, bool TMA, int NST>
 __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant__ LaunchParams p,
                                                            const __grid_constant__ CUtensorMap tmap) {
   using T = AmSsbTile<SSB>;
   constexpr uint32_t WARMUP = T::WARMUP_TILES;
   extern __shared__ __align__(1024) uint4 smem_raw[];
-  __shared__ uint64_t s_bar[4][2];
+  __shared__ uint64_t s_bar[4][NST];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n_warps = p.aux;  // worker warps of the whole grid
   const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -412,15 +414,14 @@ __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant
   uint64_t g0 = total * gw / n_warps;
   const uint64_t g1 = total * (gw + 1) / n_warps;
 
-  char *slots = reinterpret_cast<char *>(smem_raw) + warp * 2 * TILE_BYTES;
+  char *slots = reinterpret_cast<char *>(smem_raw) + warp * NST * TILE_BYTES;
   TileIo io;
   TmaIo tio;
-  if constexpr (TMA) tio.init(slots, s_bar[warp], lane);
+  if constexpr (TMA) tio.init(slots, s_bar[warp], lane, NST);
   else io.init(slots, lane);
   PrevMasks pm;
   pm.init(lane);
   const int fmt = p.fmt;
-  const uint64_t sp_step = (uint64_t)p.n_list * 32;
 
   while (g0 < g1) {
     // the piece of one channel: tiles [t0, t1) of list entry li
@@ -452,42 +453,43 @@ __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant
     // multiple of 32 samples) takes the generic path once.
     const uint32_t partial = (t1 == n_tiles && (p.n_samples & (TILE - 1))) ? 1u : 0u;
     const uint32_t tf = t1 - partial;
-    const uint8_t *g = src + (uint64_t)tw * TILE_BYTES + 16 * lane;  // the lane's chunk 0 of the tile to fetch next
-    // the scratch row of tile tw; rows of warm-up tiles are walked over but not written
-    float *sp = p.scratch + ((uint64_t)tw * p.n_list + li) * 32 + lane;
-    uint32_t buf = 0;  // 0 or 1
-    __syncwarp();  // the previous piece's last reads of the slot buffers are done
-    if (tw < tf) {
-      if constexpr (TMA) { if (lane == 0) tio.issue(0, &tmap, tw, ch); }
-      else io.fill_full(0, g);
-    } else {
-      tile_fill(slots, g - 16 * lane, lane, (int)(p.n_samples - tw * TILE) >> 3);
-    }
-    cp_async_commit();
-    for (uint32_t t = tw; t < tf; ++t) {
-      g += TILE_BYTES;
-      if (t + 1 < tf) {
-        if constexpr (TMA) { if (lane == 0) tio.issue(buf ^ 1u, &tmap, t + 1, ch); }
-        else io.fill_full((buf ^ 1u) * TILE_BYTES, g);
-      } else if (partial) {
-        tile_fill(slots + (buf ^ 1u) * TILE_BYTES, g - 16 * lane, lane, (int)(p.n_samples - (t + 1) * TILE) >> 3);
+    const uint8_t *g = src + 16 * lane;  // the lane's chunk 0 of tile 0
+    // the scratch row of tile tw ([list entry][row][32] int16); rows of warm-up tiles are walked
+    // over but not written
+    int16_t *sp = p.scratch + ((uint64_t)li * n_tiles + tw) * 32 + lane;
+    // tile `tt` goes to slot buffer `b`: TMA or cp.async for a full tile, cp.async for the partial one
+    auto fetch = [&](uint32_t tt, uint32_t b) {
+      if (tt < tf) {
+        if constexpr (TMA) { if (lane == 0) tio.issue(b, &tmap, tt, ch); }
+        else io.fill_full(b * TILE_BYTES, g + (uint64_t)tt * TILE_BYTES);
+      } else if (tt == tf && partial) {
+        tile_fill(slots + b * TILE_BYTES, src + (uint64_t)tt * TILE_BYTES, lane, (int)(p.n_samples - tt * TILE) >> 3);
       }
+    };
+    __syncwarp();  // the previous piece's last reads of the slot buffers are done
+#pragma unroll
+    for (uint32_t k = 0; k < NST - 1; ++k) {
+      fetch(tw + k, k);
+      cp_async_commit();
+    }
+    uint32_t buf = 0;  // slot buffer of the tile being computed
+    for (uint32_t t = tw; t < tf; ++t) {
+      fetch(t + NST - 1, buf == 0 ? NST - 1 : buf - 1);  // where tile t - 1 was; every lane has read it
+      cp_async_commit();
       uint32_t w[16];
       if constexpr (TMA) {
-        if (partial) cp_async_commit();
         tio.wait(buf);
         tio.read(buf, w);
       } else {
-        cp_async_commit();
-        cp_async_wait<1>();
+        cp_async_wait<NST - 1>();
         __syncwarp();
         io.read(buf * TILE_BYTES, w);
       }
-      __syncwarp();  // this buffer may be refilled (tile t+2) once every lane has read it
-      const uint32_t d = T::template tile<true>(w, fmt, lsb, pv, lane, 32, pm);
-      if (t >= t0) *sp = u2f(d);
-      sp += sp_step;
-      buf ^= 1u;
+      __syncwarp();  // this buffer may be refilled once every lane has read it
+      const int d = T::template tile<true>(w, fmt, lsb, pv, lane, 32, pm);
+      if (t >= t0) *sp = (int16_t)d;
+      sp += 32;
+      buf = buf + 1 == NST ? 0 : buf + 1;
     }
     if (partial) {
       cp_async_wait<0>();
@@ -495,8 +497,8 @@ __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant
       uint32_t w[16];
       tile_read(slots + buf * TILE_BYTES, lane, w);
       const int r = (int)(p.n_samples - tf * TILE) >> 5;
-      const uint32_t d = T::template tile<false>(w, fmt, lsb, pv, lane, r, pm);
-      if (lane < r) *sp = u2f(d);  // tf >= t0 always
+      const int d = T::template tile<false>(w, fmt, lsb, pv, lane, r, pm);
+      if (lane < r) *sp = (int16_t)d;  // tf >= t0 always
     }
     // Only the piece that ends the block leaves the channel's state: into the carry buffer
     // that is not current, then it publishes the switch. Pieces that read the carry later in
@@ -517,8 +519,8 @@ __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant
 // The recurrence is strictly sequential and bit-exactness forbids re-association, but it
 // CONTRACTS: two trajectories fed the same numerators from different start states differ by
 // 0.95^n times the initial difference until the difference drops below the rounding step, and a
-// few steps later they are bit-identical for good (measured on 200,000 random starts per input
-// class: median 360-500 steps, maximum 807; tools/iir_merge.py). So a call's rows (a row = 32 PCM
+// few steps later they are bit-identical for good (200,000 random starts per input class: median
+// 360-500 steps, never later than 807; tools/iir_merge.py). So a call's rows (a row = 32 PCM
 // samples = one FIR tile) are cut into up to 32 SEGMENTS per channel and every (channel, segment)
 // pair gets a lane:
 //   * segment 0 starts from the carried y[n-1];
@@ -530,28 +532,36 @@ __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant
 //     (the trajectories had not merged yet; or never do: a y stuck on a denormal under
 //     all-zero numerators): the first such segment of the channel is redone from the true state,
 //     then the comparison is repeated -- the serial order, paid only where it is needed.
-// The chain per call is warm_rows + seg_rows rows long instead of all rows (AM x1024, sixteen
-// blocks per call: 1536 steps on 512 warps instead of 8192 steps on 32), which is what lets the
-// kernel finish long before the next call's FIR kernel does.
+// The chain per call is warm_rows + seg_rows rows long instead of all rows.
 //
-// A warp does everything for its 32 lanes: the numerators of a row are 128 contiguous bytes per
-// lane (fetched one row ahead), the 32 dependent FMUL -> FSUB pairs, gain, (int16_t), and the
-// row's 64 bytes of PCM. No shared memory, no barrier.
+// One CTA = ONE warp, and the warp does everything for its 32 lanes: a row of numerators is 64
+// contiguous bytes per lane (int16, [list entry][row][32]), fetched DC_PF rows ahead by cp.async into
+// the lane's own ring in shared memory (an L2 round trip is several rows of chain long; a lane only
+// ever reads what it fetched itself, so nothing synchronises), then the 32 dependent FMUL -> FSUB
+// pairs, gain, (int16_t) and the row's 64 bytes of PCM. At 32 threads and under 128 registers a
+// CTA fits beside the five resident CTAs of the next call's FIR kernel without taking one's place
+// (profiles/r02_am_timeline.txt).
+constexpr int DC_PF = 8;             // rows in flight per lane
+constexpr int DC_LANE_PITCH = 80;    // 64 + 16: lane-per-row 128-bit reads are bank-conflict free
+constexpr int DC_STAGE_BYTES = 32 * DC_LANE_PITCH;
+
 struct DcRows {
   uint32_t begin, store, end;  // rows [begin, end) are run, PCM is kept from row `store` on
 };
 
 // one full row of one lane: 32 steps of the chain; KEEP: also gain, (int16_t) and the row's PCM
 template <bool KEEP>
-__device__ __forceinline__ void dc_row(const u32x4 (&v)[8], float &y, float a1, float gain, bool no_patch, bool keep,
+__device__ __forceinline__ void dc_row(const uint32_t (&w)[16], float &y, float a1, float gain, bool no_patch, bool keep,
                                        int16_t *dst) {
   uint32_t o[16];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float y0 = fsub(u2f(v[j].x), fmul(a1, y));
-    const float y2 = fsub(u2f(v[j].y), fmul(a1, y0));
-    const float y3 = fsub(u2f(v[j].z), fmul(a1, y2));
-    y = fsub(u2f(v[j].w), fmul(a1, y3));
+    const float d0 = i2f((int)(int16_t)(w[2 * j] & 0xffffu)), d1 = i2f((int)w[2 * j] >> 16);
+    const float d2 = i2f((int)(int16_t)(w[2 * j + 1] & 0xffffu)), d3 = i2f((int)w[2 * j + 1] >> 16);
+    const float y0 = fsub(d0, fmul(a1, y));
+    const float y2 = fsub(d1, fmul(a1, y0));
+    const float y3 = fsub(d2, fmul(a1, y2));
+    y = fsub(d3, fmul(a1, y3));
     if constexpr (KEEP) {
       if (no_patch) {
         o[2 * j] = __byte_perm((uint32_t)f2i_rz(fmul(gain, y0)), (uint32_t)f2i_rz(fmul(gain, y2)), 0x5410);
@@ -570,11 +580,21 @@ __device__ __forceinline__ void dc_row(const u32x4 (&v)[8], float &y, float a1, 
   }
 }
 
-__global__ void __launch_bounds__(128) dc_block_kernel(const __grid_constant__ LaunchParams p) {
+// the lane's 64 bytes of row `g` into its place in ring stage `stage_s` (shared address)
+__device__ __forceinline__ void dc_fetch_row(uint32_t stage_s, const int16_t *g) {
+  asm volatile(
+      "cp.async.cg.shared.global [%0], [%1], 16;\n\t"
+      "cp.async.cg.shared.global [%0+16], [%1+16], 16;\n\t"
+      "cp.async.cg.shared.global [%0+32], [%1+32], 16;\n\t"
+      "cp.async.cg.shared.global [%0+48], [%1+48], 16;" ::"r"(stage_s), "l"(g)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(32) dc_block_kernel(const __grid_constant__ LaunchParams p) {
   trace_begin(p);
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x;
   const uint32_t S = p.seg_count, Lr = p.seg_rows;       // S: power of two <= 32
-  const uint32_t idx = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32u + (uint32_t)lane;
+  const uint32_t idx = blockIdx.x * 32u + (uint32_t)lane;
   const uint32_t li = idx / S, s = idx & (S - 1);
   const uint32_t n_rows = (p.n_samples + TILE - 1) / TILE;
   const uint32_t n_pcm = p.n_samples >> 5;
@@ -587,9 +607,8 @@ __global__ void __launch_bounds__(128) dc_block_kernel(const __grid_constant__ L
   const float carried = valid ? tail[1] : 0.f;
   const float gain = valid ? p.scale[ch] : 0.f;
   int16_t *out = p.pcm + (uint64_t)ch * p.pcm_stride;
-  const float *src = p.scratch + (uint64_t)li * 32;
-  const uint64_t row_stride = (uint64_t)p.n_list * 32;
-  // |y| <= max(|y[-1]|, 20 |d|max) and |d| <= 2^17: with |gain| < 500 and |y[-1]| < 2e6 no
+  const int16_t *src = p.scratch + (uint64_t)(valid ? li : 0) * n_rows * 32;
+  // |y| <= max(|y[-1]|, 20 |d|max) and |d| < 2^15: with |gain| < 500 and |y[-1]| < 2e6 no
   // gain * y can reach 2^31, where cvt.rzi saturates but x86 cvttss2si wraps
   const bool no_patch = __all_sync(FULL, !valid || (fabsf(gain) < 500.f && fabsf(carried) < 2e6f));
 
@@ -602,52 +621,64 @@ __global__ void __launch_bounds__(128) dc_block_kernel(const __grid_constant__ L
   bool todo = valid, redo = false;
   float y_in = y, y_end = y;   // state on entering row `store`; state after row end - 1
 
+  __shared__ uint4 s_ring[DC_PF * DC_STAGE_BYTES / 16];
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(s_ring) + (uint32_t)lane * DC_LANE_PITCH;
+
   for (;;) {
-    // ---- run rows [begin, end) of the lanes in `todo` ----
+    // ---- run rows [begin, end) of the lanes in `todo`, DC_PF rows in flight ----
     const uint32_t trips = __reduce_max_sync(FULL, todo ? rw.end - rw.begin : 0u);
-    uint32_t row = rw.begin;
-    u32x4 nx[8];
-    {
-      const bool act = todo && row < rw.end;
-      const float *g = src + (uint64_t)row * row_stride;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) nx[j] = act ? ldg_u4(g + 4 * j) : u32x4{0, 0, 0, 0};
+    for (int k = 0; k < DC_PF - 1; ++k) {
+      if (todo && rw.begin + k < rw.end) dc_fetch_row(ring_s + k * DC_STAGE_BYTES, src + (uint64_t)(rw.begin + k) * 32);
+      cp_async_commit();
     }
-    for (uint32_t it = 0; it < trips; ++it, ++row) {
-      const bool act = todo && row < rw.end;
-      u32x4 v[8];
+    {
+      uint32_t stage = 0;  // ring stage of the row being run
+      for (uint32_t it = 0; it < trips; ++it) {
+        const uint32_t row = rw.begin + it;
+        const bool act = todo && row < rw.end;
+        {  // row + DC_PF - 1 goes where row - 1 was
+          const uint32_t ahead = stage == 0 ? DC_PF - 1 : stage - 1;
+          if (todo && row + DC_PF - 1 < rw.end)
+            dc_fetch_row(ring_s + ahead * DC_STAGE_BYTES, src + (uint64_t)(row + DC_PF - 1) * 32);
+          cp_async_commit();
+        }
+        cp_async_wait<DC_PF - 1>();  // this lane's copy of `row` has landed
+        uint32_t w[16];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = nx[j];
-      if (todo && row + 1 < rw.end) {  // the next row's numerators arrive while this row's chain runs
-        const float *g = src + (uint64_t)(row + 1) * row_stride;
+        for (int j = 0; j < 4; ++j)
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(w[4 * j]), "=r"(w[4 * j + 1]), "=r"(w[4 * j + 2]), "=r"(w[4 * j + 3])
+                       : "r"(ring_s + stage * DC_STAGE_BYTES + 16 * j)
+                       : "memory");
+        stage = stage + 1 == DC_PF ? 0 : stage + 1;
+        if (act && row == rw.store) y_in = y;
+        const bool keep = act && row >= rw.store;
+        int16_t *dst = out + (uint64_t)row * 32;
+        const uint32_t left = n_pcm - row * 32u;  // the call's last row may hold fewer than 32 samples
+        const bool part = act && left < 32u;
+        if (__any_sync(FULL, part)) {
+          if (act) {
+            const uint32_t r = min(left, 32u);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) nx[j] = ldg_u4(g + 4 * j);
-      }
-      if (act && row == rw.store) y_in = y;
-      const bool keep = act && row >= rw.store;
-      int16_t *dst = out + (uint64_t)row * 32;
-      const uint32_t left = n_pcm - row * 32u;  // the call's last row may hold fewer than 32 samples
-      const bool part = act && left < 32u;
-      if (__any_sync(FULL, part)) {
-        if (act) {
-          const uint32_t r = min(left, 32u);
+            for (int j = 0; j < 16; ++j) {
+              const int dd[2] = {(int)(int16_t)(w[j] & 0xffffu), (int)w[j] >> 16};
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t dd[4] = {v[j].x, v[j].y, v[j].z, v[j].w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              if ((uint32_t)(4 * j + i) < r) {
-                y = fsub(u2f(dd[i]), fmul(a1, y));
-                if (keep) dst[4 * j + i] = (int16_t)f2i16_wrap(fmul(gain, y));
+              for (int i = 0; i < 2; ++i) {
+                if ((uint32_t)(2 * j + i) < r) {
+                  y = fsub(i2f(dd[i]), fmul(a1, y));
+                  if (keep) dst[2 * j + i] = (int16_t)f2i16_wrap(fmul(gain, y));
+                }
               }
             }
           }
+        } else if (__any_sync(FULL, keep)) {
+          if (act) dc_row<true>(w, y, a1, gain, no_patch, keep, dst);
+        } else {
+          if (act) dc_row<false>(w, y, a1, gain, no_patch, false, dst);  // warm-up rows: the chain alone
         }
-      } else if (__any_sync(FULL, keep)) {
-        if (act) dc_row<true>(v, y, a1, gain, no_patch, keep, dst);
-      } else {
-        if (act) dc_row<false>(v, y, a1, gain, no_patch, false, dst);  // warm-up rows: the chain alone
       }
+      cp_async_wait<0>();
     }
     if (todo) {
       y_end = y;

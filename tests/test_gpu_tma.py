@@ -19,8 +19,8 @@ def _oracle_rows(modes, iq):
     return rows
 
 
-@pytest.mark.parametrize("tma", [True, False])
-@pytest.mark.parametrize("nbytes", [2048, 64 * 33, 32768, 32768 * 3 + 64 * 5, 64 * 31])
+@pytest.mark.parametrize("tma", [0, 2, 3, 4])
+@pytest.mark.parametrize("nbytes", [2048, 64 * 33, 4096 + 64, 32768, 32768 * 3 + 64 * 5, 64 * 31])
 def test_loaders_match_oracle(tma, nbytes):
     import rtlsdrdiags_b200 as R
     n = 13
@@ -40,7 +40,7 @@ def test_loaders_match_oracle(tma, nbytes):
     e.close()
 
 
-@pytest.mark.parametrize("tma", [True, False])
+@pytest.mark.parametrize("tma", [0, 2, 4])
 def test_device_input_with_stride_and_offset(tma):
     """The tensor map is built from the caller's pointer and channel stride: a view into a larger
     device array (stride > bytes, base offset by 16 bytes), changed between calls."""

@@ -25,9 +25,12 @@ L = R.load_library()
 L.sdr_debug_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
 
 
-def run(steps, sampler):
+def run(steps, sampler, tma=4, seg=0, warm=28):
     eng = R.Engine(channels, 0, nbytes)
     eng.set_modes(modes.numpy())
+    eng.debug_set_tile_loader(tma)
+    eng.debug_set_dc_shape(seg, warm)
+    print("loader %s, recurrence segments %s, warm-up rows %d" % ("TMA x%d" % tma if tma else "cp.async", seg or "auto", warm))
     stream = torch.cuda.Stream(dev)
     eng.set_stream(stream.cuda_stream)
     for _ in range(5):
@@ -72,6 +75,12 @@ def run(steps, sampler):
     return ms
 
 
-for steps, sampler in ((3000, False), (3000, True), (3000, False)):
-    run(steps, sampler)
-    time.sleep(0.5)
+if len(sys.argv) > 1 and sys.argv[1] == "sweep":
+    for tma, seg, warm in ((0, 0, 28), (2, 0, 28), (3, 0, 28), (4, 0, 28), (0, 1, 28), (4, 1, 28), (0, 4, 28), (0, 16, 28),
+                           (0, 8, 24), (0, 8, 32), (4, 4, 28)):
+        run(2000, False, tma, seg, warm)
+        time.sleep(0.3)
+else:
+    for steps, sampler in ((3000, False), (3000, True), (3000, False)):
+        run(steps, sampler)
+        time.sleep(0.5)
