@@ -46,6 +46,8 @@ def build(force=False, defines=(), verbose=False):
 
 HOST = os.path.join(PKG, "host")
 DEMOD = os.path.join(PKG, "b200_demod")
+BANK = os.path.join(PKG, "b200_bank")
+H2D_PROBE = os.path.join(ROOT, "tools", "h2d_probe")
 
 
 def build_host(force=False):
@@ -59,6 +61,17 @@ def build_host(force=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("g++ failed:\n%s\n%s" % (" ".join(cmd), r.stderr))
+    # the multi-GPU C++ driver (one host thread, sdr_bank_*) and the host->device copy probe
+    cmd = ["g++", "-O2", "-std=c++11", "-Wall", "-o", BANK, os.path.join(HOST, "bank_demo.cc"),
+           "-L", PKG, "-lsdr_b200", "-Wl,-rpath,$ORIGIN", "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n%s\n%s" % (" ".join(cmd), r.stderr))
+    cmd = [_nvcc(), "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
+           "-o", H2D_PROBE, os.path.join(ROOT, "tools", "h2d_probe.cu")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), r.stderr))
     return DEMOD
 
 

@@ -57,6 +57,8 @@ struct sdr_engine {
   // AM/SSB FIR kernel: full tiles by TMA (cp.async.bulk.tensor through a tensor map of the caller's
   // IQ array, rebuilt when pointer, stride or length change) or by cp.async
   int tile_loader = 4;  // 0 = cp.async (two slot buffers), 2 / 3 / 4 = TMA with that many slot buffers
+  bool stage1_mma = true;  // with TMA: stage 1 of the AM / SSB cascade on the tensor cores
+  uint32_t *d_am_tab = nullptr;  // am_mma_table()
   CUtensorMap tmap;
   const void *tmap_iq = nullptr;
   uint64_t tmap_stride = 0, tmap_rows = 0;
@@ -236,6 +238,66 @@ int iq_tensor_map(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_t
   return SDR_OK;
 }
 
+// Taps of the tensor-core stage 1 of the AM / SSB kernel (AmSsbTile::stage1_mma): D = A * B with A =
+// raw input bytes. A row h, K index kb = 0..63: the raw byte 32 h - 32 + kb of the tile, i.e. sample
+// js = floor((kb - 32) / 2) relative to the half-window's first sample, I at even bytes. B[kb][n]:
+// column n < 4 gives I' output n of the half-window, n >= 4 gives Q' output n - 4. Output p is
+// sum_k q[k] x'[4 p + 3 - k] (Decimator_int16.cc:310-351; AmDemodulator.cc:349-374) where x' is the
+// rotated sample (IqDataProcessor.cc:567-611): I' = I0, -Q1, -I2, Q3; Q' = Q0, I1, -Q2, -I3 by
+// js mod 4 -- or plain I, Q for input that is already rotated. The taps are doubled (the int8 result
+// is then byte 2 of the accumulator, see Doubled in sdr_tile.cuh) and split as 256 * hi + lo with both
+// parts int8. The accumulators start at the doubled rounding constant 1 << 15 (lo) and, for u8 input
+// (u = s + 128), at -128 * the column sum.
+// Layout per format: [lane][12]: words 0-7 the B fragments [hi / lo][k-step][b0, b1] (mma.m16n8k32 B
+// fragment: b0 = (k 4tq..4tq+3, column g), b1 = (k 16+4tq.., column g)), words 8-11 the starts of the
+// lane's accumulator columns [hi 2tq, hi 2tq+1, lo 2tq, lo 2tq+1].
+std::vector<uint32_t> am_mma_table() {
+  std::vector<uint32_t> tab(2 * 32 * 12, 0);
+  for (int f = 0; f < 2; ++f) {
+    int B[64][8] = {};
+    for (int kb = 0; kb < 64; ++kb) {
+      const int js = (kb - 32) >> 1, c = kb & 1, jm = ((js % 4) + 4) % 4;
+      int arm, sign;
+      if (f == 0) {
+        static const int arm_of[4][2] = {{0, 1}, {1, 0}, {0, 1}, {1, 0}};     // [jm][c]: 0 = I', 1 = Q'
+        static const int sign_of[4][2] = {{1, 1}, {1, -1}, {-1, -1}, {-1, 1}};
+        arm = arm_of[jm][c];
+        sign = sign_of[jm][c];
+      } else {
+        arm = c;
+        sign = 1;
+      }
+      for (int pp = 0; pp < 4; ++pp) {
+        const int k = 4 * pp + 3 - js;
+        if (k >= 0 && k < taps::AM1::N) B[kb][4 * arm + pp] = sign * 2 * taps::AM1::tap(k);
+      }
+    }
+    auto part = [](int v, int h) {
+      const int lo = ((v + 128) & 255) - 128;
+      return h == 0 ? (v - lo) / 256 : lo;
+    };
+    for (int lane = 0; lane < 32; ++lane) {
+      const int g = lane >> 2, tq = lane & 3;
+      uint32_t *t = tab.data() + ((size_t)f * 32 + lane) * 12;
+      for (int h = 0; h < 2; ++h)
+        for (int s2 = 0; s2 < 2; ++s2)
+          for (int r = 0; r < 2; ++r) {
+            const int k0 = 32 * s2 + 16 * r + 4 * tq;
+            uint32_t w = 0;
+            for (int b = 0; b < 4; ++b) w |= (uint32_t)(uint8_t)(int8_t)part(B[k0 + b][g], h) << (8 * b);
+            t[(h * 2 + s2) * 2 + r] = w;
+          }
+      for (int i = 0; i < 4; ++i) {
+        const int h = i >> 1, col = 2 * tq + (i & 1);
+        int sum = 0;
+        for (int kb = 0; kb < 64; ++kb) sum += part(B[kb][col], h);
+        t[8 + i] = (uint32_t)((h == 1 ? 1 << 15 : 0) - (f == 0 ? 128 * sum : 0));
+      }
+    }
+  }
+  return tab;
+}
+
 // AM / SSB: FIR kernel on the engine's stream, recurrence kernel on rec_stream.
 template <bool SSB>
 int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples, int fmt) {
@@ -282,13 +344,27 @@ int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride,
   p.trace = e->d_trace ? e->d_trace + 4 * (e->seq % sdr_engine::TRACE_CALLS) : nullptr;
   const uint32_t grid = (uint32_t)((n_warps + 3) / 4);
   if (e->tile_loader == 0) {
-    amssb_fir_kernel<SSB, false, 2><<<grid, 128, 4 * 2 * TILE_BYTES, e->stream>>>(p, e->tmap);
+    amssb_fir_kernel<SSB, false, 2, false><<<grid, 128, 4 * 2 * TILE_BYTES, e->stream>>>(p, e->tmap);
   } else {
-    const int rc = iq_tensor_map(e, iq, ch_stride, n_samples);
+    int rc = iq_tensor_map(e, iq, ch_stride, n_samples);
     if (rc) return rc;
-    if (e->tile_loader == 2) amssb_fir_kernel<SSB, true, 2><<<grid, 128, 4 * 2 * TILE_BYTES, e->stream>>>(p, e->tmap);
-    else if (e->tile_loader == 3) amssb_fir_kernel<SSB, true, 3><<<grid, 128, 4 * 3 * TILE_BYTES, e->stream>>>(p, e->tmap);
-    else amssb_fir_kernel<SSB, true, 4><<<grid, 128, 4 * 4 * TILE_BYTES, e->stream>>>(p, e->tmap);
+    if (e->stage1_mma && !e->d_am_tab) {
+      const std::vector<uint32_t> tab = am_mma_table();
+      SDR_CK(e, cudaMalloc(&e->d_am_tab, tab.size() * 4));
+      SDR_CK(e, cudaMemcpy(e->d_am_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+    }
+    p.tab = e->d_am_tab;
+    const int nst = e->tile_loader;
+    const size_t smem = (size_t)4 * nst * TILE_BYTES;
+    if (e->stage1_mma) {
+      if (nst == 2) amssb_fir_kernel<SSB, true, 2, true><<<grid, 128, smem, e->stream>>>(p, e->tmap);
+      else if (nst == 3) amssb_fir_kernel<SSB, true, 3, true><<<grid, 128, smem, e->stream>>>(p, e->tmap);
+      else amssb_fir_kernel<SSB, true, 4, true><<<grid, 128, smem, e->stream>>>(p, e->tmap);
+    } else {
+      if (nst == 2) amssb_fir_kernel<SSB, true, 2, false><<<grid, 128, smem, e->stream>>>(p, e->tmap);
+      else if (nst == 3) amssb_fir_kernel<SSB, true, 3, false><<<grid, 128, smem, e->stream>>>(p, e->tmap);
+      else amssb_fir_kernel<SSB, true, 4, false><<<grid, 128, smem, e->stream>>>(p, e->tmap);
+    }
   }
   SDR_CK(e, cudaGetLastError());
   e->launches++;
@@ -846,6 +922,7 @@ int sdr_engine_destroy(sdr_engine *e) {
   cudaFree(e->d_lsb);
   cudaFree(e->d_lut_fm);
   cudaFree(e->d_fm_tab);
+  cudaFree(e->d_am_tab);
   cudaFree(e->d_lut_wbfm);
   cudaFree(e->d_lut_wbfm_half);
   cudaFree(e->d_trace);
@@ -961,10 +1038,22 @@ int sdr_debug_set_dc_shape(sdr_engine *e, uint32_t seg_count, uint32_t warm_rows
   return SDR_OK;
 }
 
+// am_mma_table() for the CPU-side check of the tensor-core formulation (tests/test_am_mma_table.py):
+// 2 formats x 32 lanes x 12 words
+int sdr_debug_am_mma_table(uint32_t *out) {
+  if (!out) return SDR_E_ARG;
+  const std::vector<uint32_t> tab = am_mma_table();
+  memcpy(out, tab.data(), tab.size() * 4);
+  return (int)tab.size();
+}
+
 // how the AM/SSB FIR kernel fetches full tiles: 0 = cp.async with two slot buffers per warp,
-// 2 / 3 / 4 = TMA with that many (1 = the default TMA depth); for A/B runs
+// 2 / 3 / 4 = TMA with that many (1 = the default TMA depth); + 8 = keep stage 1 on the CUDA cores
+// (TMA loaders run it on the tensor cores by default). For A/B runs and tests.
 int sdr_debug_set_tile_loader(sdr_engine *e, int loader) {
-  if (!e || loader < 0 || loader > 4) return SDR_E_ARG;
+  if (!e || loader < 0 || (loader & 7) > 4 || loader > 12) return SDR_E_ARG;
+  e->stage1_mma = !(loader & 8);
+  loader &= 7;
   e->tile_loader = loader == 1 ? 4 : loader;
   return SDR_OK;
 }

@@ -272,15 +272,22 @@ struct AmSsbTile {
   // FULL_TILE: r == 32 is known at compile time (the hot loop); otherwise 1 <= r <= 32.
   template <bool FULL_TILE = false>
   __device__ __forceinline__ static int tile(const uint32_t (&w)[16], int fmt, bool lsb, AmSsbCarry<SSB> &pv, int lane, int r,
-                                                  const PrevMasks &pm) {
+                                             const PrevMasks &pm) {
     AmSsbCarry<SSB> cu;
+    stage1_simt(w, fmt, pv, cu, lane);
+    return rest<FULL_TILE>(cu, lsb, pv, lane, r, pm);
+  }
+
+  // stage 1 on the CUDA cores: front end, then 8 taps 4:1 on each arm (AmDemodulator.cc:349-374
+  // through Decimator_int16). Leaves the lane's eight outputs per arm (int8 x 4 per word) and its
+  // last rotation group in `cu`.
+  __device__ __forceinline__ static void stage1_simt(const uint32_t (&w)[16], int fmt, const AmSsbCarry<SSB> &pv,
+                                                     AmSsbCarry<SSB> &cu, int lane) {
     uint32_t a[8], b[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g) front_end_group(fmt, w[2 * g], w[2 * g + 1], a[g], b[g]);
     cu.a7 = a[7];
     cu.b7 = b[7];
-
-    // stage 1: 8 taps, 4:1 (AmDemodulator.cc:349-374 through Decimator_int16)
     const uint32_t am1 = shfl_prev(a[7], pv.a7, 1, lane), bm1 = shfl_prev(b[7], pv.b7, 1, lane);
     int ya[8], yb[8];
 #pragma unroll
@@ -294,7 +301,12 @@ struct AmSsbTile {
     cu.s1a1 = pack_b2x4(ya[4], ya[5], ya[6], ya[7]);
     cu.s1b0 = pack_b2x4(yb[0], yb[1], yb[2], yb[3]);
     cu.s1b1 = pack_b2x4(yb[4], yb[5], yb[6], yb[7]);
+  }
 
+  // Everything after stage 1, from cu.s1a0..s1b1 (cu.a7 / cu.b7 are carried along untouched).
+  template <bool FULL_TILE = false>
+  __device__ __forceinline__ static int rest(AmSsbCarry<SSB> &cu, bool lsb, AmSsbCarry<SSB> &pv, int lane, int r,
+                                             const PrevMasks &pm) {
     // stage 2: 12 taps, 4:1
     const uint32_t pa0 = shfl_prev(cu.s1a0, pv.s1a0, 1, lane), pa1 = shfl_prev(cu.s1a1, pv.s1a1, 1, lane);
     const uint32_t pb0 = shfl_prev(cu.s1b0, pv.s1b0, 1, lane), pb1 = shfl_prev(cu.s1b1, pv.s1b1, 1, lane);
@@ -358,6 +370,126 @@ struct AmSsbTile {
     return out;
   }
 
+  // ---- stage 1 on the tensor cores (slots in the TMA layout) ----
+  // The two 8-tap 4:1 decimators as a warp-private int8 GEMM on the RAW bytes, mma.sync m16n8k32:
+  //   D[16 x 8] += A[16 x 32] * B[32 x 8], twice per K (64 bytes) and per tap half
+  //   A row h = the 64 raw bytes that end with half-window h's own 32 (a half-window = 16 samples =
+  //     four outputs per arm; the 32 bytes before it hold the 4 samples of history the first output
+  //     needs), fetched with ldmatrix straight from the swizzled slot -- no de-interleave, no
+  //     offset, no rotation: those are in where the taps sit in B and which sign they carry;
+  //   B column n: taps of I' output n (n < 4) or Q' output n - 4 of the half-window, split as
+  //     256 * hi + lo (two int8 matrices); the u8 offset and the rounding constant are in the
+  //     accumulator start. Table: am_mma_table() in the engine.
+  // A lane ends up with two neighbouring outputs of one arm for eight half-windows; they go through
+  // a 512-byte shared buffer into the layout stage 2 wants (lane = window, four packed words).
+  // 8 LDSM + 16 IMMA + the transpose replace the packed-byte front end and 64 IDP.2A.
+  // As in the NBFM tuner one thing is not linear: int8 negation leaves -128 alone
+  // (IqDataProcessor.cc:594-607), so a raw byte 0 where the rotation negates makes the tile (and the
+  // one after it, whose history it is) take the exact CUDA-core path.
+  struct Mma {
+    uint32_t b[8];      // taps fragments [hi / lo][k-step][b0, b1]
+    int c[4];           // accumulator starts: hi column 2tq, hi 2tq+1, lo 2tq, lo 2tq+1
+    uint32_t off[8];    // [M-tile][k-step]: byte offset in the slot of this lane's ldmatrix row
+    uint32_t hist_s;    // shared address of the warp's 32 bytes of raw history (bytes before the tile)
+    uint32_t hist_row;  // lanes 0 and 16: their row of (M-tile 0, k-step 0) is the history; else 0
+    uint32_t zmask;     // which bytes of this lane's fragment words sit where the rotation negates
+    uint32_t xst, xld;  // transpose buffer: the lane's store base and its 16-byte read address
+    __device__ __forceinline__ void init(const uint32_t *tab, int fmt, uint32_t hist, uint32_t xbuf, int lane) {
+      const uint32_t *t = tab + ((fmt == FMT_U8_OFFSET_ROTATE ? 0 : 32) + lane) * 12;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) b[i] = t[i];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c[i] = (int)t[8 + i];
+      const int r8 = (lane & 7) + 8 * ((lane >> 3) & 1);
+#pragma unroll
+      for (int m = 0; m < 4; ++m)
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+          const int q = 2 * (16 * m + r8) + 2 * (kk - 1) + (lane >> 4);  // 16-byte chunk of the tile
+          off[2 * m + kk] = q < 0 ? 0u : (uint32_t)((q >> 3) * 128 + (((q & 7) ^ ((q >> 3) & 7)) * 16));
+        }
+      hist_s = hist;
+      hist_row = r8 == 0 ? hist + 16u * (uint32_t)(lane >> 4) : 0u;
+      zmask = (lane & 1) ? 0x00808080u : 0x80000000u;  // odd tq: bytes 4, 5, 6 of a rotation group; even: byte 3
+      const int g = lane >> 2, tq = lane & 3;
+      xst = xbuf + (uint32_t)((g >> 1) * 16 + (tq >> 1) * 8 + (g & 1) * 4 + (tq & 1) * 2);
+      xld = xbuf + 16u * (uint32_t)lane;
+    }
+  };
+  template <bool U8>
+  __device__ __forceinline__ static void imma_data(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    if constexpr (U8)
+      asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+          : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+          : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else
+      asm("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+          : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+          : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+  __device__ __forceinline__ static void ldsm4(uint32_t addr, uint32_t (&r)[4]) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(addr)
+                 : "memory");
+  }
+  // slot_s = shared address of the tile. Fills cu.s1a0 .. cu.s1b1; returns false, with cu
+  // untouched, if a raw byte 0 sits where the rotation negates.
+  template <bool U8>
+  __device__ __forceinline__ static bool stage1_mma(uint32_t slot_s, const Mma &mm, AmSsbCarry<SSB> &cu) {
+    uint32_t z = 0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      uint32_t a0[4], a1[4];
+      ldsm4(m == 0 && mm.hist_row ? mm.hist_row : slot_s + mm.off[2 * m], a0);
+      ldsm4(slot_s + mm.off[2 * m + 1], a1);
+      if constexpr (U8) {  // the tile's own bytes are the k-step 1 fragments
+#pragma unroll
+        for (int i = 0; i < 4; ++i) z |= (a1[i] - 0x01010101u) & ~a1[i];
+      }
+      int hi[4] = {mm.c[0], mm.c[1], mm.c[0], mm.c[1]}, lo[4] = {mm.c[2], mm.c[3], mm.c[2], mm.c[3]};
+      imma_data<U8>(hi, a0, mm.b[0], mm.b[1]);
+      imma_data<U8>(lo, a0, mm.b[4], mm.b[5]);
+      imma_data<U8>(hi, a1, mm.b[2], mm.b[3]);
+      imma_data<U8>(lo, a1, mm.b[6], mm.b[7]);
+      // rows g (e = 0) and g + 8 (e = 1): two neighbouring outputs of half-window 16 m + g + 8 e;
+      // the int8 result is byte 2 of the doubled accumulator (see Doubled)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const uint32_t acc0 = (uint32_t)((hi[2 * e] << 8) + lo[2 * e]), acc1 = (uint32_t)((hi[2 * e + 1] << 8) + lo[2 * e + 1]);
+        const uint32_t pair = __byte_perm(acc0, acc1, 0x0062);
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(mm.xst + 128 * m + 64 * e), "h"((uint16_t)pair) : "memory");
+      }
+    }
+    if constexpr (U8) {
+      if (__any_sync(FULL, (z & mm.zmask) != 0)) return false;
+    }
+    __syncwarp();
+    uint32_t x[4];
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]) : "r"(mm.xld) : "memory");
+    cu.s1a0 = x[0]; cu.s1a1 = x[1]; cu.s1b0 = x[2]; cu.s1b1 = x[3];
+    return true;
+  }
+  // The last rotation group before the tile, as the planes stage1_simt's lane 0 reads: from the
+  // raw history's last eight bytes. (Every lane gets the same words; lane 31's are what counts.)
+  __device__ __forceinline__ static void planes_from_history(uint32_t hist_s, int fmt, AmSsbCarry<SSB> &pv) {
+    uint32_t w0, w1;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(hist_s + 24) : "memory");
+    front_end_group(fmt, w0, w1, pv.a7, pv.b7);
+  }
+  // and back: the raw bytes of a rotation group from its planes (front_end_group's inverse;
+  // wrapping int8 negation is its own inverse)
+  __device__ __forceinline__ static void raw_from_planes(uint32_t a, uint32_t b, int fmt, uint32_t &w0, uint32_t &w1) {
+    if (fmt == FMT_U8_OFFSET_ROTATE) {
+      // I0 = I'0, Q0 = Q'0, I1 = Q'1, Q1 = -I'1  |  I2 = -I'2, Q2 = -Q'2, I3 = -Q'3, Q3 = I'3
+      w0 = offset_and_negate(byte_perm(a, b, 0x1540), 0xff000000u, 0x01000000u);
+      w1 = offset_and_negate(byte_perm(a, b, 0x3762), 0x00ffffffu, 0x00010101u);
+    } else {
+      w0 = byte_perm(a, b, 0x5140);
+      w1 = byte_perm(a, b, 0x7362);
+    }
+  }
+
   template <int I>
   __device__ __forceinline__ static void stage3(const uint32_t (&q)[8], int &acc_i, int &acc_q) {
     if constexpr (I < 8) {
@@ -395,13 +527,16 @@ struct AmSsbTile {
 // TMA = true: full tiles arrive by cp.async.bulk.tensor (TmaIo), one instruction of one lane per
 // tile; false: by four cp.async per lane (TileIo). A partial last tile takes cp.async either way.
 // NST = slot buffers per warp: NST - 1 tiles are in flight while one is computed.
-template <bool SSB, bool TMA, int NST>
+// MMA (with TMA only): stage 1 on the tensor cores (AmSsbTile::stage1_mma).
+template <bool SSB, bool TMA, int NST, bool MMA>
 __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant__ LaunchParams p,
                                                            const __grid_constant__ CUtensorMap tmap) {
   using T = AmSsbTile<SSB>;
   constexpr uint32_t WARMUP = T::WARMUP_TILES;
+  static_assert(!MMA || TMA, "the tensor-core stage 1 reads the TMA slot layout");
   extern __shared__ __align__(1024) uint4 smem_raw[];
   __shared__ uint64_t s_bar[4][NST];
+  __shared__ uint4 s_mma[MMA ? 4 : 1][34];  // per warp: 32 bytes of raw history, 512 bytes of transpose buffer
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t n_warps = p.aux;  // worker warps of the whole grid
   const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -422,6 +557,11 @@ __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant
   PrevMasks pm;
   pm.init(lane);
   const int fmt = p.fmt;
+  typename T::Mma mm;
+  if constexpr (MMA) {
+    const uint32_t ms = (uint32_t)__cvta_generic_to_shared(s_mma[warp]);
+    mm.init(p.tab, fmt, ms, ms + 32, lane);
+  }
 
   while (g0 < g1) {
     // the piece of one channel: tiles [t0, t1) of list entry li
@@ -448,6 +588,20 @@ __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant
       pv.y3a = pv.y3b = 0;
     }
     const bool lsb = SSB && p.lsb[ch] != 0;
+    // tensor-core stage 1: the raw bytes before the piece's first tile. force_simt: they (or,
+    // later, the tile before) hold a byte the GEMM cannot represent. planes_ok: pv.a7 / pv.b7
+    // hold the last rotation group (they do not after a tensor-core tile).
+    bool force_simt = false, planes_ok = true;
+    if constexpr (MMA) {
+      __syncwarp();  // the previous piece's last reads of the history are done
+      uint32_t w0, w1;
+      T::raw_from_planes(pv.a7, pv.b7, fmt, w0, w1);  // all-zero carry -> 0x80 bytes: "no signal"
+      if (lane < 6) asm volatile("st.shared.u32 [%0], %1;" ::"r"(mm.hist_s + 4 * lane), "r"(0x80808080u) : "memory");
+      if (lane == 31) asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(mm.hist_s + 24), "r"(w0), "r"(w1) : "memory");
+      if (fmt == FMT_U8_OFFSET_ROTATE)
+        force_simt = __any_sync(FULL, lane == 31 && ((w0 & 0xff000000u) == 0 || (((w1 | 0xff000000u) - 0x01010101u) & ~(w1 | 0xff000000u) & 0x80808080u) != 0));
+      __syncwarp();
+    }
 
     // Full tiles [tw, tf) go through the lean loop; a partial last tile of the block (any
     // multiple of 32 samples) takes the generic path once.
@@ -477,19 +631,49 @@ __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant
       fetch(t + NST - 1, buf == 0 ? NST - 1 : buf - 1);  // where tile t - 1 was; every lane has read it
       cp_async_commit();
       uint32_t w[16];
-      if constexpr (TMA) {
+      int d;
+      if constexpr (MMA) {
         tio.wait(buf);
-        tio.read(buf, w);
-      } else {
-        cp_async_wait<NST - 1>();
+        const uint32_t slot_s = tio.slot + buf * TILE_BYTES;
+        AmSsbCarry<SSB> cu;
+        cu.a7 = cu.b7 = 0;
+        bool ok = false;
+        if (!force_simt)
+          ok = fmt == FMT_U8_OFFSET_ROTATE ? T::template stage1_mma<true>(slot_s, mm, cu) : T::template stage1_mma<false>(slot_s, mm, cu);
+        if (!ok) {  // a clipping byte in this tile or right before it: the exact path
+          tio.read(buf, w);
+          if (!planes_ok) T::planes_from_history(mm.hist_s, fmt, pv);
+          T::stage1_simt(w, fmt, pv, cu, lane);
+        }
+        planes_ok = !ok;
+        force_simt = !ok && fmt == FMT_U8_OFFSET_ROTATE;
+        // the tile's last 32 bytes (chunks 126, 127 sit at 121, 120 under the swizzle) become the history
         __syncwarp();
-        io.read(buf * TILE_BYTES, w);
+        if (lane < 8) {
+          uint32_t hv;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hv) : "r"(slot_s + (lane < 4 ? 121u * 16u : 120u * 16u) + 4u * (lane & 3)) : "memory");
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(mm.hist_s + 4 * lane), "r"(hv) : "memory");
+        }
+        __syncwarp();  // the slot may be refilled, the history read
+        d = T::template rest<true>(cu, lsb, pv, lane, 32, pm);
+      } else {
+        if constexpr (TMA) {
+          tio.wait(buf);
+          tio.read(buf, w);
+        } else {
+          cp_async_wait<NST - 1>();
+          __syncwarp();
+          io.read(buf * TILE_BYTES, w);
+        }
+        __syncwarp();  // this buffer may be refilled once every lane has read it
+        d = T::template tile<true>(w, fmt, lsb, pv, lane, 32, pm);
       }
-      __syncwarp();  // this buffer may be refilled once every lane has read it
-      const int d = T::template tile<true>(w, fmt, lsb, pv, lane, 32, pm);
       if (t >= t0) *sp = (int16_t)d;
       sp += 32;
       buf = buf + 1 == NST ? 0 : buf + 1;
+    }
+    if constexpr (MMA) {
+      if (!planes_ok) T::planes_from_history(mm.hist_s, fmt, pv);  // the partial tile and the carry need them
     }
     if (partial) {
       cp_async_wait<0>();

@@ -4,7 +4,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_gpu_tma.py tests/test_gpu_recurrence.py tests/test_gpu_bank.py tests/test_gpu_parity.py tests/test_gpu_ingest.py -x -q 2>&1 | tail -5
 SDR_TIMELINE_ROWS=1 timeout 600 python tools/probe_timeline.py sweep 2>&1 | tee gpurun_out/r02b_timeline.txt | grep -v "call "
-for ld in 4 0; do
+for ld in 4 12 0; do
 SDR_BENCH_TILE_LOADER=$ld timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:fir_kernel|dc_block" -c 40 --csv --log-file gpurun_out/r02b_am_launches_$ld.csv python bench.py --steps 10 --warmup 3 --no-extras --no-cpu --no-e2e > /dev/null 2>&1
 python - <<PY
 import csv
