@@ -46,6 +46,9 @@ IqDataProcessor::IqDataProcessor(char *hostIpAddress, int hostPort)
   // Let all signal exceed threshold (IqDataProcessor.cc:41).
   signalDetectThreshold = -200;
   gateEngine = NULL;
+  gateThreshold = -200;
+  gateReceiveGain = 0;
+  gateDump = 0;
   blocksSeen = 0;
   signalNotificationEnabled = false;
   signalCallbackPtr = NULL;
@@ -136,6 +139,7 @@ bool IqDataProcessor::runSquelch(unsigned char *bufferPtr, unsigned long byteCou
   } // if
   if ((byteCount % 64) != 0 || byteCount == 0)
   {
+    blocksSeen++;
     return (true); // the engine works on whole PCM samples; such a block passes ungated
   } // if
   if (gateEngine == NULL)
@@ -164,9 +168,22 @@ bool IqDataProcessor::runSquelch(unsigned char *bufferPtr, unsigned long byteCou
 
   uint8_t allowed = 1;
   uint32_t magnitude = 0;
-  sdr_set_squelch_threshold(gateEngine, 0, signalDetectThreshold);
-  sdr_set_receive_gain_db(gateEngine, 0, (uint32_t)radio_adjustableReceiveGainInDb);
-  sdr_set_iq_dump(gateEngine, 0, iqDumpEnabled ? 1 : 0);
+  // each setter makes the engine re-upload its squelch tables: only on a change
+  if (signalDetectThreshold != gateThreshold)
+  {
+    gateThreshold = signalDetectThreshold;
+    sdr_set_squelch_threshold(gateEngine, 0, gateThreshold);
+  } // if
+  if (radio_adjustableReceiveGainInDb != gateReceiveGain)
+  {
+    gateReceiveGain = radio_adjustableReceiveGainInDb;
+    sdr_set_receive_gain_db(gateEngine, 0, (uint32_t)gateReceiveGain);
+  } // if
+  if ((iqDumpEnabled ? 1 : 0) != gateDump)
+  {
+    gateDump = iqDumpEnabled ? 1 : 0;
+    sdr_set_iq_dump(gateEngine, 0, gateDump);
+  } // if
   // the block may sit at any address: stage it 16-byte aligned
   static thread_local std::vector<uint8_t> staging;
   staging.resize(byteCount + 16);
@@ -213,6 +230,57 @@ void IqDataProcessor::setDemodulatorMode(demodulatorType mode)
   } // if
 } // setDemodulatorMode
 
+// Multiplication of z(n) = x(n) + j y(n) by exp(-j n pi / 2) = {1, -j, -1, j, ...}: within every
+// group of four complex samples, sample 1 becomes (y, -x), sample 2 (-x, -y), sample 3 (-y, x)
+// (Lyons, Understanding DSP, 13.1.2; IqDataProcessor.cc:500-545). int8 negation wraps: -(-128)
+// stays -128. The phase restarts at the head of every call.
+void IqDataProcessor::downconvertByFsOver4(int8_t *bufferPtr, uint32_t byteCount)
+{
+  for (uint32_t g = 0; g + 8 <= byteCount; g += 8)
+  {
+    int8_t *z = bufferPtr + g;
+    const int8_t x1 = z[2], y1 = z[3], x2 = z[4], y2 = z[5], x3 = z[6], y3 = z[7];
+    z[2] = y1;
+    z[3] = (int8_t)(-x1);
+    z[4] = (int8_t)(-x2);
+    z[5] = (int8_t)(-y2);
+    z[6] = (int8_t)(-y3);
+    z[7] = x3;
+  } // for
+} // downconvertByFsOver4
+
+// The same with exp(+j n pi / 2) = {1, j, -1, -j, ...}: sample 1 becomes (-y, x), sample 2
+// (-x, -y), sample 3 (y, -x) (IqDataProcessor.cc:567-611).
+void IqDataProcessor::upconvertByFsOver4(int8_t *bufferPtr, uint32_t byteCount)
+{
+  for (uint32_t g = 0; g + 8 <= byteCount; g += 8)
+  {
+    int8_t *z = bufferPtr + g;
+    const int8_t x1 = z[2], y1 = z[3], x2 = z[4], y2 = z[5], x3 = z[6], y3 = z[7];
+    z[2] = (int8_t)(-y1);
+    z[3] = x1;
+    z[4] = (int8_t)(-x2);
+    z[5] = (int8_t)(-y2);
+    z[6] = y3;
+    z[7] = (int8_t)(-x3);
+  } // for
+} // upconvertByFsOver4
+
+// The reference leaves the caller's buffer converted in place -- signed and Fs/4-translated
+// (IqDataProcessor.cc:735-749) -- and a caller that looks at it afterwards (or reuses it) sees
+// that. The GPU works on its own copy, so the host buffer is converted here, after the engine
+// took the raw bytes. (WbFmDemodulator additionally overwrites it with its pre-filter output,
+// WbFmDemodulator.cc:389-398; that is not reproduced.)
+static void convertCallerBuffer(IqDataProcessor *p, unsigned char *bufferPtr, unsigned long byteCount)
+{
+  int8_t *signedBufferPtr = (int8_t *)bufferPtr;
+  for (unsigned long i = 0; i < byteCount; i++)
+  {
+    signedBufferPtr[i] = (int8_t)(bufferPtr[i] - 128);
+  } // for
+  p->upconvertByFsOver4(signedBufferPtr, (uint32_t)byteCount);
+} // convertCallerBuffer
+
 void IqDataProcessor::acceptIqData(unsigned long timeStamp, unsigned char *bufferPtr, unsigned long byteCount)
 {
   (void)timeStamp;
@@ -228,6 +296,7 @@ void IqDataProcessor::acceptIqData(unsigned long timeStamp, unsigned char *buffe
 
   if (!runSquelch(bufferPtr, byteCount))
   {
+    convertCallerBuffer(this, bufferPtr, byteCount);
     return; // squelched: no demodulator is called (IqDataProcessor.cc:793)
   } // if
 
@@ -249,6 +318,7 @@ void IqDataProcessor::acceptIqData(unsigned long timeStamp, unsigned char *buffe
     default:
       break;
   } // switch
+  convertCallerBuffer(this, bufferPtr, byteCount);
 } // acceptIqData
 
 void IqDataProcessor::displayInternalInformation(void)

@@ -32,6 +32,12 @@ class IqDataProcessor
 
   void setSignalDetectThreshold(int32_t threshold);
 
+  // Frequency translation by -Fs/4 / +Fs/4 of signed interleaved IQ, in place on the host
+  // (hdr_diags/IqDataProcessor.h:32-33). acceptIqData does the +Fs/4 translation on the GPU;
+  // these serve callers that use the reference's public helpers directly.
+  void downconvertByFsOver4(int8_t *bufferPtr, uint32_t byteCount);
+  void upconvertByFsOver4(int8_t *bufferPtr, uint32_t byteCount);
+
   void enableIqDump(void);
   void disableIqDump(void);
   bool isIqDumpEnabled(void);
@@ -59,6 +65,10 @@ class IqDataProcessor
   demodulatorType demodulatorMode;
   int32_t signalDetectThreshold;
   sdr_engine *gateEngine;  // mode None: runs only the squelch kernel
+  // what the gate engine was last told, so the setters run only on a change
+  int32_t gateThreshold;
+  int32_t gateReceiveGain;
+  int gateDump;
   unsigned long blocksSeen; // blocks that passed while no gate engine existed yet
   bool signalNotificationEnabled;
   void *signalCallbackContextPtr;

@@ -132,3 +132,42 @@ def test_driver_iq_dump_datagrams():
             assert np.array_equal(np.frombuffer(b"".join(got), dtype=np.int8), O.front_end(u8[o:o + block]))
     finally:
         sock.close()
+
+
+def _helpers_exe():
+    from rtlsdrdiags_b200 import _build
+    _build.build()
+    _build.build_host()
+    exe = os.path.join(ROOT, "tests", "host", "iqdp_helpers")
+    src = os.path.join(ROOT, "tests", "host", "iqdp_helpers_main.cc")
+    pkg = os.path.join(ROOT, "rtlsdrdiags_b200")
+    deps = [src, os.path.join(HOST, "IqDataProcessor.cc"), os.path.join(HOST, "B200Demodulator.cc"), _build.LIB]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++11", "-I", HOST, "-o", exe, src, os.path.join(HOST, "IqDataProcessor.cc"),
+                        os.path.join(HOST, "B200Demodulator.cc"), "-L", pkg, "-lsdr_b200", "-Wl,-rpath," + pkg, "-lm"],
+                       check=True)
+    return exe
+
+
+def test_public_fs4_helpers_match_the_front_end():
+    """upconvertByFsOver4 / downconvertByFsOver4 (hdr_diags/IqDataProcessor.h:32-33) on the host:
+    up is what the oracle's front end does after the offset, down is its inverse (int8 negation
+    wraps, so -128 stays), and acceptIqData leaves the caller's buffer signed and translated as the
+    reference does (IqDataProcessor.cc:735-749)."""
+    exe = _helpers_exe()
+    rng = np.random.default_rng(3)
+    u8 = rng.integers(0, 256, size=4096, dtype=np.uint8)
+    u8[:64] = 0
+    s8 = (u8.astype(np.int16) - 128).astype(np.int8)
+
+    def run(what, data):
+        r = subprocess.run([exe, what], input=data.tobytes(), capture_output=True, timeout=60)
+        assert r.returncode == 0, r.stderr.decode()
+        return np.frombuffer(r.stdout, dtype=np.int8)
+
+    up = run("up", s8)
+    assert np.array_equal(up, O.front_end(u8))
+    down = run("down", up)
+    assert np.array_equal(down, s8)
+    # mode None and the default squelch: no engine is needed, the buffer is converted all the same
+    assert np.array_equal(run("accept", u8), O.front_end(u8))
