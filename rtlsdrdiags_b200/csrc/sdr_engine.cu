@@ -56,8 +56,9 @@ struct sdr_engine {
   int16_t *d_scratch[5][RING_MAX] = {};
   // AM/SSB FIR kernel: full tiles by TMA (cp.async.bulk.tensor through a tensor map of the caller's
   // IQ array, rebuilt when pointer, stride or length change) or by cp.async
-  int tile_loader = 4;  // 0 = cp.async (two slot buffers), 2 / 3 / 4 = TMA with that many slot buffers
-  bool stage1_mma = true;  // with TMA: stage 1 of the AM / SSB cascade on the tensor cores
+  int tile_loader = 2;  // 0 = cp.async (two slot buffers), 2 / 3 / 4 = TMA with that many slot buffers
+  bool stage1_mma = false;  // with TMA: stage 1 of the AM / SSB cascade on the tensor cores (measured slower)
+  int fir_ctas_per_sm = 5;  // register budget of the FIR kernel: 5 (96 registers) or 6 (80) CTAs per SM
   uint32_t *d_am_tab = nullptr;  // am_mma_table()
   CUtensorMap tmap;
   const void *tmap_iq = nullptr;
@@ -344,7 +345,13 @@ int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride,
   p.trace = e->d_trace ? e->d_trace + 4 * (e->seq % sdr_engine::TRACE_CALLS) : nullptr;
   const uint32_t grid = (uint32_t)((n_warps + 3) / 4);
   if (e->tile_loader == 0) {
-    amssb_fir_kernel<SSB, false, 2, false><<<grid, 128, 4 * 2 * TILE_BYTES, e->stream>>>(p, e->tmap);
+    if (e->fir_ctas_per_sm == 6) amssb_fir_kernel<SSB, false, 2, false, 6><<<grid, 128, 4 * 2 * TILE_BYTES, e->stream>>>(p, e->tmap);
+    else amssb_fir_kernel<SSB, false, 2, false><<<grid, 128, 4 * 2 * TILE_BYTES, e->stream>>>(p, e->tmap);
+  } else if (e->fir_ctas_per_sm == 6 && !e->stage1_mma) {
+    const int rc = iq_tensor_map(e, iq, ch_stride, n_samples);
+    if (rc) return rc;
+    if (e->tile_loader == 2) amssb_fir_kernel<SSB, true, 2, false, 6><<<grid, 128, 4 * 2 * TILE_BYTES, e->stream>>>(p, e->tmap);
+    else amssb_fir_kernel<SSB, true, 4, false, 6><<<grid, 128, 4 * 4 * TILE_BYTES, e->stream>>>(p, e->tmap);
   } else {
     int rc = iq_tensor_map(e, iq, ch_stride, n_samples);
     if (rc) return rc;
@@ -1048,13 +1055,15 @@ int sdr_debug_am_mma_table(uint32_t *out) {
 }
 
 // how the AM/SSB FIR kernel fetches full tiles: 0 = cp.async with two slot buffers per warp,
-// 2 / 3 / 4 = TMA with that many (1 = the default TMA depth); + 8 = keep stage 1 on the CUDA cores
-// (TMA loaders run it on the tensor cores by default). For A/B runs and tests.
+// 2 / 3 / 4 = TMA with that many (1 = the default: TMA, two buffers); + 8 = stage 1 on the tensor
+// cores (TMA loaders only; default: CUDA cores); + 16 = the 80-register build, six CTAs per SM
+// (stage 1 on the CUDA cores only). For A/B runs and tests.
 int sdr_debug_set_tile_loader(sdr_engine *e, int loader) {
-  if (!e || loader < 0 || (loader & 7) > 4 || loader > 12) return SDR_E_ARG;
-  e->stage1_mma = !(loader & 8);
+  if (!e || loader < 0 || (loader & 7) > 4 || loader > 31) return SDR_E_ARG;
+  e->stage1_mma = (loader & 8) != 0 && (loader & 7) != 0;
+  e->fir_ctas_per_sm = (loader & 16) ? 6 : 5;
   loader &= 7;
-  e->tile_loader = loader == 1 ? 4 : loader;
+  e->tile_loader = loader == 1 ? 2 : loader;
   return SDR_OK;
 }
 

@@ -158,6 +158,19 @@ __device__ __forceinline__ void tma_load_tile(uint32_t dst, const CUtensorMap *m
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(0), "r"(row), "r"(ch), "r"(bar)
       : "memory");
 }
+// one lane of the (converged) warp, chosen by the hardware: the TMA issue path then has
+// warp-uniform operands and needs no per-lane predicate
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
 struct TmaIo {
   uint32_t slot;    // shared address of slot buffer 0 (1024-byte aligned); buffer b follows at + b * TILE_BYTES
   uint32_t bar;     // shared address of the buffers' mbarriers (8 bytes each)
@@ -389,11 +402,17 @@ struct AmSsbTile {
   struct Mma {
     uint32_t b[8];      // taps fragments [hi / lo][k-step][b0, b1]
     int c[4];           // accumulator starts: hi column 2tq, hi 2tq+1, lo 2tq, lo 2tq+1
-    uint32_t off[8];    // [M-tile][k-step]: byte offset in the slot of this lane's ldmatrix row
+    // Byte offset in the slot of this lane's ldmatrix row, per k-step, for M-tiles 0 / 2 (`even`, + 1024
+    // for M-tile 2) and 1 / 3 (`odd`, + 1024 for M-tile 3): an M-tile is 512 bytes further on, and the
+    // 128-byte swizzle (chunk ^ (128-byte row & 7)) repeats every 1024 bytes.
+    uint32_t even[2], odd[2];
     uint32_t hist_s;    // shared address of the warp's 32 bytes of raw history (bytes before the tile)
     uint32_t hist_row;  // lanes 0 and 16: their row of (M-tile 0, k-step 0) is the history; else 0
     uint32_t zmask;     // which bytes of this lane's fragment words sit where the rotation negates
     uint32_t xst, xld;  // transpose buffer: the lane's store base and its 16-byte read address
+    __device__ __forceinline__ static uint32_t chunk_offset(int q) {  // 16-byte chunk q of the tile, q >= 0
+      return (uint32_t)((q >> 3) * 128 + (((q & 7) ^ ((q >> 3) & 7)) * 16));
+    }
     __device__ __forceinline__ void init(const uint32_t *tab, int fmt, uint32_t hist, uint32_t xbuf, int lane) {
       const uint32_t *t = tab + ((fmt == FMT_U8_OFFSET_ROTATE ? 0 : 32) + lane) * 12;
 #pragma unroll
@@ -402,12 +421,13 @@ struct AmSsbTile {
       for (int i = 0; i < 4; ++i) c[i] = (int)t[8 + i];
       const int r8 = (lane & 7) + 8 * ((lane >> 3) & 1);
 #pragma unroll
-      for (int m = 0; m < 4; ++m)
-#pragma unroll
-        for (int kk = 0; kk < 2; ++kk) {
-          const int q = 2 * (16 * m + r8) + 2 * (kk - 1) + (lane >> 4);  // 16-byte chunk of the tile
-          off[2 * m + kk] = q < 0 ? 0u : (uint32_t)((q >> 3) * 128 + (((q & 7) ^ ((q >> 3) & 7)) * 16));
-        }
+      for (int kk = 0; kk < 2; ++kk) {
+        // chunk of M-tile m: 2 * (16 m + r8) + 2 * (kk - 1) + (lane >> 4); M-tile 2's minus 1024 bytes
+        // serves M-tile 0 as well (whose row 0, k-step 0 is the history: hist_row)
+        const int q0 = 2 * r8 + 2 * (kk - 1) + (lane >> 4);
+        even[kk] = chunk_offset(64 + q0) - 1024u;
+        odd[kk] = chunk_offset(32 + q0);
+      }
       hist_s = hist;
       hist_row = r8 == 0 ? hist + 16u * (uint32_t)(lane >> 4) : 0u;
       zmask = (lane & 1) ? 0x00808080u : 0x80000000u;  // odd tq: bytes 4, 5, 6 of a rotation group; even: byte 3
@@ -427,10 +447,11 @@ struct AmSsbTile {
           : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
           : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
   }
+  template <int IMM>
   __device__ __forceinline__ static void ldsm4(uint32_t addr, uint32_t (&r)[4]) {
-    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4+%5];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(addr)
+                 : "r"(addr), "n"(IMM)
                  : "memory");
   }
   // slot_s = shared address of the tile. Fills cu.s1a0 .. cu.s1b1; returns false, with cu
@@ -438,28 +459,51 @@ struct AmSsbTile {
   template <bool U8>
   __device__ __forceinline__ static bool stage1_mma(uint32_t slot_s, const Mma &mm, AmSsbCarry<SSB> &cu) {
     uint32_t z = 0;
+    const uint32_t e0 = slot_s + mm.even[0], e1 = slot_s + mm.even[1], o0 = slot_s + mm.odd[0], o1 = slot_s + mm.odd[1];
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      uint32_t a0[4], a1[4];
-      ldsm4(m == 0 && mm.hist_row ? mm.hist_row : slot_s + mm.off[2 * m], a0);
-      ldsm4(slot_s + mm.off[2 * m + 1], a1);
+    for (int half = 0; half < 2; ++half) {  // M-tiles 2 half, 2 half + 1 together: their IMMA chains interleave
+      uint32_t a[2][2][4];
+      if (half == 0) {
+        ldsm4<0>(mm.hist_row ? mm.hist_row : e0, a[0][0]);
+        ldsm4<0>(e1, a[0][1]);
+        ldsm4<0>(o0, a[1][0]);
+        ldsm4<0>(o1, a[1][1]);
+      } else {
+        ldsm4<1024>(e0, a[0][0]);
+        ldsm4<1024>(e1, a[0][1]);
+        ldsm4<1024>(o0, a[1][0]);
+        ldsm4<1024>(o1, a[1][1]);
+      }
+      int hi[2][4], lo[2][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        hi[m][0] = hi[m][2] = mm.c[0]; hi[m][1] = hi[m][3] = mm.c[1];
+        lo[m][0] = lo[m][2] = mm.c[2]; lo[m][1] = lo[m][3] = mm.c[3];
+      }
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk)
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          imma_data<U8>(hi[m], a[m][kk], mm.b[2 * kk], mm.b[2 * kk + 1]);
+          imma_data<U8>(lo[m], a[m][kk], mm.b[4 + 2 * kk], mm.b[4 + 2 * kk + 1]);
+        }
       if constexpr (U8) {  // the tile's own bytes are the k-step 1 fragments
 #pragma unroll
-        for (int i = 0; i < 4; ++i) z |= (a1[i] - 0x01010101u) & ~a1[i];
-      }
-      int hi[4] = {mm.c[0], mm.c[1], mm.c[0], mm.c[1]}, lo[4] = {mm.c[2], mm.c[3], mm.c[2], mm.c[3]};
-      imma_data<U8>(hi, a0, mm.b[0], mm.b[1]);
-      imma_data<U8>(lo, a0, mm.b[4], mm.b[5]);
-      imma_data<U8>(hi, a1, mm.b[2], mm.b[3]);
-      imma_data<U8>(lo, a1, mm.b[6], mm.b[7]);
-      // rows g (e = 0) and g + 8 (e = 1): two neighbouring outputs of half-window 16 m + g + 8 e;
-      // the int8 result is byte 2 of the doubled accumulator (see Doubled)
+        for (int m = 0; m < 2; ++m)
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const uint32_t acc0 = (uint32_t)((hi[2 * e] << 8) + lo[2 * e]), acc1 = (uint32_t)((hi[2 * e + 1] << 8) + lo[2 * e + 1]);
-        const uint32_t pair = __byte_perm(acc0, acc1, 0x0062);
-        asm volatile("st.shared.u16 [%0], %1;" ::"r"(mm.xst + 128 * m + 64 * e), "h"((uint16_t)pair) : "memory");
+          for (int i = 0; i < 4; ++i) z |= (a[m][1][i] - 0x01010101u) & ~a[m][1][i];
       }
+      // rows g (e = 0) and g + 8 (e = 1) of M-tile mt: two neighbouring outputs of half-window
+      // 16 mt + g + 8 e; the int8 result is byte 2 of the doubled accumulator (see Doubled)
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const uint32_t acc0 = (uint32_t)((hi[m][2 * e] << 8) + lo[m][2 * e]);
+          const uint32_t acc1 = (uint32_t)((hi[m][2 * e + 1] << 8) + lo[m][2 * e + 1]);
+          const uint32_t pair = __byte_perm(acc0, acc1, 0x0062);
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(mm.xst + 128 * (2 * half + m) + 64 * e), "h"((uint16_t)pair) : "memory");
+        }
     }
     if constexpr (U8) {
       if (__any_sync(FULL, (z & mm.zmask) != 0)) return false;
@@ -528,8 +572,9 @@ struct AmSsbTile {
 // tile; false: by four cp.async per lane (TileIo). A partial last tile takes cp.async either way.
 // NST = slot buffers per warp: NST - 1 tiles are in flight while one is computed.
 // MMA (with TMA only): stage 1 on the tensor cores (AmSsbTile::stage1_mma).
-template <bool SSB, bool TMA, int NST, bool MMA>
-__global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant__ LaunchParams p,
+// MINB = CTAs resident per SM the register budget is cut for (5: 96 registers, 6: 80).
+template <bool SSB, bool TMA, int NST, bool MMA, int MINB = 5>
+__global__ void __launch_bounds__(128, MINB) amssb_fir_kernel(const __grid_constant__ LaunchParams p,
                                                            const __grid_constant__ CUtensorMap tmap) {
   using T = AmSsbTile<SSB>;
   constexpr uint32_t WARMUP = T::WARMUP_TILES;
@@ -537,7 +582,9 @@ __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant
   extern __shared__ __align__(1024) uint4 smem_raw[];
   __shared__ uint64_t s_bar[4][NST];
   __shared__ uint4 s_mma[MMA ? 4 : 1][34];  // per warp: 32 bytes of raw history, 512 bytes of transpose buffer
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // the warp index through a shuffle: the compiler then knows that everything derived from it (the
+  // warp's share, its slot and barrier addresses, the TMA coordinates) is warp-uniform
+  const int lane = threadIdx.x & 31, warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);
   const uint32_t n_warps = p.aux;  // worker warps of the whole grid
   const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + warp;
   trace_begin(p);
@@ -569,7 +616,7 @@ __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant
     const uint32_t t0 = (uint32_t)(g0 - (uint64_t)li * n_tiles);
     const uint32_t t1 = (uint32_t)min((uint64_t)n_tiles, t0 + (g1 - g0));
     g0 += t1 - t0;
-    const uint32_t ch = p.chan_ids[li];
+    const uint32_t ch = __shfl_sync(FULL, p.chan_ids[li], 0);
     if (p.allowed && !p.allowed[ch]) continue;  // squelched: the demodulator is not called, its state stays
     const uint8_t *src = p.iq + (uint64_t)ch * p.ch_stride;
     uint32_t *blob = reinterpret_cast<uint32_t *>(p.state + (uint64_t)ch * p.state_stride);
@@ -614,7 +661,7 @@ __global__ void __launch_bounds__(128, 5) amssb_fir_kernel(const __grid_constant
     // tile `tt` goes to slot buffer `b`: TMA or cp.async for a full tile, cp.async for the partial one
     auto fetch = [&](uint32_t tt, uint32_t b) {
       if (tt < tf) {
-        if constexpr (TMA) { if (lane == 0) tio.issue(b, &tmap, tt, ch); }
+        if constexpr (TMA) { if (elect_one()) tio.issue(b, &tmap, tt, ch); }
         else io.fill_full(b * TILE_BYTES, g + (uint64_t)tt * TILE_BYTES);
       } else if (tt == tf && partial) {
         tile_fill(slots + b * TILE_BYTES, src + (uint64_t)tt * TILE_BYTES, lane, (int)(p.n_samples - tt * TILE) >> 3);
