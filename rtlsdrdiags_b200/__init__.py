@@ -53,7 +53,7 @@ def load_library(build_if_missing=True):
     if not os.path.exists(_build.LIB):
         raise SdrError("libsdr_b200.so is not built (run `python -m rtlsdrdiags_b200._build`); "
                        "there is no CPU fallback")
-    L = C.CDLL(_build.LIB)
+    L = C.CDLL(os.environ.get("SDR_B200_LIB") or _build.LIB)  # SDR_B200_LIB: an A/B build of the same library
     vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
     L.sdr_engine_create.argtypes = [u32, i32, u64, C.POINTER(vp)]
     L.sdr_engine_destroy.argtypes = [vp]
@@ -94,6 +94,7 @@ def load_library(build_if_missing=True):
     L.sdr_debug_set_dc_shape.argtypes = [vp, u32, u32]
     L.sdr_debug_dc_redo_count.argtypes = [vp, C.POINTER(u32)]
     L.sdr_debug_set_tile_loader.argtypes = [vp, i32]
+    L.sdr_debug_set_wbfm_kernel.argtypes = [vp, i32]
     L.sdr_bank_create.argtypes = [u32, C.POINTER(i32), u32, u64, u32, C.POINTER(vp)]
     L.sdr_bank_destroy.argtypes = [vp]
     L.sdr_bank_device_count.argtypes = [vp]
@@ -270,6 +271,11 @@ class Engine:
         """AM/SSB FIR kernel: full tiles by TMA (cp.async.bulk.tensor; True / 1 = default depth, 2..4 =
         that many slot buffers per warp) or by cp.async (False / 0)."""
         self._ck(self.L.sdr_debug_set_tile_loader(self.h, int(loader)))
+
+    def debug_set_wbfm_kernel(self, generation=0):
+        """WBFM kernel generation: 0 = default (3), 1 = table in global memory, 2 = table in shared
+        memory with one channel per worker warp, 3 = two channels per worker warp."""
+        self._ck(self.L.sdr_debug_set_wbfm_kernel(self.h, int(generation)))
 
     def debug_dc_redo_count(self):
         """Segments the recurrence kernel had to redo serially since the engine was created."""

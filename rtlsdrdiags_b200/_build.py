@@ -28,20 +28,21 @@ def is_stale():
     return any(os.path.getmtime(s) > t for s in sources())
 
 
-def build(force=False, defines=(), verbose=False):
-    """Compile the shared library if it is missing or older than its sources."""
+def build(force=False, defines=(), verbose=False, out=None):
+    """Compile the shared library if it is missing or older than its sources. `out`: another file
+    name for an A/B build with `defines` (load it with SDR_B200_LIB=<path>)."""
     if not force and not defines and not is_stale():
         return LIB
     cmd = [_nvcc()] + NVCC_FLAGS + ["-D%s" % d for d in defines]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += ["-o", LIB, os.path.join(CSRC, "sdr_engine.cu"), os.path.join(CSRC, "sdr_filter_bank.cu")]
+    cmd += ["-o", out or LIB, os.path.join(CSRC, "sdr_engine.cu"), os.path.join(CSRC, "sdr_filter_bank.cu")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), r.stderr))
     if verbose:
         print(r.stderr)
-    return LIB
+    return out or LIB
 
 
 HOST = os.path.join(PKG, "host")

@@ -58,6 +58,7 @@ struct sdr_engine {
   // IQ array, rebuilt when pointer, stride or length change) or by cp.async
   int tile_loader = 2;  // 0 = cp.async (two slot buffers), 2 / 3 / 4 = TMA with that many slot buffers
   bool stage1_mma = false;  // with TMA: stage 1 of the AM / SSB cascade on the tensor cores (measured slower)
+  int wb_kernel = 0;  // 0 = default (SDR_WB_KERNEL or 3), 1..3 = that generation of the WBFM kernel
   int fir_ctas_per_sm = 5;  // register budget of the FIR kernel: 5 (96 registers) or 6 (80) CTAs per SM
   uint32_t *d_am_tab = nullptr;  // am_mma_table()
   CUtensorMap tmap;
@@ -530,6 +531,50 @@ int launch_fm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_
   return SDR_OK;
 }
 
+// wbfm_tile3_kernel: two channels per worker warp, up to 28 channels per CTA behind one recurrence warp
+int launch_wbfm_tile3(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples, int fmt,
+                      cudaStream_t stream) {
+  using T = WbTile3;
+  const int kind = SDR_KIND_WBFM;
+  const uint32_t n_list = (uint32_t)e->list[kind].size();
+  // one CTA per SM (table and rings fill shared memory): spread the channels evenly over the waves,
+  // an even number of channels per CTA
+  const long max_g = 2 * T::MAX_WORKERS;
+  const long slots = e->n_sm;
+  const long W = ((long)n_list + slots * max_g - 1) / (slots * max_g);
+  uint32_t G = (uint32_t)(((long)n_list + slots * W - 1) / (slots * W));
+  if (e->shape[kind].G) G = e->shape[kind].G;
+  G = (G + 1) & ~1u;
+  if (G > (uint32_t)max_g) G = (uint32_t)max_g;
+  if (G < 2) G = 2;
+  const int workers = (int)G / 2;
+  const int smem = T::smem_bytes(workers);
+  LaunchParams p = {};
+  p.iq = iq;
+  p.ch_stride = ch_stride;
+  p.n_samples = n_samples;
+  p.fmt = fmt;
+  p.chan_ids = e->d_list[kind];
+  p.n_list = n_list;
+  p.G = G;
+  p.state = e->d_state[kind];
+  p.state_stride = (uint32_t)WbTile::STATE_BYTES;
+  p.scale = e->d_scale[kind];
+  p.lsb = e->d_lsb;
+  p.pcm = e->pcm_of(e->seq);
+  p.pcm_stride = e->pcm_stride;
+  p.lut = e->d_lut_wbfm_half;
+  p.aux = (uint32_t)std::min(workers, (int)T::REC_WARP);
+  p.scratch = nullptr;
+  p.allowed = e->last_gated ? e->d_allowed[e->seq % (uint64_t)e->ring] : nullptr;
+  SDR_CK(e, cudaFuncSetAttribute(wbfm_tile3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  const uint32_t grid = (n_list + G - 1) / G;
+  wbfm_tile3_kernel<<<grid, 32 * (workers + 1), smem, stream>>>(p);
+  SDR_CK(e, cudaGetLastError());
+  e->launches++;
+  return SDR_OK;
+}
+
 // wbfm_tile2_kernel: the atan2 half-plane table in shared memory, 15 channels per CTA
 int launch_wbfm_tile2(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples, int fmt,
                       cudaStream_t stream) {
@@ -581,9 +626,12 @@ int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint3
   const int kind = SDR_KIND_WBFM;
   const uint32_t n_list = (uint32_t)e->list[kind].size();
   if (n_list == 0) return SDR_OK;
-  // SDR_WB_KERNEL=1 selects the first-generation kernel (table gathered from global memory)
-  static const int gen_env = getenv("SDR_WB_KERNEL") ? atoi(getenv("SDR_WB_KERNEL")) : 2;
-  if (gen_env != 1 && e->d_lut_wbfm_half) return launch_wbfm_tile2(e, iq, ch_stride, n_samples, fmt, stream);
+  // SDR_WB_KERNEL=1 / 2 select the first- / second-generation kernel (1: table gathered from global
+  // memory; 2: one channel per worker warp); the default is the third (two channels per worker warp)
+  static const int gen_env = getenv("SDR_WB_KERNEL") ? atoi(getenv("SDR_WB_KERNEL")) : 3;
+  const int gen = e->wb_kernel ? e->wb_kernel : gen_env;
+  if (gen == 3 && e->d_lut_wbfm_half) return launch_wbfm_tile3(e, iq, ch_stride, n_samples, fmt, stream);
+  if (gen != 1 && e->d_lut_wbfm_half) return launch_wbfm_tile2(e, iq, ch_stride, n_samples, fmt, stream);
   // one CTA per SM (the rings fill shared memory): spread the channels evenly over the waves
   const long slots = e->n_sm;
   const long W = ((long)n_list + slots * T::MAX_WORKERS - 1) / (slots * T::MAX_WORKERS);
@@ -1042,6 +1090,14 @@ int sdr_debug_set_dc_shape(sdr_engine *e, uint32_t seg_count, uint32_t warm_rows
   if (!e || seg_count > 32 || (seg_count & (seg_count - 1))) return SDR_E_ARG;
   e->dc_seg_count = seg_count;
   e->dc_warm_rows = warm_rows;
+  return SDR_OK;
+}
+
+// which generation of the WBFM kernel runs (0 = default); the three share the carry blob, so a test
+// may switch between calls
+int sdr_debug_set_wbfm_kernel(sdr_engine *e, int generation) {
+  if (!e || generation < 0 || generation > 3) return SDR_E_ARG;
+  e->wb_kernel = generation;
   return SDR_OK;
 }
 

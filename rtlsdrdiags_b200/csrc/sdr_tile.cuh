@@ -24,6 +24,10 @@
 
 #if SDR_DEVICE_BUILD
 #include <cuda.h>  // CUtensorMap
+#ifndef SDR_FIR_UNROLL
+#define SDR_FIR_UNROLL 1  // tiles per trip of the AM / SSB FIR loop (A/B builds: -DSDR_FIR_UNROLL=2)
+#endif
+namespace sdr { constexpr int FIR_UNROLL = SDR_FIR_UNROLL; }
 namespace sdr {
 
 constexpr int TILE = 1024;             // complex samples per tile
@@ -225,7 +229,7 @@ struct AmSsbCarry {
   uint32_t a7, b7;            // last rotation group of the lane: I' and Q' words
   uint32_t s1a0, s1a1, s1b0, s1b1;  // the lane's eight stage-1 outputs per arm (int8 x 4)
   uint32_t p;                 // stage-2 outputs: I pair in bytes 0-1, Q pair in bytes 2-3
-  float dem;                  // the lane's demodulated value (AM magnitude / SSB phased sum)
+  int dem;                    // the lane's demodulated value (AM magnitude / SSB phased sum): a small integer
   int y3a, y3b;               // SSB: stage-3 outputs (delay line and Hilbert history)
 };
 
@@ -263,7 +267,7 @@ struct AmSsbTile {
     c.s1a0 = blob[2 * 32 + lane]; c.s1a1 = blob[3 * 32 + lane];
     c.s1b0 = blob[4 * 32 + lane]; c.s1b1 = blob[5 * 32 + lane];
     c.p = blob[6 * 32 + lane];
-    c.dem = u2f(blob[7 * 32 + lane]);
+    c.dem = (int)blob[7 * 32 + lane];
     if constexpr (SSB) { c.y3a = (int)blob[8 * 32 + lane]; c.y3b = (int)blob[9 * 32 + lane]; }
     else { c.y3a = 0; c.y3b = 0; }
   }
@@ -272,7 +276,7 @@ struct AmSsbTile {
     blob[2 * 32 + lane] = c.s1a0; blob[3 * 32 + lane] = c.s1a1;
     blob[4 * 32 + lane] = c.s1b0; blob[5 * 32 + lane] = c.s1b1;
     blob[6 * 32 + lane] = c.p;
-    blob[7 * 32 + lane] = f2u(c.dem);
+    blob[7 * 32 + lane] = (uint32_t)c.dem;
     if constexpr (SSB) { blob[8 * 32 + lane] = (uint32_t)c.y3a; blob[9 * 32 + lane] = (uint32_t)c.y3b; }
   }
 
@@ -350,7 +354,7 @@ struct AmSsbTile {
       // |y3| <= 128 * 48394 / 32768 < 190 for 8-bit input, so none of the reference's int16 casts
       // can bite and max + min/2 is the same whichever branch a tie takes
       const int im = iabs(cu.y3a), qm = iabs(cu.y3b);
-      cu.dem = i2f(max(im, qm) + (min(im, qm) >> 1));
+      cu.dem = max(im, qm) + (min(im, qm) >> 1);
     } else {
       // phasing network (SsbDemodulator.cc:569-590): delay line {0 x15, -32768}, Hilbert 31 taps
       const int x15 = shfl_prev(cu.y3a, pv.y3a, 15, lane);
@@ -361,10 +365,11 @@ struct AmSsbTile {
       int h = (1 << 14) + taps::SSB_HILBERT::tap(0) * cu.y3b;
       hilbert<2>(h, cu.y3b, pv.y3b, lane);
       const int q_shifted = (int)(int16_t)(h >> 15);
-      cu.dem = i2f(lsb ? i_delayed - q_shifted : i_delayed + q_shifted);
+      cu.dem = lsb ? i_delayed - q_shifted : i_delayed + q_shifted;
     }
-    // numerator of the DC-removal IIR, b = {1, -1}: fl(1*x[n] + (-1)*x[n-1]) (IirFilter.cc:164)
-    const int out = f2i_rz(fadd(cu.dem, fmul(-1.0f, shfl_prev(cu.dem, pv.dem, 1, lane))));
+    // numerator of the DC-removal IIR, b = {1, -1}: fl(1*x[n] + (-1)*x[n-1]) (IirFilter.cc:164). x is a
+    // small integer, so the float products and the sum are exact: the difference is taken in int
+    const int out = cu.dem - shfl_prev(cu.dem, pv.dem, 1, lane);
 
     // the last 32 lanes of the stream become the next tile's "previous" registers
     if (FULL_TILE || r == 32) {
@@ -631,7 +636,7 @@ __global__ void __launch_bounds__(128, MINB) amssb_fir_kernel(const __grid_const
       T::load_carry(pv, blob + cur * T::CARRY_WORDS, lane);
     } else {
       pv.a7 = pv.b7 = pv.s1a0 = pv.s1a1 = pv.s1b0 = pv.s1b1 = pv.p = 0;
-      pv.dem = 0.f;
+      pv.dem = 0;
       pv.y3a = pv.y3b = 0;
     }
     const bool lsb = SSB && p.lsb[ch] != 0;
@@ -674,6 +679,7 @@ __global__ void __launch_bounds__(128, MINB) amssb_fir_kernel(const __grid_const
       cp_async_commit();
     }
     uint32_t buf = 0;  // slot buffer of the tile being computed
+#pragma unroll FIR_UNROLL
     for (uint32_t t = tw; t < tf; ++t) {
       fetch(t + NST - 1, buf == 0 ? NST - 1 : buf - 1);  // where tile t - 1 was; every lane has read it
       cp_async_commit();
