@@ -416,7 +416,7 @@ int launch_dc_block(sdr_engine *e, int kind, uint32_t n_samples) {
   p.warm_rows = e->dc_warm_rows;
   p.counters = e->d_counters;
   const uint64_t lanes = (uint64_t)n_list * p.seg_count;
-  dc_block_kernel<<<(uint32_t)((lanes + 31) / 32), 32, 0, e->rec_stream>>>(p);
+  dc_block_kernel<<<(uint32_t)((lanes + 31) / 32), 64, 0, e->rec_stream>>>(p);
   SDR_CK(e, cudaGetLastError());
   e->launches++;
   return SDR_OK;
@@ -539,13 +539,16 @@ int launch_wbfm_tile3(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint
   const uint32_t n_list = (uint32_t)e->list[kind].size();
   // one CTA per SM (table and rings fill shared memory): spread the channels evenly over the waves,
   // an even number of channels per CTA
-  const long max_g = 2 * T::MAX_WORKERS;
+  // 12 workers = three per scheduler; with 13 or 14 two schedulers carry four and set the round's
+  // length (profiles/r02_wbfm3_ncu.txt)
+  static const int g_env = getenv("SDR_WB_G") ? atoi(getenv("SDR_WB_G")) : 0;  // tuning override
+  const long max_g = g_env ? g_env : 2 * 12;
   const long slots = e->n_sm;
   const long W = ((long)n_list + slots * max_g - 1) / (slots * max_g);
   uint32_t G = (uint32_t)(((long)n_list + slots * W - 1) / (slots * W));
   if (e->shape[kind].G) G = e->shape[kind].G;
   G = (G + 1) & ~1u;
-  if (G > (uint32_t)max_g) G = (uint32_t)max_g;
+  if (G > 2u * (uint32_t)T::MAX_WORKERS) G = 2u * (uint32_t)T::MAX_WORKERS;
   if (G < 2) G = 2;
   const int workers = (int)G / 2;
   const int smem = T::smem_bytes(workers);
@@ -629,7 +632,10 @@ int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint3
   // SDR_WB_KERNEL=1 / 2 select the first- / second-generation kernel (1: table gathered from global
   // memory; 2: one channel per worker warp); the default is the third (two channels per worker warp)
   static const int gen_env = getenv("SDR_WB_KERNEL") ? atoi(getenv("SDR_WB_KERNEL")) : 3;
-  const int gen = e->wb_kernel ? e->wb_kernel : gen_env;
+  // The third generation pays off once a bank needs more than one wave of one-channel-per-warp CTAs;
+  // below that (the WBFM share of a mixed bank) it would only halve the workers per CTA.
+  int gen = e->wb_kernel ? e->wb_kernel : gen_env;
+  if (!e->wb_kernel && gen == 3 && n_list <= (uint32_t)(WbTile2::MAX_WORKERS - 1) * (uint32_t)e->n_sm) gen = 2;
   if (gen == 3 && e->d_lut_wbfm_half) return launch_wbfm_tile3(e, iq, ch_stride, n_samples, fmt, stream);
   if (gen != 1 && e->d_lut_wbfm_half) return launch_wbfm_tile2(e, iq, ch_stride, n_samples, fmt, stream);
   // one CTA per SM (the rings fill shared memory): spread the channels evenly over the waves
@@ -1158,16 +1164,23 @@ int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_str
   // Bounded run-ahead. With hundreds of calls queued the driver's launch queues fill up and the
   // GPU is fed in bursts (profiles/r01v7_pacing.txt); holding the caller once RUN_AHEAD calls are
   // in flight keeps the queues shallow.
-  const int slot = (int)(e->seq % (uint64_t)sdr_engine::PACE);
-  if (e->seq >= (uint64_t)sdr_engine::RUN_AHEAD)
-    SDR_CK(e, cudaEventSynchronize(e->ev_pace[(int)((e->seq - (uint64_t)sdr_engine::RUN_AHEAD) % (uint64_t)sdr_engine::PACE)]));
+  // (An event every fourth call: the bound is then RUN_AHEAD .. RUN_AHEAD + 3 calls, and three of
+  // four calls queue one stream operation less.)
+  const int slot = (int)((e->seq / 4) % (uint64_t)sdr_engine::PACE);
+  if (e->seq % 4 == 0 && e->seq >= (uint64_t)sdr_engine::RUN_AHEAD)
+    SDR_CK(e, cudaEventSynchronize(e->ev_pace[(int)(((e->seq - (uint64_t)sdr_engine::RUN_AHEAD) / 4) % (uint64_t)sdr_engine::PACE)]));
   const int fmt = (flags & SDR_IQ_S8_ROTATED) ? FMT_S8_ROTATED : FMT_U8_OFFSET_ROTATE;
   const uint32_t n_samples = (uint32_t)(bytes / 2);
   const bool have_rec = !e->list[SDR_KIND_AM].empty() || !e->list[SDR_KIND_SSB].empty();
   const int par = (int)(e->seq % (uint64_t)e->ring);
   // scratch[par] and allowed[par] were last read by the recurrence kernels RING calls ago
-  if (have_rec || e->squelch_armed || e->signal_reports || e->squelch_dirty)
-    SDR_CK(e, cudaStreamWaitEvent(e->stream, e->ev_rec[par], 0));
+  // (usually long over: then no wait is queued at all)
+  if (have_rec || e->squelch_armed || e->signal_reports || e->squelch_dirty) {
+    if (cudaEventQuery(e->ev_rec[par]) != cudaSuccess) {
+      (void)cudaGetLastError();  // "not ready" is an answer, not an error to be found later
+      SDR_CK(e, cudaStreamWaitEvent(e->stream, e->ev_rec[par], 0));
+    }
+  }
   if ((rc = run_iq_dump(e, dev_iq, dev_stride, bytes, fmt))) return rc;
   if ((rc = run_squelch(e, dev_iq, dev_stride, bytes, fmt))) return rc;
   // WBFM first, and beside the others when there are others: its CTAs (one per SM for the whole
@@ -1195,7 +1208,7 @@ int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_str
   e->rec_pending = true;
   if ((rc = launch_fm_tile(e, dev_iq, dev_stride, n_samples, fmt))) return rc;
   if (!wb_beside && (rc = launch_wbfm_tile(e, dev_iq, dev_stride, n_samples, fmt, e->stream))) return rc;
-  SDR_CK(e, cudaEventRecord(e->ev_pace[slot], e->stream));
+  if (e->seq % 4 == 0) SDR_CK(e, cudaEventRecord(e->ev_pace[slot], e->stream));
   e->seq++;
   e->last_samples = (uint32_t)(bytes / 64);
   return SDR_OK;

@@ -25,9 +25,15 @@
 #if SDR_DEVICE_BUILD
 #include <cuda.h>  // CUtensorMap
 #ifndef SDR_FIR_UNROLL
-#define SDR_FIR_UNROLL 1  // tiles per trip of the AM / SSB FIR loop (A/B builds: -DSDR_FIR_UNROLL=2)
+// Tiles per trip of the AM / SSB FIR loop. Two: the "previous tile" registers need no copying (the
+// roles alternate) and stage 1 of one tile overlaps the shuffle chains of the other: AM x1024
+// 0.1238 -> 0.1190 ms per step, SSB x8192 0.1453 -> 0.1374 (profiles/r02_am_fir_variants.txt).
+#define SDR_FIR_UNROLL 2
 #endif
-namespace sdr { constexpr int FIR_UNROLL = SDR_FIR_UNROLL; }
+#ifndef SDR_FM_UNROLL
+#define SDR_FM_UNROLL 1  // tiles per trip of the NBFM loop (A/B builds)
+#endif
+namespace sdr { constexpr int FIR_UNROLL = SDR_FIR_UNROLL, FM_UNROLL = SDR_FM_UNROLL; }
 namespace sdr {
 
 constexpr int TILE = 1024;             // complex samples per tile
@@ -771,51 +777,25 @@ __global__ void __launch_bounds__(128, MINB) amssb_fir_kernel(const __grid_const
 //     then the comparison is repeated -- the serial order, paid only where it is needed.
 // The chain per call is warm_rows + seg_rows rows long instead of all rows.
 //
-// One CTA = ONE warp, and the warp does everything for its 32 lanes: a row of numerators is 64
+// One CTA = TWO warps over the same 32 lanes. Warp 0 is the CHAIN warp: a row of numerators is 64
 // contiguous bytes per lane (int16, [list entry][row][32]), fetched DC_PF rows ahead by cp.async into
-// the lane's own ring in shared memory (an L2 round trip is several rows of chain long; a lane only
-// ever reads what it fetched itself, so nothing synchronises), then the 32 dependent FMUL -> FSUB
-// pairs, gain, (int16_t) and the row's 64 bytes of PCM. At 32 threads and under 128 registers a
-// CTA fits beside the five resident CTAs of the next call's FIR kernel without taking one's place
-// (profiles/r02_am_timeline.txt).
+// the lane's own ring in shared memory (an L2 round trip is several rows of chain long), then the 32
+// dependent FMUL -> FSUB pairs, and the row's 32 y into a double-buffered row in shared memory --
+// nothing else, because whatever else the warp issued would sit between the chain's dependent
+// instructions (the first version converted and stored in the same warp: 1500 cycles per row against
+// ~350, the float -> int conversions queue on the quarter-rate XU pipe; profiles/r02_dc_block_ncu.txt).
+// Warp 1 is the CONVERTER, one row behind: gain, (int16_t) and the row's 64 bytes of PCM. One
+// CTA barrier per row. At 64 threads x 64 registers a CTA fits beside the five resident CTAs of the
+// next call's FIR kernel without taking one's place.
 constexpr int DC_PF = 8;             // rows in flight per lane
 constexpr int DC_LANE_PITCH = 80;    // 64 + 16: lane-per-row 128-bit reads are bank-conflict free
 constexpr int DC_STAGE_BYTES = 32 * DC_LANE_PITCH;
+constexpr int DC_Y_PITCH = 144;      // 128 + 16, ditto
+constexpr int DC_Y_BYTES = 32 * DC_Y_PITCH;
 
 struct DcRows {
   uint32_t begin, store, end;  // rows [begin, end) are run, PCM is kept from row `store` on
 };
-
-// one full row of one lane: 32 steps of the chain; KEEP: also gain, (int16_t) and the row's PCM
-template <bool KEEP>
-__device__ __forceinline__ void dc_row(const uint32_t (&w)[16], float &y, float a1, float gain, bool no_patch, bool keep,
-                                       int16_t *dst) {
-  uint32_t o[16];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float d0 = i2f((int)(int16_t)(w[2 * j] & 0xffffu)), d1 = i2f((int)w[2 * j] >> 16);
-    const float d2 = i2f((int)(int16_t)(w[2 * j + 1] & 0xffffu)), d3 = i2f((int)w[2 * j + 1] >> 16);
-    const float y0 = fsub(d0, fmul(a1, y));
-    const float y2 = fsub(d1, fmul(a1, y0));
-    const float y3 = fsub(d2, fmul(a1, y2));
-    y = fsub(d3, fmul(a1, y3));
-    if constexpr (KEEP) {
-      if (no_patch) {
-        o[2 * j] = __byte_perm((uint32_t)f2i_rz(fmul(gain, y0)), (uint32_t)f2i_rz(fmul(gain, y2)), 0x5410);
-        o[2 * j + 1] = __byte_perm((uint32_t)f2i_rz(fmul(gain, y3)), (uint32_t)f2i_rz(fmul(gain, y)), 0x5410);
-      } else {
-        o[2 * j] = f2i16x2_wrap(fmul(gain, y0), fmul(gain, y2));
-        o[2 * j + 1] = f2i16x2_wrap(fmul(gain, y3), fmul(gain, y));
-      }
-    }
-  }
-  if constexpr (KEEP) {
-    if (keep) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) stg_u4(dst + 8 * j, u32x4{o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]});
-    }
-  }
-}
 
 // the lane's 64 bytes of row `g` into its place in ring stage `stage_s` (shared address)
 __device__ __forceinline__ void dc_fetch_row(uint32_t stage_s, const int16_t *g) {
@@ -827,9 +807,10 @@ __device__ __forceinline__ void dc_fetch_row(uint32_t stage_s, const int16_t *g)
       : "memory");
 }
 
-__global__ void __launch_bounds__(32) dc_block_kernel(const __grid_constant__ LaunchParams p) {
+__global__ void __launch_bounds__(64, 16) dc_block_kernel(const __grid_constant__ LaunchParams p) {
   trace_begin(p);
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const bool chain = threadIdx.x < 32;
   const uint32_t S = p.seg_count, Lr = p.seg_rows;       // S: power of two <= 32
   const uint32_t idx = blockIdx.x * 32u + (uint32_t)lane;
   const uint32_t li = idx / S, s = idx & (S - 1);
@@ -849,6 +830,13 @@ __global__ void __launch_bounds__(32) dc_block_kernel(const __grid_constant__ La
   // gain * y can reach 2^31, where cvt.rzi saturates but x86 cvttss2si wraps
   const bool no_patch = __all_sync(FULL, !valid || (fabsf(gain) < 500.f && fabsf(carried) < 2e6f));
 
+  __shared__ uint4 s_ring[DC_PF * DC_STAGE_BYTES / 16];
+  __shared__ uint4 s_y[2 * DC_Y_BYTES / 16];
+  __shared__ uint32_t s_begin[32];  // per pass: row the lane starts at, or ~0u if it sits the pass out
+  __shared__ uint32_t s_more;       // another pass follows
+  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(s_ring) + (uint32_t)lane * DC_LANE_PITCH;
+  char *ybuf = reinterpret_cast<char *>(s_y) + lane * DC_Y_PITCH;
+
   DcRows rw;
   rw.store = s * Lr;
   rw.end = min(rw.store + Lr, n_rows);
@@ -858,88 +846,135 @@ __global__ void __launch_bounds__(32) dc_block_kernel(const __grid_constant__ La
   bool todo = valid, redo = false;
   float y_in = y, y_end = y;   // state on entering row `store`; state after row end - 1
 
-  __shared__ uint4 s_ring[DC_PF * DC_STAGE_BYTES / 16];
-  const uint32_t ring_s = (uint32_t)__cvta_generic_to_shared(s_ring) + (uint32_t)lane * DC_LANE_PITCH;
-
   for (;;) {
-    // ---- run rows [begin, end) of the lanes in `todo`, DC_PF rows in flight ----
-    const uint32_t trips = __reduce_max_sync(FULL, todo ? rw.end - rw.begin : 0u);
+    // ---- both warps learn which lanes run this pass and from which row ----
+    if (chain) s_begin[lane] = todo ? rw.begin : ~0u;
+    __syncthreads();
+    const uint32_t begin = s_begin[lane];
+    const bool on = begin != ~0u;
+    const uint32_t trips = __reduce_max_sync(FULL, on ? rw.end - begin : 0u);
+
+    if (chain) {
 #pragma unroll
-    for (int k = 0; k < DC_PF - 1; ++k) {
-      if (todo && rw.begin + k < rw.end) dc_fetch_row(ring_s + k * DC_STAGE_BYTES, src + (uint64_t)(rw.begin + k) * 32);
-      cp_async_commit();
+      for (int k = 0; k < DC_PF - 1; ++k) {
+        if (on && begin + k < rw.end) dc_fetch_row(ring_s + k * DC_STAGE_BYTES, src + (uint64_t)(begin + k) * 32);
+        cp_async_commit();
+      }
     }
-    {
-      uint32_t stage = 0;  // ring stage of the row being run
-      for (uint32_t it = 0; it < trips; ++it) {
-        const uint32_t row = rw.begin + it;
-        const bool act = todo && row < rw.end;
-        {  // row + DC_PF - 1 goes where row - 1 was
-          const uint32_t ahead = stage == 0 ? DC_PF - 1 : stage - 1;
-          if (todo && row + DC_PF - 1 < rw.end)
-            dc_fetch_row(ring_s + ahead * DC_STAGE_BYTES, src + (uint64_t)(row + DC_PF - 1) * 32);
-          cp_async_commit();
-        }
-        cp_async_wait<DC_PF - 1>();  // this lane's copy of `row` has landed
-        uint32_t w[16];
+    uint32_t stage = 0;  // ring stage of the row being run
+    // iteration `it`: the chain warp runs row begin + it, the converter row begin + it - 1
+    for (uint32_t it = 0; it <= trips; ++it) {
+      if (chain) {
+        const uint32_t row = begin + it;
+        const bool act = on && row < rw.end;
+        if (it < trips) {
+          {  // row + DC_PF - 1 goes where row - 1 was
+            const uint32_t ahead = stage == 0 ? DC_PF - 1 : stage - 1;
+            if (on && row + DC_PF - 1 < rw.end)
+              dc_fetch_row(ring_s + ahead * DC_STAGE_BYTES, src + (uint64_t)(row + DC_PF - 1) * 32);
+            cp_async_commit();
+          }
+          cp_async_wait<DC_PF - 1>();  // this lane's copy of `row` has landed
+          uint32_t w[16];
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                       : "=r"(w[4 * j]), "=r"(w[4 * j + 1]), "=r"(w[4 * j + 2]), "=r"(w[4 * j + 3])
-                       : "r"(ring_s + stage * DC_STAGE_BYTES + 16 * j)
-                       : "memory");
-        stage = stage + 1 == DC_PF ? 0 : stage + 1;
-        if (act && row == rw.store) y_in = y;
-        const bool keep = act && row >= rw.store;
-        int16_t *dst = out + (uint64_t)row * 32;
-        const uint32_t left = n_pcm - row * 32u;  // the call's last row may hold fewer than 32 samples
-        const bool part = act && left < 32u;
-        if (__any_sync(FULL, part)) {
-          if (act) {
-            const uint32_t r = min(left, 32u);
+          for (int j = 0; j < 4; ++j)
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(w[4 * j]), "=r"(w[4 * j + 1]), "=r"(w[4 * j + 2]), "=r"(w[4 * j + 3])
+                         : "r"(ring_s + stage * DC_STAGE_BYTES + 16 * j)
+                         : "memory");
+          stage = stage + 1 == DC_PF ? 0 : stage + 1;
+          if (act && row == rw.store) y_in = y;
+          const bool keep = act && row >= rw.store;
+          const uint32_t left = n_pcm - row * 32u;  // the call's last row may hold fewer than 32 samples
+          const uint32_t r = act ? min(left, 32u) : 0u;
+          char *yrow = ybuf + (it & 1) * DC_Y_BYTES;
+          if (__any_sync(FULL, act && r < 32u)) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int dd[2] = {(int)(int16_t)(w[j] & 0xffffu), (int)w[j] >> 16};
 #pragma unroll
               for (int i = 0; i < 2; ++i) {
-                if ((uint32_t)(2 * j + i) < r) {
-                  y = fsub(i2f(dd[i]), fmul(a1, y));
-                  if (keep) dst[2 * j + i] = (int16_t)f2i16_wrap(fmul(gain, y));
-                }
+                if ((uint32_t)(2 * j + i) < r) y = fsub(i2f(dd[i]), fmul(a1, y));
+                if (keep) sts<float>(yrow + 4 * (2 * j + i), y);
               }
             }
+          } else if (act) {
+            const bool any_keep = keep;  // the converter reads the row only where it keeps it
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float d0 = i2f((int)(int16_t)(w[2 * j] & 0xffffu)), d1 = i2f((int)w[2 * j] >> 16);
+              const float d2 = i2f((int)(int16_t)(w[2 * j + 1] & 0xffffu)), d3 = i2f((int)w[2 * j + 1] >> 16);
+              const float y0 = fsub(d0, fmul(a1, y));
+              const float y2 = fsub(d1, fmul(a1, y0));
+              const float y3 = fsub(d2, fmul(a1, y2));
+              y = fsub(d3, fmul(a1, y3));
+              if (any_keep) sts_u4(yrow + 16 * j, u32x4{f2u(y0), f2u(y2), f2u(y3), f2u(y)});
+            }
           }
-        } else if (__any_sync(FULL, keep)) {
-          if (act) dc_row<true>(w, y, a1, gain, no_patch, keep, dst);
-        } else {
-          if (act) dc_row<false>(w, y, a1, gain, no_patch, false, dst);  // warm-up rows: the chain alone
+        }
+      } else if (it >= 1) {
+        const uint32_t row = begin + it - 1;
+        const bool keep = on && row < rw.end && row >= rw.store;
+        if (keep) {
+          const uint32_t r = min(n_pcm - row * 32u, 32u);
+          const char *yrow = ybuf + ((it - 1) & 1) * DC_Y_BYTES;
+          int16_t *dst = out + (uint64_t)row * 32;
+          u32x4 v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = lds_u4(yrow + 16 * j);
+          uint32_t o[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float g0 = fmul(gain, u2f(v[j].x)), g1 = fmul(gain, u2f(v[j].y));
+            const float g2 = fmul(gain, u2f(v[j].z)), g3 = fmul(gain, u2f(v[j].w));
+            if (no_patch) {
+              o[2 * j] = __byte_perm((uint32_t)f2i_rz(g0), (uint32_t)f2i_rz(g1), 0x5410);
+              o[2 * j + 1] = __byte_perm((uint32_t)f2i_rz(g2), (uint32_t)f2i_rz(g3), 0x5410);
+            } else {
+              o[2 * j] = f2i16x2_wrap(g0, g1);
+              o[2 * j + 1] = f2i16x2_wrap(g2, g3);
+            }
+          }
+          if (r == 32u) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) stg_u4(dst + 8 * j, u32x4{o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]});
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if ((uint32_t)j < r) dst[j] = (int16_t)(o[j >> 1] >> (16 * (j & 1)));
+          }
         }
       }
-      cp_async_wait<0>();
+      __syncthreads();
     }
-    if (todo) {
-      y_end = y;
-      exact = exact || redo;  // a redo starts from its predecessor's final state
-    }
+    if (chain) cp_async_wait<0>();
 
-    // ---- verify: lane s entered its rows in the state lane s - 1 left them in ----
-    const float prev_end = __shfl_up_sync(FULL, y_end, 1);
-    const bool bad = valid && !exact && f2u(y_in) != f2u(prev_end);
-    const uint32_t bad_mask = __ballot_sync(FULL, bad);
-    if (bad_mask == 0) break;
-    // The first bad segment of each channel is redone from its predecessor's state, which is
-    // final (every segment before it verified). Later bad ones wait: their predecessors may change.
-    const uint32_t ch_lanes = S >= 32 ? 0xffffffffu : ((1u << S) - 1u) << ((uint32_t)lane & ~(S - 1));
-    const bool first = bad && (bad_mask & ch_lanes & ((1u << lane) - 1u)) == 0;
-    if (first && p.counters) atomicAdd(p.counters, 1u);
-    todo = redo = first;
-    if (first) {
-      rw.begin = rw.store;
-      y = prev_end;
-      y_in = prev_end;
+    // ---- the chain warp verifies: lane s entered its rows in the state lane s - 1 left them in ----
+    if (chain) {
+      if (todo) {
+        y_end = y;
+        exact = exact || redo;  // a redo starts from its predecessor's final state
+      }
+      const float prev_end = __shfl_up_sync(FULL, y_end, 1);
+      const bool bad = valid && !exact && f2u(y_in) != f2u(prev_end);
+      const uint32_t bad_mask = __ballot_sync(FULL, bad);
+      // The first bad segment of each channel is redone from its predecessor's state, which is
+      // final (every segment before it verified). Later bad ones wait: their predecessors may change.
+      const uint32_t ch_lanes = S >= 32 ? 0xffffffffu : ((1u << S) - 1u) << ((uint32_t)lane & ~(S - 1));
+      const bool first = bad && (bad_mask & ch_lanes & ((1u << lane) - 1u)) == 0;
+      if (first && p.counters) atomicAdd(p.counters, 1u);
+      todo = redo = first;
+      if (first) {
+        rw.begin = rw.store;
+        y = prev_end;
+        y_in = prev_end;
+      }
+      if (lane == 0) s_more = bad_mask;
     }
+    __syncthreads();
+    if (s_more == 0) break;
   }
-  if (valid && rw.end == n_rows) tail[1] = y_end;
+  if (chain && valid && rw.end == n_rows) tail[1] = y_end;
   trace_end(p);
 }
 
@@ -1345,6 +1380,7 @@ __global__ void __launch_bounds__(128, MIN_CTAS) fm_tile_kernel(const __grid_con
     if (tw < tf) io.fill_full(off, g);
     else tile_fill(buf0 + off, g - 16 * lane, lane, (int)(p.n_samples - tw * TILE) >> 3);
     cp_async_commit();
+#pragma unroll FM_UNROLL
     for (uint32_t t = tw; t < t1; ++t) {
       const uint32_t nxt = FM_BUF_STRIDE - off;
       g += TILE_BYTES;
