@@ -180,6 +180,46 @@ def run_cpu_reference(workload, modes_np, n_blocks, seconds_target=6.0, signal="
     return msps, desc
 
 
+def capture_baseline(seconds_target=3.0):
+    """BASELINE.json's config 1: FM demodulation of a capture through the reference's FmDemodulator
+    chain on the CPU (demod.cc:200-323: signed, rotated int8 IQ in 16384-byte reads). The capture it
+    names (demodulatorResearch/f135_4.iq) is absent from the reference mount; the stand-in is the
+    committed 64 KiB excerpt of demodulatorResearch/yoyo.iq (tests/golden/golden_capture_v1.npz),
+    played 32 times in a row (2 MiB, the size of yoyo.iq). One host thread, as demod.cc runs. The GPU
+    engine demodulates the same stream and must return the same PCM."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_binding as O
+    import rtlsdrdiags_b200 as R
+    path = os.path.join(ROOT, "tests", "golden", "golden_capture_v1.npz")
+    if not os.path.exists(path):
+        return None
+    s8 = np.tile(np.load(path)["iq_s8"], 32)
+    use_ref = O.ref("research") is not None
+    done, elapsed, reps, pcm = 0, 0.0, 0, None
+    while elapsed < seconds_target and reps < 200:
+        t0 = time.perf_counter()
+        if use_ref:
+            d = O.RefDemod(O.KIND_FM, "research")
+            pcm = d.accept(s8, block=16384)
+        else:
+            pcm = O.OracleChain(O.VARIANT_RESEARCH).accept_s8(O.MODE_FM, s8)
+        elapsed += time.perf_counter() - t0
+        done += s8.size // 2
+        reps += 1
+    eng = R.Engine(1, 0, 16384)
+    eng.set_scaling(R.SCALING_RESEARCH)
+    eng.set_mode(0, R.MODE_FM)
+    got, _ = eng.demodulate(s8.reshape(1, -1), fmt=R.IQ_S8_ROTATED)
+    eng.close()
+    return {"value": round(done / elapsed / 1e6, 3), "unit": "Msamples/s", "cores": 1,
+            "kind": "reference" if use_ref else "port",
+            "sample": "FM, 64 KiB excerpt of demodulatorResearch/yoyo.iq x 32 (stand-in for the absent f135_4.iq), "
+                      "16384-byte reads, %d repetitions, 1 host thread" % reps,
+            "realtime_factor": round(done / elapsed / 256000.0, 1),
+            "gpu_pcm_identical": bool(np.array_equal(got[0], pcm))}
+
+
 def shard_parity(R, synth, workload, channels, first_channel, n_blocks, device_index, signal, seed):
     """This rank's shard against the CPU chain (oracle/_ref, the compiled reference, when it was
     built): a sample of the shard's channels, two passes of the bench's own call shape (n_blocks
@@ -525,6 +565,8 @@ def main():
         _, cpu = run_cpu_reference(workload, modes, n_blocks, seconds_target=12.0 if world == 1 else 4.0,
                                    signal=args.signal, check_gpu=True)
 
+    config1 = capture_baseline() if rank == 0 and world == 1 and not args.no_cpu else None
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": "Msamples/s",
@@ -556,6 +598,7 @@ def main():
             "parity": {"gpu_pcm_identical": all(per_rank), "per_rank": per_rank, **parity_desc,
                        "recurrence_segments_redone_in_timed_region": res["dc_redo"]},
             "cpu_baseline": cpu,
+            "cpu_baseline_config1_capture": config1,
             "am_weak": am_weak,
             "other_workloads": extras,
         }

@@ -126,6 +126,10 @@ struct sdr_engine {
   uint32_t last_samples = 0;  // PCM samples per channel of the last accept
   uint64_t launches = 0;
   std::string err;
+  // a call failed after part of its work was queued: events, ring slots and carried state are no
+  // longer in step, so every later data-path call returns this error again
+  bool poisoned = false;
+  std::string poison_text;
 };
 
 namespace {
@@ -539,10 +543,10 @@ int launch_wbfm_tile3(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint
   const uint32_t n_list = (uint32_t)e->list[kind].size();
   // one CTA per SM (table and rings fill shared memory): spread the channels evenly over the waves,
   // an even number of channels per CTA
-  // 12 workers = three per scheduler; with 13 or 14 two schedulers carry four and set the round's
-  // length (profiles/r02_wbfm3_ncu.txt)
+  // (24 or 26 channels per CTA -- three workers on every scheduler -- were measured and lost:
+  // 0.909 ms against 0.783 for WBFM x8192, profiles/r02_wbfm_generations.txt)
   static const int g_env = getenv("SDR_WB_G") ? atoi(getenv("SDR_WB_G")) : 0;  // tuning override
-  const long max_g = g_env ? g_env : 2 * 12;
+  const long max_g = g_env ? g_env : 2 * T::MAX_WORKERS;
   const long slots = e->n_sm;
   const long W = ((long)n_list + slots * max_g - 1) / (slots * max_g);
   uint32_t G = (uint32_t)(((long)n_list + slots * W - 1) / (slots * W));
@@ -1139,8 +1143,36 @@ int sdr_debug_dc_redo_count(sdr_engine *e, uint32_t *count) {
   return SDR_OK;
 }
 
+}  // extern "C"
+
+namespace {
+int accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_stride, uint32_t flags);
+int poisoned(sdr_engine *e) {
+  e->err = "the engine is in a failed state after: " + e->poison_text;
+  return SDR_E_CUDA;
+}
+}  // namespace
+
+extern "C" {
+
 int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_stride, uint32_t flags) {
   if (!e || !iq) return SDR_E_ARG;
+  if (e->poisoned) return poisoned(e);
+  const uint64_t launches_before = e->launches;
+  const int rc = accept_iq(e, iq, bytes, ch_stride, flags);
+  // an argument error queues nothing and leaves the engine usable; a failure after the first
+  // launch leaves ring slots and events half used
+  if (rc != SDR_OK && (rc == SDR_E_CUDA || e->launches != launches_before)) {
+    e->poisoned = true;
+    e->poison_text = e->err;
+  }
+  return rc;
+}
+
+}  // extern "C"
+
+namespace {
+int accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_stride, uint32_t flags) {
   if (bytes == 0 || bytes % 64) return fail(e, SDR_E_ARG, "bytes_per_channel must be a positive multiple of 64");
   if (bytes > e->max_bytes) return fail(e, SDR_E_TOO_LONG, "bytes_per_channel exceeds max_bytes_per_channel");
   if (ch_stride < bytes || ch_stride % 16 || ((uintptr_t)iq & 15))
@@ -1213,9 +1245,13 @@ int sdr_accept_iq(sdr_engine *e, const void *iq, uint64_t bytes, uint64_t ch_str
   e->last_samples = (uint32_t)(bytes / 64);
   return SDR_OK;
 }
+}  // namespace
+
+extern "C" {
 
 int sdr_get_pcm(sdr_engine *e, int16_t *pcm, uint32_t *counts) {
   if (!e) return SDR_E_ARG;
+  if (e->poisoned) return poisoned(e);
   SDR_CK(e, cudaSetDevice(e->device));
   {
     int rc = join_streams(e);

@@ -65,6 +65,44 @@ constexpr uint32_t FB_SMEM_WORDS = 11 * 1024;  // 44 KB: under the 48 KB a kerne
 
 }  // namespace
 
+// The launch plan of a bank: the tile (outputs per CTA), the staged span and the shared memory it
+// takes. One function for sdr_filter_bank_create, which refuses taps / factor combinations that no
+// tile can serve, and for sdr_filter_bank_run.
+static size_t fb_plan(const sdr_filter_bank *b, FilterBankParams &p, uint32_t &tile) {
+  // tile: as many outputs (<= 2048) as the staged span fits next to the taps
+  const uint32_t M = b->interp ? 1 : b->F;
+  const uint32_t budget = FB_SMEM_WORDS - b->N - 64;
+  if (b->interp) {
+    uint32_t ti = 2048 / b->F;
+    if (ti < 1) ti = 1;
+    while (ti > 1 && ti + b->q - 1 > budget) ti /= 2;
+    tile = ti * b->F;
+    p.span = ti + b->q - 1;
+    p.pitch = p.span;
+  } else {
+    tile = 2048;
+    while (tile > 32 && (uint64_t)M * (tile - 1) + b->N + 3 * 32 * M > budget) tile /= 2;
+    p.span = M * (tile - 1) + b->N;
+    // phases land in different banks when the staging loop writes 32 consecutive samples; the eight
+    // extra words are what the 16-byte window loads of the float M = 2, 4 path may read past the data
+    p.pitch = ((p.span + M - 1) / M + 8 + 31) / 32 * 32 + ((32 % M) == 0 && M > 1 ? 32 / M : (M > 1 ? 1 : 0));
+  }
+  // decimators with M = 2, 4: taps above the highest full block of four a-values (see the kernel)
+  p.kp = 0;
+  p.hoff = 0;
+  if (!b->interp && (M == 2 || M == 4)) {
+    const uint32_t a_top = (b->N - 1) / M, ph_top = (b->N - 1) % M;
+    const int a_full = (ph_top == M - 1) ? (int)a_top : (int)a_top - 1;  // largest a with every phase present
+    const int n_blocks = a_full >= 3 ? (a_full + 1) / 4 : 0;
+    p.kp = b->N - (uint32_t)n_blocks * 4 * M;
+    p.hoff = (4 - p.kp % 4) % 4;
+  }
+  p.np = (p.hoff + b->N + 3) / 4 * 4;
+  p.tile_out = tile;
+  const size_t smem = (size_t)4 * p.np + (size_t)(b->interp ? p.span : (size_t)M * p.pitch) * b->esize + 16;
+  return smem;
+}
+
 extern "C" {
 
 int sdr_filter_bank_create(int device, int kind, uint32_t n_rows, const float *taps, uint32_t n_taps,
@@ -94,6 +132,14 @@ int sdr_filter_bank_create(int device, int kind, uint32_t n_rows, const float *t
   b->esize = b->i16 ? 2 : 4;
   b->q = interp ? n_taps / factor : n_taps;
   b->C = interp ? b->q - 1 : (n_taps - 1) + (factor - 1);
+  {  // the plan sdr_filter_bank_run will use must fit the shared memory a kernel gets without opt-in
+    FilterBankParams plan;
+    uint32_t tile = 0;
+    if (fb_plan(b, plan, tile) > 48 * 1024) {
+      delete b;
+      return fb_fail(nullptr, SDR_E_ARG, "n_taps and factor need a tile that does not fit in 48 KB of shared memory");
+    }
+  }
   cudaError_t ce = cudaStreamCreateWithFlags(&b->own_stream, cudaStreamNonBlocking);
   if (ce != cudaSuccess) { delete b; return fb_fail(nullptr, SDR_E_CUDA, "cudaStreamCreate", ce); }
   b->stream = b->own_stream;
@@ -225,38 +271,8 @@ int sdr_filter_bank_run(sdr_filter_bank *b, const void *in, uint64_t in_stride, 
   p.C = b->C;
   p.pending = b->pending;
   p.sum_abs_taps = b->sum_abs_q15;
-  // tile: as many outputs (<= 2048) as the staged span fits next to the taps
-  const uint32_t M = b->interp ? 1 : b->F;
-  const uint32_t budget = FB_SMEM_WORDS - b->N - 64;
   uint32_t tile;
-  if (b->interp) {
-    uint32_t ti = 2048 / b->F;
-    if (ti < 1) ti = 1;
-    while (ti > 1 && ti + b->q - 1 > budget) ti /= 2;
-    tile = ti * b->F;
-    p.span = ti + b->q - 1;
-    p.pitch = p.span;
-  } else {
-    tile = 2048;
-    while (tile > 32 && (uint64_t)M * (tile - 1) + b->N + 3 * 32 * M > budget) tile /= 2;
-    p.span = M * (tile - 1) + b->N;
-    // phases land in different banks when the staging loop writes 32 consecutive samples; the eight
-    // extra words are what the 16-byte window loads of the float M = 2, 4 path may read past the data
-    p.pitch = ((p.span + M - 1) / M + 8 + 31) / 32 * 32 + ((32 % M) == 0 && M > 1 ? 32 / M : (M > 1 ? 1 : 0));
-  }
-  // decimators with M = 2, 4: taps above the highest full block of four a-values (see the kernel)
-  p.kp = 0;
-  p.hoff = 0;
-  if (!b->interp && (M == 2 || M == 4)) {
-    const uint32_t a_top = (b->N - 1) / M, ph_top = (b->N - 1) % M;
-    const int a_full = (ph_top == M - 1) ? (int)a_top : (int)a_top - 1;  // largest a with every phase present
-    const int n_blocks = a_full >= 3 ? (a_full + 1) / 4 : 0;
-    p.kp = b->N - (uint32_t)n_blocks * 4 * M;
-    p.hoff = (4 - p.kp % 4) % 4;
-  }
-  p.np = (p.hoff + b->N + 3) / 4 * 4;
-  p.tile_out = tile;
-  const size_t smem = (size_t)4 * p.np + (size_t)(b->interp ? p.span : (size_t)M * p.pitch) * b->esize + 16;
+  const size_t smem = fb_plan(b, p, tile);
   if (smem > 48 * 1024) return fb_fail(b, SDR_E_ARG, "tile does not fit in shared memory");
   const uint64_t tiles = n_out ? (n_out + tile - 1) / tile : 1;
   if (tiles > 0x7fffffffull) return fb_fail(b, SDR_E_TOO_LONG, "too many tiles");

@@ -152,3 +152,17 @@ def test_q15_decimator_block_path_edges(factor):
         for r in range(rows):
             exp = O.Multirate(3, taps, factor).run(x[r])
             assert got[r].tobytes() == exp.tobytes(), (factor, n_taps, r)
+
+
+def test_create_refuses_what_no_tile_can_serve():
+    """A bank whose taps and factor need more shared memory than any tile leaves is refused when it
+    is created, not at its first run (create and run share one launch plan)."""
+    import rtlsdrdiags_b200 as R
+    for kind, n_taps, factor in [(R.FILTER_DECIMATOR_F32, 8000, 1), (R.FILTER_DECIMATOR_F32, 300, 300),
+                                 (R.FILTER_DECIMATOR_I16, 10000, 2)]:
+        with pytest.raises(R.SdrError):
+            R.FilterBank(kind, 4, np.ones(n_taps, dtype=np.float32) / n_taps, factor)
+    # the largest filters the reference itself ships still fit
+    b = R.FilterBank(R.FILTER_DECIMATOR_F32, 4, np.ones(80, dtype=np.float32) / 80, 4)
+    assert b.run(np.zeros((4, 64), dtype=np.float32)).shape == (4, 16)
+    b.close()
