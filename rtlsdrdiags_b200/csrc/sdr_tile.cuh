@@ -763,9 +763,9 @@ __global__ void __launch_bounds__(128, MINB) amssb_fir_kernel(const __grid_const
 // CONTRACTS: two trajectories fed the same numerators from different start states differ by
 // 0.95^n times the initial difference until the difference drops below the rounding step, and a
 // few steps later they are bit-identical for good (200,000 random starts per input class: median
-// 360-500 steps, never later than 807; tools/iir_merge.py). So a call's rows (a row = 32 PCM
-// samples = one FIR tile) are cut into up to 32 SEGMENTS per channel and every (channel, segment)
-// pair gets a lane:
+// 360-500 steps, latest 717-807 depending on the run; tools/iir_merge.py,
+// profiles/r02_iir_merge.txt). So a call's rows (a row = 32 PCM samples = one FIR tile) are cut
+// into up to 32 SEGMENTS per channel and every (channel, segment) pair gets a lane:
 //   * segment 0 starts from the carried y[n-1];
 //   * segment s > 0 starts `warm_rows` rows early from y = 0 (or at row 0 from the carried state if
 //     that is nearer), discards the outputs of the warm-up rows, and keeps the state it had when

@@ -37,8 +37,8 @@ def test_long_calls_default_segmentation(mode, signal):
     exp = _oracle_rows([mode] * n, iq)
     for ch in range(n):
         assert np.array_equal(pcm[ch], exp[ch]), "channel %d" % ch
-    # trajectories merge long before the 1024-step warm-up ends (tools/iir_merge.py: never later than
-    # 807 steps in 200,000 trials per input class): no segment needed the serial redo
+    # trajectories merge before the 896-step warm-up ends (tools/iir_merge.py: latest 717-807 steps in
+    # 200,000 trials per input class): no segment needed the serial redo
     assert e.debug_dc_redo_count() == 0
     e.close()
 
