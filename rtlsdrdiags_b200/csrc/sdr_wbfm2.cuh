@@ -25,6 +25,12 @@
 #include "sdr_tile.cuh"
 
 #if SDR_DEVICE_BUILD
+#ifndef SDR_WB_FP32_PREFILTER
+#define SDR_WB_FP32_PREFILTER 0  // 1: the pre-filter on FFMA2 (A/B builds; exact, measured slower, see theta_fp32)
+#endif
+#ifndef SDR_WB_FP32_SPLIT
+#define SDR_WB_FP32_SPLIT 2      // partial sums per pre-filter output (1, 2 or 4)
+#endif
 namespace sdr {
 
 struct WbTile2 {
@@ -57,13 +63,84 @@ struct WbTile2 {
     asm("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(addr));
     return u2f(t ^ (sg & 0x80000000u));
   }
+  // ---- the same pre-filter on the FP32 pipe (-DSDR_WB_FP32_PREFILTER=1; NOT the default) ----
+  // Measured (profiles/r02_wbfm_fp32_prefilter.txt): bit-exact, and slower -- WBFM x8192 343 -> 290 G S/s
+  // with one chain of 16 FFMA2 per output, 284 / 274 with two / four partial sums (so it is not the chains'
+  // latency): 132 I2F per tile queue on the quarter-rate XU pipe behind the shared-memory traffic (ncu:
+  // mio_throttle 0.48 -> 0.84 per issue, wait 0.88 -> 1.64) and the kernel executes 7 % more instructions.
+  // IDP.2A runs on the integer datapath, half the FP32 rate, and the workers are bound by it: 634 of
+  // 2,068 warp-instructions per 1024 samples and a third of all stall samples (profiles/r02_wbfm3_ncu.txt).
+  // The 16-tap pre-filter is exact in FP32: with the taps scaled by 2^-15 (exact) every partial sum is
+  // a multiple of 2^-16 below 256 -- 24 bits -- so FFMA2 (two FP32 FMAs per lane and instruction: the I
+  // and the Q arm as one register pair, the tap an immediate) adds up without rounding whatever the
+  // order. The accumulator starts at 2^-16 instead of the rounding constant 1/2: then
+  // floor(1/2 + sum) == round-to-nearest(2^-16 + sum) (the fraction is an odd multiple of 2^-16: never
+  // a tie), and one FADD2 of 1.5 * 2^23 leaves that integer in the low mantissa bits, its low byte
+  // being the reference's (int8_t) truncation (WbFmDemodulator.cc:393-397). The samples become floats
+  // with I2F.S8 straight from the packed bytes (XU pipe, otherwise idle here).
+  template <int S>  // sample S of the lane's window, -16 .. 31, as the pair (I', Q')
+  __device__ __forceinline__ static unsigned long long xpair(const uint32_t (&ea)[12], const uint32_t (&eb)[12]) {
+    constexpr int w = (S + 16) >> 2, by = (S + 16) & 3;
+    const float fi = (float)(int8_t)(ea[w] >> (8 * by)), fq = (float)(int8_t)(eb[w] >> (8 * by));
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(fi), "f"(fq));
+    return r;
+  }
+  template <int N, int K, int KEND>
+  __device__ __forceinline__ static void pre_fp32(const uint32_t (&ea)[12], const uint32_t (&eb)[12], unsigned long long &acc) {
+    if constexpr (K < KEND) {
+      constexpr float h = (float)taps::WB_PRE::tap(K) * (1.0f / 32768.0f);
+      unsigned long long hh;
+      asm("mov.b64 %0, {%1, %1};" : "=l"(hh) : "f"(h));
+      asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(xpair<N - K>(ea, eb)), "l"(hh));
+      pre_fp32<N, K + 1, KEND>(ea, eb, acc);
+    }
+  }
+  template <int N>
+  __device__ __forceinline__ static float theta_fp32(const uint32_t (&ea)[12], const uint32_t (&eb)[12], uint32_t lut_s) {
+    // SDR_WB_FP32_SPLIT partial sums per output (every order of summation is exact): shorter dependent chains
+    unsigned long long acc, part[SDR_WB_FP32_SPLIT];
+    asm("mov.b64 %0, {%1, %1};" : "=l"(part[0]) : "f"(1.52587890625e-05f));   // 2^-16
+    constexpr int STEP = 16 / SDR_WB_FP32_SPLIT;
+    pre_fp32<N, 0, STEP>(ea, eb, part[0]);
+#pragma unroll
+    for (int i = 1; i < SDR_WB_FP32_SPLIT; ++i) asm("mov.b64 %0, {%1, %1};" : "=l"(part[i]) : "f"(0.0f));
+    if constexpr (SDR_WB_FP32_SPLIT >= 2) pre_fp32<N, STEP, 2 * STEP>(ea, eb, part[1]);
+    if constexpr (SDR_WB_FP32_SPLIT >= 4) {
+      pre_fp32<N, 2 * STEP, 3 * STEP>(ea, eb, part[2]);
+      pre_fp32<N, 3 * STEP, 4 * STEP>(ea, eb, part[3]);
+      asm("add.rn.f32x2 %0, %0, %1;" : "+l"(part[0]) : "l"(part[2]));
+      asm("add.rn.f32x2 %0, %0, %1;" : "+l"(part[1]) : "l"(part[3]));
+    }
+    acc = part[0];
+    if constexpr (SDR_WB_FP32_SPLIT >= 2) asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(part[1]));
+    unsigned long long magic;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(magic) : "f"(12582912.0f));        // 1.5 * 2^23
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(magic));
+    uint32_t ri, rq;  // low byte = i, q of the pre-filter's int8 output
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(ri), "=r"(rq) : "l"(acc));
+    const uint32_t x = __byte_perm(ri, rq, 0x0040);
+    const uint32_t sg = prmt_sx(rq, 0, 0x8484);  // 0xFF00FF00 where q < 0
+    const uint32_t v = __byte_perm(x ^ (sg & 0xff00u), 0, 0x4410);
+    const uint32_t addr = lut_s + (v << 2) + (sg & 0x400u);
+    uint32_t t;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(t) : "r"(addr));
+    return u2f(t ^ (sg & 0x80000000u));
+  }
   template <int N0>
   __device__ __forceinline__ static void theta4(const uint32_t (&ea)[12], const uint32_t (&eb)[12], uint32_t lut_s,
                                                 float (&th)[4]) {
+#if SDR_WB_FP32_PREFILTER
+    th[0] = theta_fp32<N0>(ea, eb, lut_s);
+    th[1] = theta_fp32<N0 + 1>(ea, eb, lut_s);
+    th[2] = theta_fp32<N0 + 2>(ea, eb, lut_s);
+    th[3] = theta_fp32<N0 + 3>(ea, eb, lut_s);
+#else
     th[0] = theta<N0>(ea, eb, lut_s);
     th[1] = theta<N0 + 1>(ea, eb, lut_s);
     th[2] = theta<N0 + 2>(ea, eb, lut_s);
     th[3] = theta<N0 + 3>(ea, eb, lut_s);
+#endif
   }
   // four samples from their thetas -> u[0..3], advances (th_prev, v_prev)  (WbFmDemodulator.cc:463-486;
   // numerator of the de-emphasis IIR, IirFilter.cc:161-176 with b0 == b1)
