@@ -171,3 +171,42 @@ def test_public_fs4_helpers_match_the_front_end():
     assert np.array_equal(down, s8)
     # mode None and the default squelch: no engine is needed, the buffer is converted all the same
     assert np.array_equal(run("accept", u8), O.front_end(u8))
+
+
+def _filters_exe():
+    from rtlsdrdiags_b200 import _build
+    _build.build()
+    exe = os.path.join(ROOT, "tests", "host", "filters_main")
+    src = os.path.join(ROOT, "tests", "host", "filters_main.cc")
+    pkg = os.path.join(ROOT, "rtlsdrdiags_b200")
+    deps = [src, os.path.join(HOST, "B200Filters.h"), _build.LIB]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.run(["g++", "-O2", "-std=c++11", "-I", HOST, "-o", exe, src, "-L", pkg, "-lsdr_b200",
+                        "-Wl,-rpath," + pkg, "-lm"], check=True)
+    return exe
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("what,kind,factor,n_taps", [("dec32", O.MR_DECIMATOR_F32, 4, 80), ("dec16", O.MR_DECIMATOR_I16, 2, 40),
+                                                    ("int32", O.MR_INTERPOLATOR_F32, 2, 64), ("int16", O.MR_INTERPOLATOR_I16, 4, 32),
+                                                    ("fir32", O.MR_DECIMATOR_F32, 1, 7), ("fir16", O.MR_DECIMATOR_I16, 1, 16)])
+@pytest.mark.parametrize("how", ["block", "sample"])
+def test_filter_class_drop_ins(tmp_path, what, kind, factor, n_taps, how):
+    """Decimator / Interpolator / FirFilter and their _int16 twins with the reference's class names
+    (Filters/Decimator.h:28-42, Interpolator.h:35-49, FirFilter.h:21-27, Int16/*.h) over a one-row
+    filter bank: block calls cut unevenly and sample-at-a-time calls against the oracle's classes."""
+    exe = _filters_exe()
+    rng = np.random.default_rng(n_taps)
+    h = (rng.standard_normal(n_taps) / n_taps).astype(np.float32)
+    tf = tmp_path / "taps.f32"
+    h.tofile(tf)
+    n = 600 if how == "block" else 96
+    if what.endswith("16"):
+        x = rng.integers(-20000, 20000, size=n).astype(np.int16)
+    else:
+        x = rng.standard_normal(n).astype(np.float32)
+    r = subprocess.run([exe, what, str(factor), str(tf), how], input=x.tobytes(), capture_output=True, timeout=600)
+    assert r.returncode == 0, r.stderr.decode()
+    got = np.frombuffer(r.stdout, dtype=x.dtype)
+    exp = O.Multirate(kind, h, factor).run(x)
+    assert np.array_equal(got, exp)
