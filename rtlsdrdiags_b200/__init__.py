@@ -95,6 +95,7 @@ def load_library(build_if_missing=True):
     L.sdr_debug_dc_redo_count.argtypes = [vp, C.POINTER(u32)]
     L.sdr_debug_set_tile_loader.argtypes = [vp, i32]
     L.sdr_debug_set_wbfm_kernel.argtypes = [vp, i32]
+    L.sdr_debug_wb_prefilter_counts.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
     L.sdr_bank_create.argtypes = [u32, C.POINTER(i32), u32, u64, u32, C.POINTER(vp)]
     L.sdr_bank_destroy.argtypes = [vp]
     L.sdr_bank_device_count.argtypes = [vp]
@@ -274,8 +275,16 @@ class Engine:
 
     def debug_set_wbfm_kernel(self, generation=0):
         """WBFM kernel generation: 0 = default (3), 1 = table in global memory, 2 = table in shared
-        memory with one channel per worker warp, 3 = two channels per worker warp."""
+        memory with one channel per worker warp, 3 = two channels per worker warp; + 16 = 2 or 3
+        with the pre-filter on the tensor cores (default: CUDA cores)."""
         self._ck(self.L.sdr_debug_set_wbfm_kernel(self.h, int(generation)))
+
+    def debug_wb_prefilter_counts(self):
+        """(tensor-core, CUDA-core) counts of WBFM (half-)tiles by where their pre-filter ran, since the
+        first call of this method (which switches the counting on)."""
+        a, b = C.c_uint32(), C.c_uint32()
+        self._ck(self.L.sdr_debug_wb_prefilter_counts(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def debug_dc_redo_count(self):
         """Segments the recurrence kernel had to redo serially since the engine was created."""

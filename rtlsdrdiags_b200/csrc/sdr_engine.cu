@@ -59,6 +59,8 @@ struct sdr_engine {
   int tile_loader = 2;  // 0 = cp.async (two slot buffers), 2 / 3 / 4 = TMA with that many slot buffers
   bool stage1_mma = false;  // with TMA: stage 1 of the AM / SSB cascade on the tensor cores (measured slower)
   int wb_kernel = 0;  // 0 = default (SDR_WB_KERNEL or 3), 1..3 = that generation of the WBFM kernel
+  bool wb_count = false;  // sdr_debug_wb_prefilter_counts was called: the kernels count their tiles
+  bool wb_prefilter_mma = false;  // generations 2, 3: the pre-filter on the tensor cores (WbMma; measured: no faster)
   int fir_ctas_per_sm = 5;  // register budget of the FIR kernel: 5 (96 registers) or 6 (80) CTAs per SM
   uint32_t *d_am_tab = nullptr;  // am_mma_table()
   CUtensorMap tmap;
@@ -90,6 +92,7 @@ struct sdr_engine {
   float *d_lut_fm = nullptr, *d_lut_wbfm = nullptr;
   float *d_lut_wbfm_half = nullptr;  // q >= 0 half plane for wbfm_tile2_kernel, [129][256]
   uint32_t *d_fm_tab = nullptr;  // tensor-core tuner tables, fm_mma_table()
+  uint32_t *d_wb_tab = nullptr;  // tensor-core WBFM pre-filter table, wb_mma_table()
   uint8_t *d_iq = nullptr;
   // two PCM buffers, used by alternate calls: the read-back of call k (sdr_get_pcm, the ingest
   // ring's device->host copy) does not hold up the kernels of call k+1
@@ -485,6 +488,81 @@ std::vector<uint32_t> fm_mma_table() {
   return tab;
 }
 
+// Table of the tensor-core WBFM pre-filter (WbMma::prefilter): D = A * B with B = raw u8 input bytes.
+// A[row][kb]: row o < 8 gives I' output o of an M-tile (eight consecutive samples = one 16-byte granule),
+// row 8 + o gives Q'; kb = 0..47 indexes the raw bytes from 32 before the granule's first to its last
+// (complex sample c = kb >> 1 counted from 16 before the granule, I at even bytes). Output o is
+// sum_k 2 h[k] x'[16 + o - k] (FirFilter_int16.cc:151-213 with the taps doubled, WbTile::Pre2) where x' is the
+// rotated sample (IqDataProcessor.cc:567-611): I' = I0, -Q1, -I2, Q3; Q' = Q0, I1, -Q2, -I3 by c mod 4 (a
+// granule starts a rotation period). Each tap is split as 256 * hi + lo with both parts int8.
+// The accumulators' starts -- the doubled rounding constant 1 << 15 (lo) and, for u = s + 128, -128 * the row
+// sum -- ride in the K dimension: the first MMA of an accumulator is an m16n8k32 whose K 0..15 is the granule
+// kb 0..15 and whose K 16..31 meets the constant granule C (twelve bytes 255, four bytes 1): start = 255 * (sum
+// of the twelve A entries there) + (sum of the last four), every entry an int8.
+// Layout: four A fragments of [lane][4 words] (mma.m16n8k32: row g, row g+8, row g k+16, row g+8 k+16; k 4tq..4tq+3):
+//   0, 1: hi and lo of [kb 0..15 | start]      2, 3: hi and lo of kb 16..47
+// then the four words of C.
+std::vector<uint32_t> wb_mma_table() {
+  std::vector<uint32_t> tab(WB_TAB_WORDS, 0);
+  int A[16][48] = {};
+  for (int kb = 0; kb < 48; ++kb) {
+    const int c = kb >> 1, comp = kb & 1, cm = c & 3;
+    static const int arm_of[4][2] = {{0, 1}, {1, 0}, {0, 1}, {1, 0}};     // [c mod 4][comp]: 0 = I', 1 = Q'
+    static const int sign_of[4][2] = {{1, 1}, {1, -1}, {-1, -1}, {-1, 1}};
+    for (int o = 0; o < 8; ++o) {
+      const int k = 16 + o - c;
+      if (k >= 0 && k < taps::WB_PRE::N) A[8 * arm_of[cm][comp] + o][kb] = sign_of[cm][comp] * 2 * taps::WB_PRE::tap(k);
+    }
+  }
+  auto part = [](int v, int h) {
+    const int lo = ((v + 128) & 255) - 128;
+    return h == 0 ? (v - lo) / 256 : lo;
+  };
+  // E[h][row][0..63]: K 0..15 = kb 0..15, K 16..31 = the start spread over C's weights, K 32..63 = kb 16..47
+  static int E[2][16][64];
+  for (int h = 0; h < 2; ++h)
+    for (int row = 0; row < 16; ++row) {
+      int sum = 0;
+      for (int kb = 0; kb < 48; ++kb) {
+        const int v = part(A[row][kb], h);
+        sum += v;
+        E[h][row][kb < 16 ? kb : 16 + kb] = v;
+      }
+      const int start = (h == 1 ? 1 << 15 : 0) - 128 * sum;
+      int big = (start >= 0 ? start + 127 : start - 127) / 255;  // start = 255 * big + small, |small| <= 127
+      int small = start - 255 * big;
+      for (int i = 0; i < 12; ++i) {  // big over twelve int8 entries, small over four
+        const int left = 12 - i, v = big >= 0 ? (big + left - 1) / left : -((-big + left - 1) / left);
+        E[h][row][16 + i] = v;
+        big -= v;
+      }
+      for (int i = 0; i < 4; ++i) {
+        const int left = 4 - i, v = small >= 0 ? (small + left - 1) / left : -((-small + left - 1) / left);
+        E[h][row][28 + i] = v;
+        small -= v;
+      }
+    }
+  auto word = [&](int h, int row, int k0) {
+    uint32_t w = 0;
+    for (int b = 0; b < 4; ++b) {
+      const int v = E[h][row][k0 + b];
+      if (v < -128 || v > 127) abort();  // cannot happen: |start| < 255 * 12 * 127
+      w |= (uint32_t)(uint8_t)(int8_t)v << (8 * b);
+    }
+    return w;
+  };
+  for (int lane = 0; lane < 32; ++lane) {
+    const int g = lane >> 2, tq = lane & 3;
+    for (int h = 0; h < 2; ++h)
+      for (int s2 = 0; s2 < 2; ++s2)
+        for (int r = 0; r < 4; ++r)
+          tab[((2 * s2 + h) * 32 + lane) * 4 + r] = word(h, g + 8 * (r & 1), 32 * s2 + 16 * (r >> 1) + 4 * tq);
+  }
+  tab[WB_TAB_A_WORDS + 0] = tab[WB_TAB_A_WORDS + 1] = tab[WB_TAB_A_WORDS + 2] = 0xffffffffu;
+  tab[WB_TAB_A_WORDS + 3] = 0x01010101u;
+  return tab;
+}
+
 int launch_fm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples, int fmt) {
   const int kind = SDR_KIND_FM;
   const uint32_t n_list = (uint32_t)e->list[kind].size();
@@ -535,10 +613,20 @@ int launch_fm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_
   return SDR_OK;
 }
 
+int wb_tab_ready(sdr_engine *e) {
+  if (!e->d_wb_tab) {
+    const std::vector<uint32_t> tab = wb_mma_table();
+    SDR_CK(e, cudaMalloc(&e->d_wb_tab, tab.size() * 4));
+    SDR_CK(e, cudaMemcpy(e->d_wb_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice));
+  }
+  return SDR_OK;
+}
+
 // wbfm_tile3_kernel: two channels per worker warp, up to 28 channels per CTA behind one recurrence warp
 int launch_wbfm_tile3(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples, int fmt,
                       cudaStream_t stream) {
   using T = WbTile3;
+  int rc_tab = SDR_OK;
   const int kind = SDR_KIND_WBFM;
   const uint32_t n_list = (uint32_t)e->list[kind].size();
   // one CTA per SM (table and rings fill shared memory): spread the channels evenly over the waves,
@@ -555,7 +643,10 @@ int launch_wbfm_tile3(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint
   if (G > 2u * (uint32_t)T::MAX_WORKERS) G = 2u * (uint32_t)T::MAX_WORKERS;
   if (G < 2) G = 2;
   const int workers = (int)G / 2;
-  const int smem = T::smem_bytes(workers);
+  static const bool mma_env = getenv("SDR_WB_MMA") && atoi(getenv("SDR_WB_MMA")) != 0;  // A/B switch
+  const bool mma = e->wb_prefilter_mma || mma_env;
+  const int smem = T::smem_bytes(workers, mma);
+  if (mma && (rc_tab = wb_tab_ready(e))) return rc_tab;
   LaunchParams p = {};
   p.iq = iq;
   p.ch_stride = ch_stride;
@@ -574,9 +665,16 @@ int launch_wbfm_tile3(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint
   p.aux = (uint32_t)std::min(workers, (int)T::REC_WARP);
   p.scratch = nullptr;
   p.allowed = e->last_gated ? e->d_allowed[e->seq % (uint64_t)e->ring] : nullptr;
-  SDR_CK(e, cudaFuncSetAttribute(wbfm_tile3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  p.tab = e->d_wb_tab;
+  p.counters = e->wb_count ? e->d_counters : nullptr;  // one atomic per tile: only when somebody asked
   const uint32_t grid = (n_list + G - 1) / G;
-  wbfm_tile3_kernel<<<grid, 32 * (workers + 1), smem, stream>>>(p);
+  if (mma) {
+    SDR_CK(e, cudaFuncSetAttribute(wbfm_tile3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    wbfm_tile3_kernel<true><<<grid, 32 * (workers + 1), smem, stream>>>(p);
+  } else {
+    SDR_CK(e, cudaFuncSetAttribute(wbfm_tile3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    wbfm_tile3_kernel<false><<<grid, 32 * (workers + 1), smem, stream>>>(p);
+  }
   SDR_CK(e, cudaGetLastError());
   e->launches++;
   return SDR_OK;
@@ -599,7 +697,11 @@ int launch_wbfm_tile2(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint
   if (gx_env) G = (uint32_t)gx_env;
   if (e->shape[kind].G) G = e->shape[kind].G;
   if (G > (uint32_t)T::MAX_WORKERS) G = T::MAX_WORKERS;
-  const int smem = T::smem_bytes((int)G);
+  static const bool mma_env = getenv("SDR_WB_MMA") && atoi(getenv("SDR_WB_MMA")) != 0;  // A/B switch
+  const bool mma = e->wb_prefilter_mma || mma_env;
+  const int smem = T::smem_bytes((int)G, mma);
+  int rc_tab = SDR_OK;
+  if (mma && (rc_tab = wb_tab_ready(e))) return rc_tab;
   LaunchParams p = {};
   p.iq = iq;
   p.ch_stride = ch_stride;
@@ -615,13 +717,20 @@ int launch_wbfm_tile2(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint
   p.pcm = e->pcm_of(e->seq);
   p.pcm_stride = e->pcm_stride;
   p.lut = e->d_lut_wbfm_half;
+  p.tab = e->d_wb_tab;
+  p.counters = e->wb_count ? e->d_counters : nullptr;  // one atomic per tile: only when somebody asked
   static const int rec_env = getenv("SDR_WB_REC") ? atoi(getenv("SDR_WB_REC")) : -1;  // tuning override
   p.aux = (uint32_t)((rec_env >= 0 && rec_env <= (int)G) ? rec_env : std::min((int)G, (int)T::REC_WARP));
   p.scratch = nullptr;
   p.allowed = e->last_gated ? e->d_allowed[e->seq % (uint64_t)e->ring] : nullptr;
-  SDR_CK(e, cudaFuncSetAttribute(wbfm_tile2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   const uint32_t grid = (n_list + G - 1) / G;
-  wbfm_tile2_kernel<<<grid, 32 * T::warps_for((int)G), smem, stream>>>(p);
+  if (mma) {
+    SDR_CK(e, cudaFuncSetAttribute(wbfm_tile2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    wbfm_tile2_kernel<true><<<grid, 32 * T::warps_for((int)G), smem, stream>>>(p);
+  } else {
+    SDR_CK(e, cudaFuncSetAttribute(wbfm_tile2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    wbfm_tile2_kernel<false><<<grid, 32 * T::warps_for((int)G), smem, stream>>>(p);
+  }
   SDR_CK(e, cudaGetLastError());
   e->launches++;
   return SDR_OK;
@@ -987,6 +1096,7 @@ int sdr_engine_destroy(sdr_engine *e) {
   cudaFree(e->d_lsb);
   cudaFree(e->d_lut_fm);
   cudaFree(e->d_fm_tab);
+  cudaFree(e->d_wb_tab);
   cudaFree(e->d_am_tab);
   cudaFree(e->d_lut_wbfm);
   cudaFree(e->d_lut_wbfm_half);
@@ -1105,10 +1215,20 @@ int sdr_debug_set_dc_shape(sdr_engine *e, uint32_t seg_count, uint32_t warm_rows
 
 // which generation of the WBFM kernel runs (0 = default); the three share the carry blob, so a test
 // may switch between calls
+// + 16: generations 2 and 3 with the pre-filter on the tensor cores (WbMma; default: CUDA cores)
 int sdr_debug_set_wbfm_kernel(sdr_engine *e, int generation) {
-  if (!e || generation < 0 || generation > 3) return SDR_E_ARG;
-  e->wb_kernel = generation;
+  if (!e || generation < 0 || (generation & ~16) > 3) return SDR_E_ARG;
+  e->wb_kernel = generation & ~16;
+  e->wb_prefilter_mma = (generation & 16) != 0;
   return SDR_OK;
+}
+
+// wb_mma_table() for the CPU-side check of the tensor-core formulation (tests/test_wb_mma_table.py)
+int sdr_debug_wb_mma_table(uint32_t *out) {
+  if (!out) return SDR_E_ARG;
+  const std::vector<uint32_t> tab = wb_mma_table();
+  memcpy(out, tab.data(), tab.size() * 4);
+  return (int)tab.size();
 }
 
 // am_mma_table() for the CPU-side check of the tensor-core formulation (tests/test_am_mma_table.py):
@@ -1130,6 +1250,22 @@ int sdr_debug_set_tile_loader(sdr_engine *e, int loader) {
   e->fir_ctas_per_sm = (loader & 16) ? 6 : 5;
   loader &= 7;
   e->tile_loader = loader == 1 ? 2 : loader;
+  return SDR_OK;
+}
+
+// (half-)tiles whose WBFM pre-filter ran on the tensor cores / on the CUDA cores since the first call of this
+// function (which switches the counting on)
+int sdr_debug_wb_prefilter_counts(sdr_engine *e, uint32_t *mma, uint32_t *simt) {
+  if (!e || !mma || !simt) return SDR_E_ARG;
+  e->wb_count = true;
+  SDR_CK(e, cudaSetDevice(e->device));
+  int rc = join_streams(e);
+  if (rc) return rc;
+  uint32_t c[4] = {};
+  SDR_CK(e, cudaMemcpyAsync(c, e->d_counters, 16, cudaMemcpyDeviceToHost, e->stream));
+  SDR_CK(e, cudaStreamSynchronize(e->stream));
+  *mma = c[1];
+  *simt = c[2];
   return SDR_OK;
 }
 

@@ -23,6 +23,7 @@
 // between calls.
 #pragma once
 #include "sdr_tile.cuh"
+#include "sdr_wbfm_mma.cuh"
 
 #if SDR_DEVICE_BUILD
 #ifndef SDR_WB_FP32_PREFILTER
@@ -38,7 +39,10 @@ struct WbTile2 {
   static constexpr int LUT_ROWS = 129, LUT_BYTES = LUT_ROWS * 256 * 4;
   static constexpr int MAX_WORKERS = 15;   // 512 threads x 128 registers; 14 is the default (see warps_for)
   static constexpr int RING_BYTES = 4096 + 16;  // one slot + pad: channel stride == 16 (mod 128)
-  __host__ __device__ static constexpr int smem_bytes(int nw) { return LUT_BYTES + nw * (TILE_BYTES + RING_BYTES) + 64; }
+  // mma: the pre-filter on the tensor cores (WbMma): + each channel's raw history and the taps table
+  __host__ __device__ static constexpr int smem_bytes(int nw, bool mma = false) {
+    return LUT_BYTES + nw * ((mma ? WbMma::area_bytes<false>() : TILE_BYTES) + RING_BYTES) + 64 + (mma ? WB_TAB_WORDS * 4 : 0);
+  }
   // The recurrence warp's dependent FMUL -> FSUB chain is the round's critical path (measured:
   // the round time does not depend on the number of workers between 12 and 14). It is warp
   // REC_WARP = 3, so that with 14 workers (15 warps) its scheduler carries two workers and the
@@ -142,17 +146,8 @@ struct WbTile2 {
     th[3] = theta<N0 + 3>(ea, eb, lut_s);
 #endif
   }
-  // four samples from their thetas -> u[0..3], advances (th_prev, v_prev)  (WbFmDemodulator.cc:463-486;
-  // numerator of the de-emphasis IIR, IirFilter.cc:161-176 with b0 == b1)
   __device__ __forceinline__ static void u4(const float (&th)[4], float k, float &th_prev, float &v_prev, uint32_t *u) {
-    const float b0 = (float)(0.0253863), b1 = (float)(0.0253863);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float v = fmul(k, wrap_pi_table(fsub(th[i], th_prev)));
-      u[i] = f2u(fadd(fmul(b0, v), fmul(b1, v_prev)));
-      th_prev = th[i];
-      v_prev = v;
-    }
+    wb_u4(th, k, th_prev, v_prev, u);
   }
   template <int J>
   __device__ __forceinline__ static void u_chunks(const uint32_t (&ea)[12], const uint32_t (&eb)[12], uint32_t lut_s,
@@ -228,6 +223,9 @@ struct WbTile2 {
 // blockDim = 32 * WbTile2::warps_for(p.G). The last warp runs the recurrences (lane == channel
 // slot), warps 0 .. G-1 are workers. All roles share one round loop and meet the same two barrier
 // instructions.
+// MMA: the pre-filter of full tiles of u8 input runs on the tensor cores (sdr_wbfm_mma.cuh); the pre-filter
+// history then lives as raw bytes in shared memory instead of WbCarry::a, b.
+template <bool MMA>
 __global__ void __launch_bounds__(32 * (WbTile2::MAX_WORKERS + 1), 1) wbfm_tile2_kernel(const __grid_constant__ LaunchParams p) {
   using T = WbTile2;
   using T1 = WbTile;
@@ -242,15 +240,23 @@ __global__ void __launch_bounds__(32 * (WbTile2::MAX_WORKERS + 1), 1) wbfm_tile2
   const uint32_t list0 = blockIdx.x * (uint32_t)nw;
   const int n_here = (int)min((uint32_t)nw, p.n_list - list0);
   const uint32_t n_tiles = (p.n_samples + TILE - 1) / TILE;
+  // a worker's input area: 2 KB of windows, or (MMA) WbMma's layout with the history area in front
+  constexpr int AREA = MMA ? WbMma::area_bytes<false>() : TILE_BYTES;
   char *in_base = smem + T::LUT_BYTES;
-  char *ring_base = in_base + nw * TILE_BYTES;
+  char *ring_base = in_base + nw * AREA;
   const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(smem);
+  char *tab_base = ring_base + nw * T::RING_BYTES;  // MMA: wb_mma_table() (every size before it is a multiple of 16)
 
   // the table: 129 KB from L2 once per CTA
   {
     const uint4 *src = reinterpret_cast<const uint4 *>(p.lut);
     uint4 *dst = reinterpret_cast<uint4 *>(smem);
     for (int i = threadIdx.x; i < T::LUT_BYTES / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    if constexpr (MMA) {
+      const uint4 *tsrc = reinterpret_cast<const uint4 *>(p.tab);
+      uint4 *tdst = reinterpret_cast<uint4 *>(tab_base);
+      for (int i = threadIdx.x; i < WB_TAB_WORDS / 4; i += blockDim.x) tdst[i] = __ldg(tsrc + i);
+    }
   }
 
   const int slot_id = is_iir ? lane : widx;  // channel slot in this CTA
@@ -264,7 +270,10 @@ __global__ void __launch_bounds__(32 * (WbTile2::MAX_WORKERS + 1), 1) wbfm_tile2
   WbCarry pv;
   const uint8_t *src = p.iq + (uint64_t)ch * p.ch_stride;
   int16_t *out = p.pcm + (uint64_t)ch * p.pcm_stride;
-  char *in_slot = in_base + (active && is_worker ? slot_id : 0) * TILE_BYTES;
+  char *area = in_base + (active && is_worker ? slot_id : 0) * AREA;
+  char *in_slot = MMA ? area + WbMma::window_base<false>(0) : area;
+  char *hist = area;  // MMA: the channel's raw pre-filter history, in front of its windows
+  const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(tab_base);
   float k = 0.f, v_boundary = 0.f;
   bool big_b = false, no_patch = false;
   // phase 2 -> phase 1: numerators of the tile computed this round, waiting for the slot;
@@ -283,6 +292,9 @@ __global__ void __launch_bounds__(32 * (WbTile2::MAX_WORKERS + 1), 1) wbfm_tile2
       // |y| <= max(|y[-1]|, |u|max / (1 - |a1|)) < 3.2 |k|: with |k| < 1e8 and |y[-1]| < 1e9 no
       // value can reach 2^31, where cvt.rzi (saturating) and x86 cvttss2si (wrapping) differ
       no_patch = fabsf(k) < 1e8f && fabsf(u2f(blob[T1::NREG * 32])) < 1e9f;
+      if constexpr (MMA) {
+        if (lane == 31) WbMma::history_from_planes(hist, p.fmt, pv);
+      }
       tile_fill(in_slot, src, lane, (int)min((uint32_t)TILE, p.n_samples) >> 3);
     }
     cp_async_commit();
@@ -324,6 +336,15 @@ __global__ void __launch_bounds__(32 * (WbTile2::MAX_WORKERS + 1), 1) wbfm_tile2
       if (kk < n_tiles) {
         cp_async_wait<0>();
         __syncwarp();
+        const int r = (int)min((uint32_t)TILE, p.n_samples - kk * TILE) >> 5;
+        bool pairs = false;  // the slot holds the pre-filter's outputs instead of raw samples
+        if constexpr (MMA) {
+          if (r == 32 && p.fmt == FMT_U8_OFFSET_ROTATE)
+            pairs = WbMma::prefilter<false>((uint32_t)__cvta_generic_to_shared(area), tab_s, lane, true);
+          __syncwarp();
+          // diagnostics: [1] = tiles whose pre-filter ran on the tensor cores, [2] = on the CUDA cores
+          if (lane == 0 && p.counters) atomicAdd(p.counters + (pairs ? 1 : 2), 1u);
+        }
         uint32_t w[16];
         tile_read(in_slot, lane, w);
         __syncwarp();
@@ -332,8 +353,17 @@ __global__ void __launch_bounds__(32 * (WbTile2::MAX_WORKERS + 1), 1) wbfm_tile2
           tile_fill(in_slot, src + (uint64_t)s1 * 2, lane, (int)min((uint32_t)TILE, p.n_samples - s1) >> 3);
         }
         cp_async_commit();
-        const int r = (int)min((uint32_t)TILE, p.n_samples - kk * TILE) >> 5;
-        T::part_a(w, p.fmt, k, lut_s, pv, v_boundary, u, lane, r);
+        if (MMA && pairs) {
+          WbMma::part_a<false>(w, k, lut_s, pv, v_boundary, u, lane);
+        } else {
+          if constexpr (MMA) WbMma::planes_from_history(hist, p.fmt, pv);
+          T::part_a(w, p.fmt, k, lut_s, pv, v_boundary, u, lane, r);
+          if constexpr (MMA) {
+            __syncwarp();
+            if (lane == r - 1) WbMma::history_from_window(hist, w);
+            __syncwarp();
+          }
+        }
       }
     } else if (is_iir && active && kk >= 1 && kk <= n_tiles) {
       // B(kk-1): y[n] = fl(u[n] - fl(a1 * y[n-1])) in place, lane == channel (IirFilter.cc:161-176)
@@ -381,6 +411,7 @@ __global__ void __launch_bounds__(32 * (WbTile2::MAX_WORKERS + 1), 1) wbfm_tile2
 
   if (active) {
     if (is_worker) {
+      if constexpr (MMA) WbMma::planes_from_history(hist, p.fmt, pv);
       T1::store_carry(pv, blob, lane);
       if (lane == 0) {
         blob[T1::NREG * 32 + 1] = f2u(v_boundary);

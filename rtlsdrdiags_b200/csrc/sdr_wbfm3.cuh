@@ -43,8 +43,10 @@ struct WbTile3 {
   static constexpr int MAX_WORKERS = 14;           // 15 warps x 128 registers; 28 channels per CTA
   static constexpr int RING_BYTES = 2048 + 16;     // 16 rows of 32 floats + pad: channel stride == 16 (mod 128)
   static constexpr int ERING_WORDS = 48;           // the last 48 decimator-2 output pairs of a channel
-  __host__ __device__ static constexpr int smem_bytes(int workers) {
-    return T2::LUT_BYTES + workers * (TILE_BYTES + 2 * RING_BYTES + 2 * ERING_WORDS * 4) + 64;
+  // mma: the pre-filter on the tensor cores (WbMma): + each channel's raw history and the taps table
+  __host__ __device__ static constexpr int smem_bytes(int workers, bool mma = false) {
+    return T2::LUT_BYTES + workers * ((mma ? WbMma::area_bytes<true>() : TILE_BYTES) + 2 * RING_BYTES + 2 * ERING_WORDS * 4) + 64 +
+           (mma ? WB_TAB_WORDS * 4 : 0);
   }
   static constexpr int REC_WARP = 3;  // as in WbTile2: the recurrence warp's scheduler carries fewer workers
 
@@ -195,6 +197,9 @@ struct WbTile3 {
 // blockDim = 32 * (workers + 1), p.G = channels per CTA = 2 * workers. Warp p.aux runs the
 // recurrences (lane == channel slot), the others are workers (two channel slots each). All roles
 // share one round loop and meet the same two barrier instructions.
+// MMA: the pre-filter of full half-tiles of u8 input runs on the tensor cores (sdr_wbfm_mma.cuh); the
+// pre-filter history then lives as raw bytes in shared memory instead of WbCarry::a, b.
+template <bool MMA>
 __global__ void __launch_bounds__(32 * (WbTile3::MAX_WORKERS + 1), 1) wbfm_tile3_kernel(const __grid_constant__ LaunchParams p) {
   using T = WbTile3;
   using T1 = WbTile;
@@ -210,16 +215,25 @@ __global__ void __launch_bounds__(32 * (WbTile3::MAX_WORKERS + 1), 1) wbfm_tile3
   const uint32_t list0 = blockIdx.x * p.G;
   const int n_here = (int)min(p.G, p.n_list - list0);
   const uint32_t n_half = (p.n_samples + T::HALF - 1) / T::HALF;
+  // a worker's input area: 2 KB of windows, or (MMA) WbMma's layout with a history area in front of each channel's
+  constexpr int AREA = MMA ? WbMma::area_bytes<true>() : TILE_BYTES;
   char *in_base = smem + T2::LUT_BYTES;
-  char *ring_base = in_base + nw * TILE_BYTES;
+  char *ring_base = in_base + nw * AREA;
   uint32_t *ering_base = reinterpret_cast<uint32_t *>(ring_base + 2 * nw * T::RING_BYTES);
   const uint32_t lut_s = (uint32_t)__cvta_generic_to_shared(smem);
+  char *tab_base = reinterpret_cast<char *>(ering_base + 2 * nw * T::ERING_WORDS);  // MMA: wb_mma_table()
 
   // the table: 129 KB from L2 once per CTA
   {
     const uint4 *src = reinterpret_cast<const uint4 *>(p.lut);
     uint4 *dst = reinterpret_cast<uint4 *>(smem);
     for (int i = threadIdx.x; i < T2::LUT_BYTES / 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    if constexpr (MMA) {
+      const uint4 *tsrc = reinterpret_cast<const uint4 *>(p.tab);
+      uint4 *tdst = reinterpret_cast<uint4 *>(tab_base);
+      for (int i = threadIdx.x; i < WB_TAB_WORDS / 4; i += blockDim.x) tdst[i] = __ldg(tsrc + i);
+      // (the history areas' 32 bytes nobody writes are never read either)
+    }
   }
 
   // channel slot of this lane: a worker's lanes 0-15 serve slot 2 widx, lanes 16-31 slot 2 widx + 1;
@@ -234,12 +248,17 @@ __global__ void __launch_bounds__(32 * (WbTile3::MAX_WORKERS + 1), 1) wbfm_tile3
   char *ring = ring_base + (is_worker || owned ? slot_id : 0) * T::RING_BYTES;
   uint32_t *er = ering_base + (is_worker ? 2 * widx + (lane >> 4) : 0) * T::ERING_WORDS;
   const int l16 = lane & 15;
+  const uint32_t tab_s = (uint32_t)__cvta_generic_to_shared(tab_base);
 
   // ---- worker state ----
   WbCarry pv;
   const uint8_t *src = p.iq + (uint64_t)ch * p.ch_stride;
   int16_t *out = p.pcm + (uint64_t)ch * p.pcm_stride;
-  char *in_slot = in_base + (is_worker ? widx : 0) * TILE_BYTES;
+  char *area = in_base + (is_worker ? widx : 0) * AREA;
+  // where tile_read's "window = lane" numbering starts for this lane, and (MMA) the lane's channel's raw
+  // pre-filter history in front of the channel's windows
+  char *in_slot = MMA ? area + WbMma::window_base<true>(0) + (lane >> 4) * WB_HIST_AREA : area;
+  char *hist = area + (lane >> 4) * (WB_HIST_AREA + TILE_BYTES / 2);
   float k = 0.f, v_boundary = 0.f;
   bool big_b = false, no_patch = true;
   uint32_t u[32] = {};
@@ -278,6 +297,9 @@ __global__ void __launch_bounds__(32 * (WbTile3::MAX_WORKERS + 1), 1) wbfm_tile3
       pv = WbCarry{};
     }
     no_patch = __all_sync(FULL, no_patch);
+    if constexpr (MMA) {
+      if (l16 == 15) WbMma::history_from_planes(hist, p.fmt, pv);  // a dead channel's: 0x80 bytes
+    }
     fetch_half(0);
     cp_async_commit();
   } else if (is_iir && active) {
@@ -315,13 +337,31 @@ __global__ void __launch_bounds__(32 * (WbTile3::MAX_WORKERS + 1), 1) wbfm_tile3
       if (kk < n_half) {
         cp_async_wait<0>();
         __syncwarp();
+        const int r = (int)min((uint32_t)T::HALF, p.n_samples - kk * T::HALF) >> 5;
+        bool pairs = false;  // the slot holds the pre-filter's outputs instead of raw samples
+        if constexpr (MMA) {
+          if (r == 16 && p.fmt == FMT_U8_OFFSET_ROTATE)
+            pairs = WbMma::prefilter<true>((uint32_t)__cvta_generic_to_shared(area), tab_s, lane, active);
+          __syncwarp();
+          // diagnostics: [1] = tiles whose pre-filter ran on the tensor cores, [2] = on the CUDA cores
+          if (lane == 0 && p.counters) atomicAdd(p.counters + (pairs ? 1 : 2), 1u);
+        }
         uint32_t w[16];
         tile_read(in_slot, lane, w);
         __syncwarp();
         if (kk + 1 < n_half) fetch_half(kk + 1);  // the input slot is free again
         cp_async_commit();
-        const int r = (int)min((uint32_t)T::HALF, p.n_samples - kk * T::HALF) >> 5;
-        T::part_a(w, p.fmt, k, lut_s, pv, v_boundary, u, lane, r);
+        if (MMA && pairs) {
+          WbMma::part_a<true>(w, k, lut_s, pv, v_boundary, u, lane);
+        } else {
+          if constexpr (MMA) WbMma::planes_from_history(hist, p.fmt, pv);
+          T::part_a(w, p.fmt, k, lut_s, pv, v_boundary, u, lane, r);
+          if constexpr (MMA) {
+            __syncwarp();
+            if (l16 == r - 1) WbMma::history_from_window(hist, w);
+            __syncwarp();
+          }
+        }
       }
     } else if (is_iir && active && kk >= 1 && kk <= n_half) {
       // B(kk-1): y[n] = fl(u[n] - fl(a1 * y[n-1])) in place, lane == channel (IirFilter.cc:161-176)
@@ -366,6 +406,7 @@ __global__ void __launch_bounds__(32 * (WbTile3::MAX_WORKERS + 1), 1) wbfm_tile3
 
   if (active) {
     if (is_worker) {
+      if constexpr (MMA) WbMma::planes_from_history(hist, p.fmt, pv);
       T::store_carry(pv, blob, er, lane);  // a lane reads back the ring words it wrote itself
       if (l16 == 0) {
         blob[T1::NREG * 32 + 1] = f2u(v_boundary);

@@ -101,3 +101,78 @@ def test_squelched_half_and_reset():
             if exp.size:
                 assert np.array_equal(pcm[ch], exp), "step %d channel %d" % (step, ch)
     e.close()
+
+
+def _quiet(n, nbytes, seed, amp=45.0):
+    """Band-limited-ish noise that never reaches the rails: no raw byte 0, the tensor-core path's case."""
+    rng = np.random.default_rng(seed)
+    x = 128 + amp * rng.standard_normal((n, nbytes))
+    return np.clip(np.round(x), 1, 255).astype(np.uint8)
+
+
+@pytest.mark.parametrize("gen", [2, 3])
+@pytest.mark.parametrize("n", [1, 2, 29, 61])
+def test_tensor_core_prefilter(gen, n):
+    """The pre-filter as an int8 GEMM on the raw bytes (WbMma::prefilter; an option, generation + 16): streams
+    without a clipping byte take it for every full (half-)tile; a raw byte 0 where the Fs/4 rotation negates sends exactly
+    the tiles that see it -- the one that holds it and, through the 15 samples of history, the next --
+    down the CUDA-core path. Bit-exact against the oracle either way, and against the CUDA-core build."""
+    import rtlsdrdiags_b200 as R
+    nbytes = 2 * 32768
+    iq = _quiet(n, nbytes, seed=100 + n)
+    iq[0, 2048 * 3 + 64 * 5 + 3] = 0          # Q1: negated -> the tile falls back
+    iq[0, 2048 * 7 + 2047] = 0                # the tile's last byte (Q3, not negated): no fallback
+    iq[0, 2048 * 9 + 2044] = 0                # I2 of the tile's last group: this tile and the next fall back
+    iq[n - 1, 1024 * 21 + 7] = 255
+    exp = _oracle_rows(n, iq)
+    outs = {}
+    for flag in (16, 0):
+        e = R.Engine(n, 0, nbytes)
+        e.set_modes(np.full(n, 3, dtype=np.uint8))
+        e.debug_set_wbfm_kernel(gen | flag)
+        e.debug_wb_prefilter_counts()
+        pcm, counts = e.demodulate(iq)
+        assert (counts == nbytes // 64).all()
+        outs[flag] = pcm.copy()
+        mma, simt = e.debug_wb_prefilter_counts()
+        per_ch = nbytes // (2048 if gen == 2 else 1024)
+        units = n * per_ch if gen == 2 else ((n + 1) // 2) * per_ch   # gen 3: one count per warp and half-tile pair
+        if flag == 0:
+            assert (mma, simt) == (0, 0)     # the CUDA-core build does not count
+        else:
+            assert mma + simt == units
+            assert simt == 3, (mma, simt)      # the tile with the Q1 byte; the one with the I2 byte and its successor
+        e.close()
+    for ch in range(n):
+        assert np.array_equal(outs[16][ch], exp[ch]), "channel %d" % ch
+    assert np.array_equal(outs[0], outs[16])
+
+
+def test_tensor_core_prefilter_ragged_calls_and_switches():
+    """Call lengths that leave partial (half-)tiles, both kernel generations and both pre-filter builds
+    alternating between calls on the same streams: the raw history in shared memory and the planes in the
+    carry blob are two views of the same 16 samples."""
+    import rtlsdrdiags_b200 as R
+    n = 7
+    e = R.Engine(n, 0, 4 * 32768)
+    e.set_modes(np.full(n, 3, dtype=np.uint8))
+    sizes = [2048, 64, 64 * 15, 1024, 64 * 17, 32768, 64 * 33, 2 * 32768, 64 * 31, 1024 + 64, 4096, 64 * 47, 32768 + 64 * 5]
+    gens = [3 | 16, 2 | 16, 3, 3 | 16, 2, 2 | 16, 3 | 16, 3 | 16, 2 | 16, 3, 2 | 16, 1, 3 | 16]
+    iq = _quiet(n, sum(sizes), seed=31)
+    iq[2] = S.noise(1, sum(sizes), seed=3)[0]          # full-scale bytes: clipping bytes all over
+    iq[3] = S.tone(3, sum(sizes) // 2, seed=2)
+    iq[4, ::4099] = 0
+    out, off = [], 0
+    e.debug_wb_prefilter_counts()
+    for sz, g in zip(sizes, gens):
+        e.debug_set_wbfm_kernel(g)
+        e.accept_iq_host(np.ascontiguousarray(iq[:, off:off + sz]))
+        out.append(e.get_pcm()[0])
+        off += sz
+    mma, simt = e.debug_wb_prefilter_counts()
+    assert mma > 0 and simt > 0
+    pcm = np.concatenate(out, axis=1)
+    exp = _oracle_rows(n, iq)
+    for ch in range(n):
+        assert np.array_equal(pcm[ch], exp[ch]), "channel %d" % ch
+    e.close()
