@@ -274,9 +274,10 @@ class Engine:
         self._ck(self.L.sdr_debug_set_tile_loader(self.h, int(loader)))
 
     def debug_set_wbfm_kernel(self, generation=0):
-        """WBFM kernel generation: 0 = default (3), 1 = table in global memory, 2 = table in shared
-        memory with one channel per worker warp, 3 = two channels per worker warp; + 16 = 2 or 3
-        with the pre-filter on the tensor cores (default: CUDA cores)."""
+        """WBFM kernel generation: 0 = default, 1 = table in global memory, 2 = table in shared memory with
+        one channel per worker warp, 3 = two channels per worker warp, 4 = the pre-filter on the tcgen05
+        tensor cores (geometry of 2 or 3 by bank size; 5 / 6 force two / one channel(s) per warp); + 16 = 2 or 3
+        with the pre-filter on the legacy mma.sync path."""
         self._ck(self.L.sdr_debug_set_wbfm_kernel(self.h, int(generation)))
 
     def debug_wb_prefilter_counts(self):

@@ -59,6 +59,7 @@ struct sdr_engine {
   int tile_loader = 2;  // 0 = cp.async (two slot buffers), 2 / 3 / 4 = TMA with that many slot buffers
   bool stage1_mma = false;  // with TMA: stage 1 of the AM / SSB cascade on the tensor cores (measured slower)
   int wb_kernel = 0;  // 0 = default (SDR_WB_KERNEL or 3), 1..3 = that generation of the WBFM kernel
+  int wb4_geometry = 0;  // generation 4: 0 = by bank size, 1 = two channels per worker warp, 2 = one
   bool wb_count = false;  // sdr_debug_wb_prefilter_counts was called: the kernels count their tiles
   bool wb_prefilter_mma = false;  // generations 2, 3: the pre-filter on the tensor cores (WbMma; measured: no faster)
   int fir_ctas_per_sm = 5;  // register budget of the FIR kernel: 5 (96 registers) or 6 (80) CTAs per SM
@@ -93,6 +94,7 @@ struct sdr_engine {
   float *d_lut_wbfm_half = nullptr;  // q >= 0 half plane for wbfm_tile2_kernel, [129][256]
   uint32_t *d_fm_tab = nullptr;  // tensor-core tuner tables, fm_mma_table()
   uint32_t *d_wb_tab = nullptr;  // tensor-core WBFM pre-filter table, wb_mma_table()
+  uint8_t *d_wb4_tab = nullptr;  // tap matrices of the tcgen05 WBFM pre-filter, wb_umma_table()
   uint8_t *d_iq = nullptr;
   // two PCM buffers, used by alternate calls: the read-back of call k (sdr_get_pcm, the ingest
   // ring's device->host copy) does not hold up the kernels of call k+1
@@ -613,6 +615,35 @@ int launch_fm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_
   return SDR_OK;
 }
 
+// Tap matrices of the tcgen05 WBFM pre-filter (wbfm_tile4_kernel, WbUmma): D = A * B with A = raw u8 input bytes,
+// 64 per row. B[ks][part] is 32 columns x K = 32: column n = 2 p + arm gives I' (arm 0) or Q' (arm 1) of sample p
+// (0..15) of a group of 16; K step ks covers the raw bytes 32 ks - 32 .. 32 ks - 1 counted from the group's first
+// (complex sample c = kb >> 1 counted from 16 before the group, I at even bytes). Output p is
+// sum_k 2 h[k] x'[16 + p - k] (FirFilter_int16.cc:151-213 with the taps doubled, WbTile::Pre2), x' the rotated sample
+// (IqDataProcessor.cc:567-611; a group starts a rotation period). part 0 / 1: the tap's high / low byte, 256 * hi + lo
+// with both int8. The accumulator starts are not here: WbUmma::start_of, stored into tensor memory by the kernel.
+// Element (n, k) of a matrix sits at WbUmma::b_offset(n, k).
+std::vector<uint8_t> wb_umma_table() {
+  std::vector<uint8_t> tab(WB4_TAB_BYTES, 0);
+  auto part = [](int v, int h) {
+    const int lo = ((v + 128) & 255) - 128;
+    return h == 0 ? (v - lo) / 256 : lo;
+  };
+  for (int kb = 0; kb < 64; ++kb) {
+    const int c = kb >> 1, comp = kb & 1, cm = c & 3;
+    // which arm this raw component feeds at phase cm: I' = I0, -Q1, -I2, Q3; Q' = Q0, I1, -Q2, -I3
+    const int arm = (cm & 1) ? 1 - comp : comp;
+    for (int pp = 0; pp < 16; ++pp) {
+      const int k = 16 + pp - c;
+      if (k < 0 || k >= taps::WB_PRE::N) continue;
+      const int v = WbUmma::sign_of(cm, arm) * 2 * taps::WB_PRE::tap(k);
+      for (int h = 0; h < 2; ++h)
+        tab[((kb >> 5) * 2 + h) * WB4_B_TILE + WbUmma::b_offset(2 * pp + arm, kb & 31)] = (uint8_t)(int8_t)part(v, h);
+    }
+  }
+  return tab;
+}
+
 int wb_tab_ready(sdr_engine *e) {
   if (!e->d_wb_tab) {
     const std::vector<uint32_t> tab = wb_mma_table();
@@ -736,6 +767,68 @@ int launch_wbfm_tile2(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint
   return SDR_OK;
 }
 
+// wbfm_tile4_kernel: the pre-filter on the tcgen05 tensor cores; two channels per worker warp for banks that need more
+// than one wave of one-channel-per-warp CTAs (as generation 3 against 2), else one
+int launch_wbfm_tile4(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples, int fmt,
+                      cudaStream_t stream) {
+  const int kind = SDR_KIND_WBFM;
+  const uint32_t n_list = (uint32_t)e->list[kind].size();
+  const int max_workers = WB4_MAX_WARPS - 2;
+  static const int two_env = getenv("SDR_WB4_TWO") ? atoi(getenv("SDR_WB4_TWO")) : -1;  // tuning override
+  const bool two = e->wb4_geometry ? e->wb4_geometry == 1
+                   : two_env >= 0  ? two_env != 0
+                                   : n_list > (uint32_t)(max_workers - 1) * (uint32_t)e->n_sm;
+  static const int g_env = getenv("SDR_WB_G") ? atoi(getenv("SDR_WB_G")) : 0;  // tuning override
+  const long max_g = g_env ? g_env : (two ? 2 : 1) * max_workers;
+  const long slots = e->n_sm;
+  const long W = ((long)n_list + slots * max_g - 1) / (slots * max_g);
+  uint32_t G = (uint32_t)(((long)n_list + slots * W - 1) / (slots * W));
+  if (e->shape[kind].G) G = e->shape[kind].G;
+  if (two) G = (G + 1) & ~1u;
+  if (G > (uint32_t)max_g) G = (uint32_t)max_g;
+  if (G < (two ? 2u : 1u)) G = two ? 2 : 1;
+  const int workers = two ? (int)G / 2 : (int)G;
+  const int rec = std::min(workers, (int)WbTile2::REC_WARP);
+  const int n_slots = rec < workers ? workers + 1 : workers;
+  const int smem = two ? WbUmma::smem_bytes<true>(workers, n_slots) : WbUmma::smem_bytes<false>(workers, n_slots);
+  if (!e->d_wb4_tab) {
+    const std::vector<uint8_t> tab = wb_umma_table();
+    SDR_CK(e, cudaMalloc(&e->d_wb4_tab, tab.size()));
+    SDR_CK(e, cudaMemcpy(e->d_wb4_tab, tab.data(), tab.size(), cudaMemcpyHostToDevice));
+  }
+  LaunchParams p = {};
+  p.iq = iq;
+  p.ch_stride = ch_stride;
+  p.n_samples = n_samples;
+  p.fmt = fmt;
+  p.chan_ids = e->d_list[kind];
+  p.n_list = n_list;
+  p.G = G;
+  p.state = e->d_state[kind];
+  p.state_stride = (uint32_t)WbTile::STATE_BYTES;
+  p.scale = e->d_scale[kind];
+  p.lsb = e->d_lsb;
+  p.pcm = e->pcm_of(e->seq);
+  p.pcm_stride = e->pcm_stride;
+  p.lut = e->d_lut_wbfm_half;
+  p.aux = (uint32_t)rec;
+  p.tab = reinterpret_cast<const uint32_t *>(e->d_wb4_tab);
+  p.counters = e->wb_count ? e->d_counters : nullptr;  // one atomic per tile: only when somebody asked
+  p.scratch = nullptr;
+  p.allowed = e->last_gated ? e->d_allowed[e->seq % (uint64_t)e->ring] : nullptr;
+  const uint32_t grid = (n_list + G - 1) / G;
+  if (two) {
+    SDR_CK(e, cudaFuncSetAttribute(wbfm_tile4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    wbfm_tile4_kernel<true><<<grid, 32 * (workers + 2), smem, stream>>>(p);
+  } else {
+    SDR_CK(e, cudaFuncSetAttribute(wbfm_tile4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    wbfm_tile4_kernel<false><<<grid, 32 * (workers + 2), smem, stream>>>(p);
+  }
+  SDR_CK(e, cudaGetLastError());
+  e->launches++;
+  return SDR_OK;
+}
+
 int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_t n_samples, int fmt,
                      cudaStream_t stream) {
   using T = WbTile;
@@ -749,6 +842,7 @@ int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint3
   // below that (the WBFM share of a mixed bank) it would only halve the workers per CTA.
   int gen = e->wb_kernel ? e->wb_kernel : gen_env;
   if (!e->wb_kernel && gen == 3 && n_list <= (uint32_t)(WbTile2::MAX_WORKERS - 1) * (uint32_t)e->n_sm) gen = 2;
+  if (gen == 4 && e->d_lut_wbfm_half) return launch_wbfm_tile4(e, iq, ch_stride, n_samples, fmt, stream);
   if (gen == 3 && e->d_lut_wbfm_half) return launch_wbfm_tile3(e, iq, ch_stride, n_samples, fmt, stream);
   if (gen != 1 && e->d_lut_wbfm_half) return launch_wbfm_tile2(e, iq, ch_stride, n_samples, fmt, stream);
   // one CTA per SM (the rings fill shared memory): spread the channels evenly over the waves
@@ -1097,6 +1191,7 @@ int sdr_engine_destroy(sdr_engine *e) {
   cudaFree(e->d_lut_fm);
   cudaFree(e->d_fm_tab);
   cudaFree(e->d_wb_tab);
+  cudaFree(e->d_wb4_tab);
   cudaFree(e->d_am_tab);
   cudaFree(e->d_lut_wbfm);
   cudaFree(e->d_lut_wbfm_half);
@@ -1215,12 +1310,26 @@ int sdr_debug_set_dc_shape(sdr_engine *e, uint32_t seg_count, uint32_t warm_rows
 
 // which generation of the WBFM kernel runs (0 = default); the three share the carry blob, so a test
 // may switch between calls
-// + 16: generations 2 and 3 with the pre-filter on the tensor cores (WbMma; default: CUDA cores)
+// 4 = the pre-filter on the tcgen05 tensor cores (5, 6: with two / one channel(s) per worker warp whatever the
+// bank's size); + 16: generations 2 and 3 with the pre-filter on the legacy mma.sync path (WbMma)
 int sdr_debug_set_wbfm_kernel(sdr_engine *e, int generation) {
-  if (!e || generation < 0 || (generation & ~16) > 3) return SDR_E_ARG;
-  e->wb_kernel = generation & ~16;
+  if (!e || generation < 0 || (generation & ~16) > 6 || ((generation & 16) && (generation & ~16) > 3)) return SDR_E_ARG;
+  // 5, 6: generation 4 with two / one channel(s) per worker warp whatever the bank's size
+  e->wb4_geometry = (generation & ~16) > 4 ? (generation & ~16) - 4 : 0;
+  e->wb_kernel = std::min(generation & ~16, 4);
   e->wb_prefilter_mma = (generation & 16) != 0;
   return SDR_OK;
+}
+
+// wb_umma_table() and the accumulator starts for the CPU-side check of the tcgen05 formulation
+// (tests/test_wb_umma_table.py): 4096 bytes of tap matrices; starts[2 p + arm] for p = 0..3
+int sdr_debug_wb_umma_table(uint8_t *taps_out, int32_t *starts_out) {
+  if (!taps_out || !starts_out) return SDR_E_ARG;
+  const std::vector<uint8_t> tab = wb_umma_table();
+  memcpy(taps_out, tab.data(), tab.size());
+  for (int pp = 0; pp < 4; ++pp)
+    for (int arm = 0; arm < 2; ++arm) starts_out[2 * pp + arm] = WbUmma::start_of(pp, arm);
+  return (int)tab.size();
 }
 
 // wb_mma_table() for the CPU-side check of the tensor-core formulation (tests/test_wb_mma_table.py)

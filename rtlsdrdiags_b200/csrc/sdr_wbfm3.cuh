@@ -344,7 +344,8 @@ __global__ void __launch_bounds__(32 * (WbTile3::MAX_WORKERS + 1), 1) wbfm_tile3
             pairs = WbMma::prefilter<true>((uint32_t)__cvta_generic_to_shared(area), tab_s, lane, active);
           __syncwarp();
           // diagnostics: [1] = tiles whose pre-filter ran on the tensor cores, [2] = on the CUDA cores
-          if (lane == 0 && p.counters) atomicAdd(p.counters + (pairs ? 1 : 2), 1u);
+          const bool warp_live = __any_sync(FULL, active);
+          if (lane == 0 && p.counters && warp_live) atomicAdd(p.counters + (pairs ? 1 : 2), 1u);
         }
         uint32_t w[16];
         tile_read(in_slot, lane, w);

@@ -110,13 +110,15 @@ def _quiet(n, nbytes, seed, amp=45.0):
     return np.clip(np.round(x), 1, 255).astype(np.uint8)
 
 
-@pytest.mark.parametrize("gen", [2, 3])
-@pytest.mark.parametrize("n", [1, 2, 29, 61])
+@pytest.mark.parametrize("gen", [2 | 16, 3 | 16, 5, 6])
+@pytest.mark.parametrize("n", [1, 2, 29, 61, 330])
 def test_tensor_core_prefilter(gen, n):
-    """The pre-filter as an int8 GEMM on the raw bytes (WbMma::prefilter; an option, generation + 16): streams
-    without a clipping byte take it for every full (half-)tile; a raw byte 0 where the Fs/4 rotation negates sends exactly
-    the tiles that see it -- the one that holds it and, through the 15 samples of history, the next --
-    down the CUDA-core path. Bit-exact against the oracle either way, and against the CUDA-core build."""
+    """The pre-filter as an int8 GEMM on the raw bytes: generation 4 (tcgen05.mma, accumulators in tensor
+    memory; 5 / 6 = with two / one channel(s) per worker warp) and the legacy mma.sync option of generations
+    2 and 3 (+ 16). Streams without a clipping byte take the tensor cores for every full (half-)tile; a raw
+    byte 0 where the Fs/4 rotation negates sends exactly the tiles that see it -- the one that holds it and,
+    through the 15 samples of history, the next -- down the CUDA-core path. Bit-exact against the oracle
+    either way, and against the CUDA-core kernel."""
     import rtlsdrdiags_b200 as R
     nbytes = 2 * 32768
     iq = _quiet(n, nbytes, seed=100 + n)
@@ -125,31 +127,31 @@ def test_tensor_core_prefilter(gen, n):
     iq[0, 2048 * 9 + 2044] = 0                # I2 of the tile's last group: this tile and the next fall back
     iq[n - 1, 1024 * 21 + 7] = 255
     exp = _oracle_rows(n, iq)
+    two = gen in (3 | 16, 5)                  # two channels per worker warp: half-tiles, one count per warp
     outs = {}
-    for flag in (16, 0):
+    for g in (gen, 3):
         e = R.Engine(n, 0, nbytes)
         e.set_modes(np.full(n, 3, dtype=np.uint8))
-        e.debug_set_wbfm_kernel(gen | flag)
+        e.debug_set_wbfm_kernel(g)
         e.debug_wb_prefilter_counts()
         pcm, counts = e.demodulate(iq)
         assert (counts == nbytes // 64).all()
-        outs[flag] = pcm.copy()
+        outs[g] = pcm.copy()
         mma, simt = e.debug_wb_prefilter_counts()
-        per_ch = nbytes // (2048 if gen == 2 else 1024)
-        units = n * per_ch if gen == 2 else ((n + 1) // 2) * per_ch   # gen 3: one count per warp and half-tile pair
-        if flag == 0:
-            assert (mma, simt) == (0, 0)     # the CUDA-core build does not count
+        units = ((n + 1) // 2) * (nbytes // 1024) if two else n * (nbytes // 2048)
+        if g == 3:
+            assert (mma, simt) == (0, 0)     # the CUDA-core kernel does not count
         else:
             assert mma + simt == units
             assert simt == 3, (mma, simt)      # the tile with the Q1 byte; the one with the I2 byte and its successor
         e.close()
     for ch in range(n):
-        assert np.array_equal(outs[16][ch], exp[ch]), "channel %d" % ch
-    assert np.array_equal(outs[0], outs[16])
+        assert np.array_equal(outs[gen][ch], exp[ch]), "channel %d" % ch
+    assert np.array_equal(outs[gen], outs[3])
 
 
 def test_tensor_core_prefilter_ragged_calls_and_switches():
-    """Call lengths that leave partial (half-)tiles, both kernel generations and both pre-filter builds
+    """Call lengths that leave partial (half-)tiles, every kernel generation and pre-filter build
     alternating between calls on the same streams: the raw history in shared memory and the planes in the
     carry blob are two views of the same 16 samples."""
     import rtlsdrdiags_b200 as R
@@ -157,7 +159,7 @@ def test_tensor_core_prefilter_ragged_calls_and_switches():
     e = R.Engine(n, 0, 4 * 32768)
     e.set_modes(np.full(n, 3, dtype=np.uint8))
     sizes = [2048, 64, 64 * 15, 1024, 64 * 17, 32768, 64 * 33, 2 * 32768, 64 * 31, 1024 + 64, 4096, 64 * 47, 32768 + 64 * 5]
-    gens = [3 | 16, 2 | 16, 3, 3 | 16, 2, 2 | 16, 3 | 16, 3 | 16, 2 | 16, 3, 2 | 16, 1, 3 | 16]
+    gens = [5, 2 | 16, 3, 6, 2, 5, 3 | 16, 6, 5, 3, 4, 1, 5]
     iq = _quiet(n, sum(sizes), seed=31)
     iq[2] = S.noise(1, sum(sizes), seed=3)[0]          # full-scale bytes: clipping bytes all over
     iq[3] = S.tone(3, sum(sizes) // 2, seed=2)
@@ -172,6 +174,29 @@ def test_tensor_core_prefilter_ragged_calls_and_switches():
     mma, simt = e.debug_wb_prefilter_counts()
     assert mma > 0 and simt > 0
     pcm = np.concatenate(out, axis=1)
+    exp = _oracle_rows(n, iq)
+    for ch in range(n):
+        assert np.array_equal(pcm[ch], exp[ch]), "channel %d" % ch
+    e.close()
+
+
+@pytest.mark.parametrize("gen,per_cta", [(5, 28), (6, 14), (5, 10), (6, 5)])
+def test_generation4_full_ctas(gen, per_cta):
+    """Generation 4 with as many channels per CTA as a large bank gets (28 = 14 worker warps x 2, or 14 x 1):
+    every M-block, the hole at the recurrence warp's slot, the MMA warp as warp 15."""
+    import rtlsdrdiags_b200 as R
+    n, nbytes = 61, 32768
+    e = R.Engine(n, 0, nbytes)
+    e.set_modes(np.full(n, 3, dtype=np.uint8))
+    e.set_launch_shape(R.KIND_WBFM, per_cta, 0)
+    e.debug_set_wbfm_kernel(gen)
+    iq = _quiet(n, 2 * nbytes, seed=77)
+    iq[7, 5000] = 0
+    iq[33] = S.noise(1, 2 * nbytes, seed=5)[0]
+    e.debug_wb_prefilter_counts()
+    pcm, counts = e.demodulate(iq)
+    mma, simt = e.debug_wb_prefilter_counts()
+    assert mma > simt > 0
     exp = _oracle_rows(n, iq)
     for ch in range(n):
         assert np.array_equal(pcm[ch], exp[ch]), "channel %d" % ch
