@@ -42,9 +42,9 @@ METRIC = "aggregate_iq_msamples_per_s"
 # (dc_block_kernel) runs one step behind on a second stream and is inside the timed region.
 KERNELS = {"am": "amssb_fir_kernel<false> (+ dc_block_kernel overlapped on the second stream)",
            "ssb": "amssb_fir_kernel<true> (+ dc_block_kernel overlapped on the second stream)",
-           "fm": "fm_tile_kernel", "wbfm": "wbfm_tile2_kernel",
+           "fm": "fm_tile_kernel", "wbfm": "wbfm_tile4_kernel<true> (tcgen05 pre-filter, two channels per worker warp)",
            "mixed": "amssb_fir_kernel<false> + amssb_fir_kernel<true> + 2 x dc_block_kernel + fm_tile_kernel + "
-                    "wbfm_tile2_kernel (the step is timed as a whole)"}
+                    "wbfm_tile2_kernel<false> (the step is timed as a whole)"}
 # BASELINE.json configs per GPU count: (workload, total channels, scaling label)
 BASELINE_CONFIGS = {1: ("am", 1024, "weak"), 2: ("ssb", 16384, "strong"), 4: ("ssb", 16384, "strong"),
                     8: ("mixed", 65536, "weak")}

@@ -53,8 +53,9 @@ struct LaunchParams {
   // dc_block_kernel: a call's rows (32 PCM samples each) are cut into seg_count segments of
   // seg_rows rows per channel; a segment warms up on the warm_rows rows before it
   uint32_t seg_count, seg_rows, warm_rows;
-  uint32_t *counters;        // diagnostics: [0] = segments dc_block_kernel had to redo serially; [1], [2] =
-                             // WBFM (half-)tiles whose pre-filter ran on the tensor / CUDA cores
+  uint32_t *counters;        // [0] = segments dc_block_kernel had to redo serially (diagnostics); [1], [2] = WBFM
+                             // (half-)tiles whose pre-filter ran on the tensor / CUDA cores (diagnostics; generation 4:
+                             // when call_id != 0); [3] = generation 4: (half-)tiles a clipping byte kept off the tensor cores
 };
 
 #if SDR_DEVICE_BUILD

@@ -58,7 +58,11 @@ struct sdr_engine {
   // IQ array, rebuilt when pointer, stride or length change) or by cp.async
   int tile_loader = 2;  // 0 = cp.async (two slot buffers), 2 / 3 / 4 = TMA with that many slot buffers
   bool stage1_mma = false;  // with TMA: stage 1 of the AM / SSB cascade on the tensor cores (measured slower)
-  int wb_kernel = 0;  // 0 = default (SDR_WB_KERNEL or 3), 1..3 = that generation of the WBFM kernel
+  int wb_kernel = 0;  // 0 = default (SDR_WB_KERNEL, or 4 / 2 by bank size), 1..4 = that generation of the WBFM kernel
+  volatile uint32_t *h_wb_clip = nullptr;  // pinned: counters[3] after the last generation-4 launch that has finished
+  uint32_t wb_clip_seen = 0;               // its value when last looked at
+  uint64_t wb4_units = 0;                  // (half-)tiles per worker warp in the last generation-4 launch
+  int wb_clip_hold = 0;                    // calls left on generation 3 because the input clips
   int wb4_geometry = 0;  // generation 4: 0 = by bank size, 1 = two channels per worker warp, 2 = one
   bool wb_count = false;  // sdr_debug_wb_prefilter_counts was called: the kernels count their tiles
   bool wb_prefilter_mma = false;  // generations 2, 3: the pre-filter on the tensor cores (WbMma; measured: no faster)
@@ -724,6 +728,12 @@ int launch_wbfm_tile2(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint
   const long slots = e->n_sm;
   const long W = ((long)n_list + slots * max_g - 1) / (slots * max_g);
   uint32_t G = (uint32_t)(((long)n_list + slots * W - 1) / (slots * W));
+  // A round is as long as the recurrence warp's 1024 dependent steps whatever the number of workers up to 14, and
+  // a CTA keeps its SM to itself: when other modes share the GPU, 14 channels per CTA cost this kernel nothing and
+  // leave them the SMs it does not need (mixed x8192: 0.373 -> 0.348 ms, profiles/r02_wbfm4.txt)
+  bool others = false;
+  for (int k2 = SDR_KIND_AM; k2 <= SDR_KIND_SSB; ++k2) others = others || (k2 != kind && !e->list[k2].empty());
+  if (others) G = (uint32_t)max_g;
   static const int gx_env = getenv("SDR_WB_GX") ? atoi(getenv("SDR_WB_GX")) : 0;  // exact, for sweeps
   if (gx_env) G = (uint32_t)gx_env;
   if (e->shape[kind].G) G = e->shape[kind].G;
@@ -783,6 +793,8 @@ int launch_wbfm_tile4(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint
   const long slots = e->n_sm;
   const long W = ((long)n_list + slots * max_g - 1) / (slots * max_g);
   uint32_t G = (uint32_t)(((long)n_list + slots * W - 1) / (slots * W));
+  static const int gx_env = getenv("SDR_WB_GX") ? atoi(getenv("SDR_WB_GX")) : 0;  // exact, for sweeps
+  if (gx_env) G = (uint32_t)gx_env;
   if (e->shape[kind].G) G = e->shape[kind].G;
   if (two) G = (G + 1) & ~1u;
   if (G > (uint32_t)max_g) G = (uint32_t)max_g;
@@ -813,7 +825,8 @@ int launch_wbfm_tile4(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint
   p.lut = e->d_lut_wbfm_half;
   p.aux = (uint32_t)rec;
   p.tab = reinterpret_cast<const uint32_t *>(e->d_wb4_tab);
-  p.counters = e->wb_count ? e->d_counters : nullptr;  // one atomic per tile: only when somebody asked
+  p.counters = e->d_counters;
+  p.call_id = e->wb_count ? 1 : 0;  // the per-tile diagnostic counters: one atomic per tile, only when somebody asked
   p.scratch = nullptr;
   p.allowed = e->last_gated ? e->d_allowed[e->seq % (uint64_t)e->ring] : nullptr;
   const uint32_t grid = (n_list + G - 1) / G;
@@ -825,6 +838,11 @@ int launch_wbfm_tile4(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint
     wbfm_tile4_kernel<false><<<grid, 32 * (workers + 2), smem, stream>>>(p);
   }
   SDR_CK(e, cudaGetLastError());
+  // how many (half-)tiles clipping bytes kept off the tensor cores, for launch_wbfm_tile's choice of kernel: read by
+  // a later call, whenever the copy has landed
+  if (!e->h_wb_clip) SDR_CK(e, cudaHostAlloc(&e->h_wb_clip, 16, cudaHostAllocDefault));
+  SDR_CK(e, cudaMemcpyAsync((void *)e->h_wb_clip, e->d_counters + 3, 4, cudaMemcpyDeviceToHost, stream));
+  e->wb4_units = (uint64_t)((n_list + (two ? 1 : 0)) / (two ? 2 : 1)) * ((n_samples + (two ? 511 : 1023)) / (two ? 512 : 1024));
   e->launches++;
   return SDR_OK;
 }
@@ -835,13 +853,34 @@ int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint3
   const int kind = SDR_KIND_WBFM;
   const uint32_t n_list = (uint32_t)e->list[kind].size();
   if (n_list == 0) return SDR_OK;
-  // SDR_WB_KERNEL=1 / 2 select the first- / second-generation kernel (1: table gathered from global
-  // memory; 2: one channel per worker warp); the default is the third (two channels per worker warp)
-  static const int gen_env = getenv("SDR_WB_KERNEL") ? atoi(getenv("SDR_WB_KERNEL")) : 3;
-  // The third generation pays off once a bank needs more than one wave of one-channel-per-warp CTAs;
-  // below that (the WBFM share of a mixed bank) it would only halve the workers per CTA.
+  // SDR_WB_KERNEL=1 .. 4 select a generation of the kernel (1: table gathered from global memory; 2: table in shared
+  // memory, one channel per worker warp; 3: two channels per worker warp; 4: 3's or 2's geometry with the pre-filter
+  // on the tcgen05 tensor cores). Default: 4 once a bank needs more than one wave of one-channel-per-warp CTAs --
+  // two channels per warp halve the recurrence warp's chain per round and the round is worker-bound, which is where
+  // taking the pre-filter off the CUDA cores pays (WBFM x8192: 0.785 -> 0.700 ms); below that (the WBFM share of a
+  // mixed bank) the round is bound by the 1024-step chain whatever the workers do, and 2 has the least overhead.
+  static const int gen_env = getenv("SDR_WB_KERNEL") ? atoi(getenv("SDR_WB_KERNEL")) : 0;
   int gen = e->wb_kernel ? e->wb_kernel : gen_env;
-  if (!e->wb_kernel && gen == 3 && n_list <= (uint32_t)(WbTile2::MAX_WORKERS - 1) * (uint32_t)e->n_sm) gen = 2;
+  const bool small_bank = n_list <= (uint32_t)(WbTile2::MAX_WORKERS - 1) * (uint32_t)e->n_sm;
+  if (gen == 0) {
+    gen = small_bank ? 2 : 4;
+    // A bank whose input clips (raw bytes 0 where the rotation negates) gets nothing from generation 4 but its
+    // overhead (+24 % when every tile falls back): if more than a quarter of the last observed launch fell back,
+    // the next 64 calls take generation 3, then generation 4 is tried again.
+    if (gen == 4) {
+      if (e->h_wb_clip) {
+        const uint32_t seen = *e->h_wb_clip;
+        if ((uint64_t)(seen - e->wb_clip_seen) * 4 > e->wb4_units) e->wb_clip_hold = 64;
+        e->wb_clip_seen = seen;
+      }
+      if (e->wb_clip_hold > 0) {
+        --e->wb_clip_hold;
+        gen = 3;
+      }
+    }
+  } else if (!e->wb_kernel && gen == 3 && small_bank) {
+    gen = 2;
+  }
   if (gen == 4 && e->d_lut_wbfm_half) return launch_wbfm_tile4(e, iq, ch_stride, n_samples, fmt, stream);
   if (gen == 3 && e->d_lut_wbfm_half) return launch_wbfm_tile3(e, iq, ch_stride, n_samples, fmt, stream);
   if (gen != 1 && e->d_lut_wbfm_half) return launch_wbfm_tile2(e, iq, ch_stride, n_samples, fmt, stream);
@@ -1192,6 +1231,7 @@ int sdr_engine_destroy(sdr_engine *e) {
   cudaFree(e->d_fm_tab);
   cudaFree(e->d_wb_tab);
   cudaFree(e->d_wb4_tab);
+  if (e->h_wb_clip) cudaFreeHost((void *)e->h_wb_clip);
   cudaFree(e->d_am_tab);
   cudaFree(e->d_lut_wbfm);
   cudaFree(e->d_lut_wbfm_half);

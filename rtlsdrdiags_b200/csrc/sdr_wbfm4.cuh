@@ -240,7 +240,7 @@ struct WbUmma {
   __host__ __device__ static constexpr int smem_bytes(int workers, int slots) {
     return WbTile2::LUT_BYTES + slots * TILE_BYTES +
            (TWO ? workers * (2 * WbTile3::RING_BYTES + 2 * WbTile3::ERING_WORDS * 4) : workers * WbTile2::RING_BYTES) + WB4_TAB_BYTES +
-           WB4_HIST_BYTES + 64;
+           WB4_HIST_BYTES + 64;  // + the barrier and the TMEM base
   }
 };
 
@@ -372,6 +372,21 @@ __global__ void __launch_bounds__(32 * WB4_MAX_WARPS, 1) wbfm_tile4_kernel(const
   } else if (is_iir && active) {
     y1 = u2f(blob[T1::NREG * 32]);
   }
+  // The MMA warp's round: after the barrier between the phases it issues the round's MMAs (every input has landed,
+  // every accumulator of the round before has been read and restarted by then); the workers run C(kk - 2) meanwhile.
+  // (Issuing a round earlier, right after the barrier that ends the round before, was measured and lost: 0.776 ms
+  // against 0.705 -- the issue then competes with the hand-over every warp is waiting for.)
+  auto issue_round = [&]() {
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    if (lane == 0) {
+      const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(slot_base), hist_s = (uint32_t)__cvta_generic_to_shared(hist_base);
+      const uint32_t taps_s = (uint32_t)__cvta_generic_to_shared(tab_base);
+      for (int b = 0; 4 * b < n_slots; ++b)
+        U::issue_block(tmem + 128u * b, rows_s + 4u * TILE_BYTES * b, hist_s + 256u * b, taps_s, FIRST_ROWS);
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_s) : "memory");
+    }
+    __syncwarp();
+  };
 
   for (uint32_t kk = 0; kk < n_rounds + 2; ++kk) {
     // ---- phase 1: hand-over through the channel's slot: y(kk-2) out, u(kk-1) in ----
@@ -386,17 +401,7 @@ __global__ void __launch_bounds__(32 * WB4_MAX_WARPS, 1) wbfm_tile4_kernel(const
     __syncthreads();
     // ---- phase 2 ----
     if (is_mma) {
-      if (kk < n_rounds) {
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        if (lane == 0) {
-          const uint32_t rows_s = (uint32_t)__cvta_generic_to_shared(slot_base), hist_s = (uint32_t)__cvta_generic_to_shared(hist_base);
-          const uint32_t taps_s = (uint32_t)__cvta_generic_to_shared(tab_base);
-          for (int b = 0; 4 * b < n_slots; ++b)
-            U::issue_block(tmem + 128u * b, rows_s + 4u * TILE_BYTES * b, hist_s + 256u * b, taps_s, FIRST_ROWS);
-          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_s) : "memory");
-        }
-        __syncwarp();
-      }
+      if (kk < n_rounds) issue_round();
     } else if (is_worker) {
       if (kk >= 2) {
         const uint32_t t = kk - 2;
@@ -427,7 +432,9 @@ __global__ void __launch_bounds__(32 * WB4_MAX_WARPS, 1) wbfm_tile4_kernel(const
         if (lw == r - 1) U::history_from_window(hist, w);
         if (kk + 1 < n_rounds) fetch(kk + 1);  // the input slot is free again
         cp_async_commit();
-        if (lane == 0 && p.counters && any_active) atomicAdd(p.counters + (umma_ok ? 1 : 2), 1u);  // diagnostics (tests only)
+        if (lane == 0 && p.call_id && any_active) atomicAdd(p.counters + (umma_ok ? 1 : 2), 1u);  // diagnostics (tests only)
+        // for the engine: how much of this launch the tensor cores could not do (it moves a clipping bank to generation 3)
+        if (lane == 0 && !umma_ok && r == ROWS && p.fmt == FMT_U8_OFFSET_ROTATE && any_active) atomicAdd(p.counters + 3, 1u);
         if (umma_ok) {
           U::template part_a<TWO>(taddr, k, lut_s, pv, v_boundary, u, lane);
         } else {

@@ -55,7 +55,6 @@ __device__ __forceinline__ void wb_u4(const float (&th)[4], float k, float &th_p
     v_prev = v;
   }
 }
-
 struct WbMma {
   // Shared-memory layout of a worker's input area when the pre-filter runs here: every channel's data is
   // preceded by WB_HIST_AREA bytes that hold, in their first 32, granules 3 and 2 of the window before the

@@ -201,3 +201,32 @@ def test_generation4_full_ctas(gen, per_cta):
     for ch in range(n):
         assert np.array_equal(pcm[ch], exp[ch]), "channel %d" % ch
     e.close()
+
+
+def test_clipping_bank_moves_to_generation_3():
+    """The default kernel of a large bank is generation 4; when more than a quarter of a launch's (half-)tiles
+    held a clipping byte and fell back to the CUDA cores, the engine takes generation 3 for the next calls.
+    The streams do not notice."""
+    import rtlsdrdiags_b200 as R
+    n, nbytes, calls = 2200, 4096, 3            # more than 14 x 148 channels: a 'large' bank
+    e = R.Engine(n, 0, nbytes)
+    e.set_modes(np.full(n, 3, dtype=np.uint8))
+    iq = _quiet(n, calls * nbytes, seed=9)
+    iq[:, nbytes:] = S.noise(n, (calls - 1) * nbytes, seed=10)      # from the second call on: full-scale bytes
+    e.debug_wb_prefilter_counts()
+    seen, out = [], []
+    for c in range(calls):
+        e.accept_iq_host(np.ascontiguousarray(iq[:, c * nbytes:(c + 1) * nbytes]))
+        out.append(e.get_pcm()[0])
+        seen.append(e.debug_wb_prefilter_counts())
+    units = (n // 2) * (nbytes // 1024)
+    assert seen[0] == (units, 0), (seen, units)                     # clean input: the tensor cores
+    # clipping input: generation 4 fell back (but for the odd half-tile pair without a byte 0 in a negated position) ...
+    assert seen[1][0] + seen[1][1] == 2 * units and seen[1][1] > 0.9 * units, (seen, units)
+    assert seen[2] == seen[1], (seen, units)                        # ... and the third call ran generation 3
+    pcm = np.concatenate(out, axis=1)
+    some = [0, 1, 2, 777, 1023, 1024, 2198, 2199]
+    exp = _oracle_rows(len(some), iq[some])
+    for i, ch in enumerate(some):
+        assert np.array_equal(pcm[ch], exp[i]), "channel %d" % ch
+    e.close()
