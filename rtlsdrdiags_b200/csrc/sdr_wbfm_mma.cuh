@@ -174,6 +174,7 @@ struct WbMma {
       imma_more(hi[1], a1h, ld[0], ld[1]); imma_more(lo[1], a1l, ld[0], ld[1]);
       imma_more(hi[2], a1h, lc[2], lc[3]); imma_more(lo[2], a1l, lc[2], lc[3]);
       imma_more(hi[3], a1h, ld[2], ld[3]); imma_more(lo[3], a1l, ld[2], ld[3]);
+      __syncwarp();  // every lane has its fragments: the windows may be overwritten
 #pragma unroll
       for (int j = 0; j < 4; ++j)
 #pragma unroll
