@@ -867,6 +867,8 @@ int launch_wbfm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint3
     // A bank whose input clips (raw bytes 0 where the rotation negates) gets nothing from generation 4 but its
     // overhead (+24 % when every tile falls back): if more than a quarter of the last observed launch fell back,
     // the next 64 calls take generation 3, then generation 4 is tried again.
+    // input that is already signed and rotated never takes the tensor cores (the tap matrices are the u8 format's)
+    if (gen == 4 && fmt != FMT_U8_OFFSET_ROTATE) gen = 3;
     if (gen == 4) {
       if (e->h_wb_clip) {
         const uint32_t seen = *e->h_wb_clip;

@@ -230,3 +230,29 @@ def test_clipping_bank_moves_to_generation_3():
     for i, ch in enumerate(some):
         assert np.array_equal(pcm[ch], exp[i]), "channel %d" % ch
     e.close()
+
+
+@pytest.mark.parametrize("gen", [5, 6])
+def test_generation4_signed_input_and_format_switches(gen):
+    """Input that is already signed and rotated (IQ_S8_ROTATED) never takes the tensor cores: generation 4 runs
+    its CUDA-core path for those calls (the engine's default would pick generation 3 for them), and a stream may
+    change format between calls -- the history record is raw bytes of whichever format the call had."""
+    import rtlsdrdiags_b200 as R
+    n, nbytes, calls = 9, 8192, 4
+    e = R.Engine(n, 0, nbytes)
+    e.set_modes(np.full(n, 3, dtype=np.uint8))
+    e.debug_set_wbfm_kernel(gen)
+    iq = _quiet(n, calls * nbytes, seed=44)
+    out = []
+    for c in range(calls):
+        piece = np.ascontiguousarray(iq[:, c * nbytes:(c + 1) * nbytes])
+        if c % 2 == 0:
+            e.accept_iq_host(piece)
+        else:
+            e.accept_iq_host(np.stack([O.front_end(piece[ch]) for ch in range(n)]), R.IQ_S8_ROTATED)
+        out.append(e.get_pcm()[0])
+    pcm = np.concatenate(out, axis=1)
+    exp = _oracle_rows(n, iq)
+    for ch in range(n):
+        assert np.array_equal(pcm[ch], exp[ch]), "channel %d" % ch
+    e.close()
