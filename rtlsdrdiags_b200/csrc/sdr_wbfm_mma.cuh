@@ -1,4 +1,5 @@
-// WBFM pre-demodulation filter on the tensor cores.
+// WBFM pre-demodulation filter on the LEGACY tensor path (mma.sync): an option of generations 2 and 3, measured and
+// not faster. The version that pays is generation 4 (tcgen05, sdr_wbfm4.cuh).
 //
 // The 16-tap pre-filter (WbFmDemodulator.cc:17-35, 389-398) runs at the full 256 kS/s on both arms:
 // 32 multiply-adds per complex sample, 512 IDP.2A per 1024-sample tile and lane on the half-rate
@@ -55,6 +56,7 @@ __device__ __forceinline__ void wb_u4(const float (&th)[4], float k, float &th_p
     v_prev = v;
   }
 }
+
 struct WbMma {
   // Shared-memory layout of a worker's input area when the pre-filter runs here: every channel's data is
   // preceded by WB_HIST_AREA bytes that hold, in their first 32, granules 3 and 2 of the window before the
