@@ -107,10 +107,12 @@ SDR_DEV float wrap_pi(float d) {
 // arbitrary floats.
 SDR_DEV float wrap_pi_table(float d) {
   const float PI_F = 3.14159274101257324f;
-  const uint32_t s = f2u(d) & 0x80000000u;
-  const float hi = u2f(0x40C90FDBu | s);   // copysign((float)(2 pi), d)
-  const float lo = u2f(0xB43BBD2Eu ^ s);   // copysign(2 pi - (float)(2 pi), ..) = -1.7484555e-7 * sign
-  const float w = fsub(fsub(d, hi), lo);
+  // d -+ HI, then +- |LO|, each rounded once: with sgn = copysign(1, d) both steps are an FMA whose product is exact
+  // (sgn * constant), i.e. the same two roundings as fsub(fsub(d, copysign(HI, d)), copysign(LO, -d)) -- and three
+  // instructions instead of five
+  const float sgn = u2f((f2u(d) & 0x80000000u) | 0x3F800000u);
+  const float w = ffma(sgn, u2f(0x343BBD2Eu) /* (float)(2 pi) - 2 pi = 1.7484555e-7 */,
+                       ffma(sgn, u2f(0xC0C90FDBu) /* -(float)(2 pi) */, d));
   return fabsf(d) >= PI_F ? w : d;
 }
 

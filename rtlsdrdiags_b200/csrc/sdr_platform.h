@@ -71,6 +71,7 @@ SDR_DEV void stg_u32(void *p, uint32_t v) { *reinterpret_cast<uint32_t *>(p) = v
 SDR_DEV float fmul(float a, float b) { return __fmul_rn(a, b); }
 SDR_DEV float fadd(float a, float b) { return __fadd_rn(a, b); }
 SDR_DEV float fsub(float a, float b) { return __fsub_rn(a, b); }
+SDR_DEV float ffma(float a, float b, float c) { return __fmaf_rn(a, b, c); }  // ONE rounding: only where that is what is wanted
 SDR_DEV float dadd_to_f(float a, double b) { return __double2float_rn(__dadd_rn((double)a, b)); }
 SDR_DEV int f2i_rz(float v) { return __float2int_rz(v); }
 SDR_DEV float i2f(int v) { return __int2float_rn(v); }
@@ -117,6 +118,7 @@ SDR_DEV void stg_u32(void *p, uint32_t v) { sts(p, v); }
 SDR_DEV float fmul(float a, float b) { volatile float r = a * b; return r; }
 SDR_DEV float fadd(float a, float b) { volatile float r = a + b; return r; }
 SDR_DEV float fsub(float a, float b) { volatile float r = a - b; return r; }
+SDR_DEV float ffma(float a, float b, float c) { return fmaf(a, b, c); }
 SDR_DEV float dadd_to_f(float a, double b) { return (float)((double)a + b); }
 SDR_DEV int f2i_rz(float v) {  // saturating, NaN -> 0: what cvt.rzi.s32.f32 does
   if (v != v) return 0;
