@@ -70,14 +70,17 @@ def test_ragged_calls_and_kernel_switches():
     e.close()
 
 
-def test_squelched_half_and_reset():
+@pytest.mark.parametrize("gen", [0, 3, 5, 6])
+def test_squelched_half_and_reset(gen):
     """An odd channel count leaves the last worker warp's second half without a channel; a
     squelched channel shares a warp with an open one; resetDemodulator keeps the de-emphasis state
-    (WbFmDemodulator.cc:304-320)."""
+    (WbFmDemodulator.cc:304-320). Generations 3 and 4 (both geometries; the quiet steps take the tensor
+    cores, the loud ones clip)."""
     import rtlsdrdiags_b200 as R
     n, nbytes = 5, 32768
     e = R.Engine(n, 0, nbytes)
     e.set_modes(np.full(n, 3, dtype=np.uint8))
+    e.debug_set_wbfm_kernel(gen)
     chains = []
     for ch in range(n):
         c = O.OracleChain()
