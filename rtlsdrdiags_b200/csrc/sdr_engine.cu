@@ -66,7 +66,7 @@ struct sdr_engine {
   int wb4_geometry = 0;  // generation 4: 0 = by bank size, 1 = two channels per worker warp, 2 = one
   bool wb_count = false;  // sdr_debug_wb_prefilter_counts was called: the kernels count their tiles
   bool wb_prefilter_mma = false;  // generations 2, 3: the pre-filter on the tensor cores (WbMma; measured: no faster)
-  int fir_ctas_per_sm = 5;  // register budget of the FIR kernel: 5 (96 registers) or 6 (80) CTAs per SM
+  int fir_ctas_per_sm = 5;  // __launch_bounds__ of the FIR kernel: 5 or 6 CTAs per SM (it needs 80 registers either way now)
   uint32_t *d_am_tab = nullptr;  // am_mma_table()
   CUtensorMap tmap;
   const void *tmap_iq = nullptr;
@@ -328,13 +328,15 @@ int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride,
       if (!e->d_scratch[kind][i])
         SDR_CK(e, cudaMalloc(&e->d_scratch[kind][i], (size_t)e->n * max_tiles * 32 * sizeof(int16_t)));
   }
-  // The launch's tiles are dealt out in equal shares to 48 worker warps per SM (12 CTAs of 4
-  // warps, of which 4-5 are resident at a time): shares small enough that SMs which also host
-  // the previous call's recurrence CTAs simply take fewer of them, large enough (>= 8 tiles)
-  // that the warm-up tiles stay in the noise. Measured: profiles/r01v5_am_sweep.txt.
+  // The launch's tiles are dealt out in equal shares to 72 (AM) or 48 (SSB) worker warps per SM: 18 or 12 CTAs of 4
+  // warps, of which six are resident at a time (80 registers since the window rings) -- three or two full waves.
+  // Shares small enough that SMs which also host the previous call's recurrence CTAs simply take fewer of them,
+  // large enough (>= 8 tiles) that the warm-up tiles (AM one, SSB two per share) stay small: AM x1024 x 16 blocks
+  // 0.1148 ms with 48, 0.1124 with 72, 0.1131 with 96; SSB x8192 0.1251 with 48, 0.1270 with 72
+  // (profiles/r02_window_rings.txt; round 1's sweep at 96 registers: profiles/r01v5_am_sweep.txt).
   static const int wps_env = getenv("SDR_AM_WARPS_PER_SM") ? atoi(getenv("SDR_AM_WARPS_PER_SM")) : 0;
   const uint64_t total_tiles = (uint64_t)n_list * n_tiles;
-  uint64_t n_warps = (uint64_t)e->n_sm * (wps_env > 0 ? wps_env : 48);
+  uint64_t n_warps = (uint64_t)e->n_sm * (wps_env > 0 ? wps_env : (SSB ? 48 : 72));
   n_warps = std::min<uint64_t>(n_warps, (total_tiles + 7) / 8);
   n_warps = std::max<uint64_t>(n_warps, 1);
   LaunchParams p = {};

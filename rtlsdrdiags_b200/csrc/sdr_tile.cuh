@@ -293,12 +293,12 @@ struct AmSsbTile {
   // 181/122, Hilbert 372/181), so the float difference is exact and travels as an int16.
   // Updates the carry to this tile's registers rolled by r valid lanes.
   // FULL_TILE: r == 32 is known at compile time (the hot loop); otherwise 1 <= r <= 32.
-  template <bool FULL_TILE = false>
+  template <bool FULL_TILE = false, bool RING = false>
   __device__ __forceinline__ static int tile(const uint32_t (&w)[16], int fmt, bool lsb, AmSsbCarry<SSB> &pv, int lane, int r,
-                                             const PrevMasks &pm) {
+                                             const PrevMasks &pm, uint32_t hring = 0) {
     AmSsbCarry<SSB> cu;
     stage1_simt(w, fmt, pv, cu, lane);
-    return rest<FULL_TILE>(cu, lsb, pv, lane, r, pm);
+    return rest<FULL_TILE, RING>(cu, lsb, pv, lane, r, pm, hring);
   }
 
   // stage 1 on the CUDA cores: front end, then 8 taps 4:1 on each arm (AmDemodulator.cc:349-374
@@ -327,9 +327,13 @@ struct AmSsbTile {
   }
 
   // Everything after stage 1, from cu.s1a0..s1b1 (cu.a7 / cu.b7 are carried along untouched).
-  template <bool FULL_TILE = false>
+  // RING: hring = shared address of the warp's window rings (else: shuffles). A ring is 64 words: [0, 32) = the value of
+  // the 32 lanes before the tile (the carry), [32, 64) = this tile's, so "the lane j below" is a load at an immediate
+  // offset instead of a select, a lane index and a shuffle. Words 0-63: stage 3's window (pv.p / cu.p); words 64-127
+  // (SSB): the Hilbert transformer's (y3b). The caller sets both carries at a piece's start (ring_init).
+  template <bool FULL_TILE = false, bool RING = false>
   __device__ __forceinline__ static int rest(AmSsbCarry<SSB> &cu, bool lsb, AmSsbCarry<SSB> &pv, int lane, int r,
-                                             const PrevMasks &pm) {
+                                             const PrevMasks &pm, uint32_t hring = 0) {
     // stage 2: 12 taps, 4:1
     const uint32_t pa0 = shfl_prev(cu.s1a0, pv.s1a0, 1, lane), pa1 = shfl_prev(cu.s1a1, pv.s1a1, 1, lane);
     const uint32_t pb0 = shfl_prev(cu.s1b0, pv.s1b0, 1, lane), pb1 = shfl_prev(cu.s1b1, pv.s1b1, 1, lane);
@@ -348,8 +352,15 @@ struct AmSsbTile {
     // (I in bytes 0-1, Q in bytes 2-3); position pos meets tap 15 - pos.
     uint32_t q[8];
     q[7] = cu.p;
+    if constexpr (RING) {
+      const uint32_t at = hring + 128u + 4u * lane;
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(at), "r"(cu.p) : "memory");
+      __syncwarp();
+      window_ring<1>(q, at);
+    } else {
 #pragma unroll
-    for (int j = 1; j < 8; ++j) q[7 - j] = shfl_prev_m(cu.p, pv.p, j, lane, pm);
+      for (int j = 1; j < 8; ++j) q[7 - j] = shfl_prev_m(cu.p, pv.p, j, lane, pm);
+    }
     int acc_i = 1 << 14, acc_q = 1 << 14;
     stage3<0>(q, acc_i, acc_q);
     cu.y3a = (int)(int16_t)(acc_i >> 15);
@@ -369,7 +380,15 @@ struct AmSsbTile {
       acc = acc < -0x40000000 ? -0x40000000 : acc;
       const int i_delayed = (int)(int16_t)(acc >> 15);
       int h = (1 << 14) + taps::SSB_HILBERT::tap(0) * cu.y3b;
-      hilbert<2>(h, cu.y3b, pv.y3b, lane);
+      if constexpr (RING) {
+        // the 15 even lanes below through the ring: a store, a warp barrier and 15 loads at immediate offsets
+        // instead of 15 select-and-shuffle pairs
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(hring + 256u + 128u + 4u * lane), "r"(cu.y3b) : "memory");
+        __syncwarp();
+        hilbert_ring<2>(h, hring + 256u + 128u + 4u * lane);
+      } else {
+        hilbert<2>(h, cu.y3b, pv.y3b, lane);
+      }
       const int q_shifted = (int)(int16_t)(h >> 15);
       cu.dem = lsb ? i_delayed - q_shifted : i_delayed + q_shifted;
     }
@@ -391,7 +410,18 @@ struct AmSsbTile {
         pv.y3b = roll_prev(cu.y3b, pv.y3b, r, lane);
       }
     }
+    if constexpr (RING) {
+      __syncwarp();  // every lane has read its windows
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(hring + 4u * lane), "r"(pv.p) : "memory");
+      if constexpr (SSB) asm volatile("st.shared.u32 [%0], %1;" ::"r"(hring + 256u + 4u * lane), "r"(pv.y3b) : "memory");
+    }
     return out;
+  }
+  // the rings' carries at a piece's start
+  __device__ __forceinline__ static void ring_init(uint32_t hring, const AmSsbCarry<SSB> &pv, int lane) {
+    __syncwarp();  // the previous piece's last reads of the rings are done
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(hring + 4u * lane), "r"(pv.p) : "memory");
+    if constexpr (SSB) asm volatile("st.shared.u32 [%0], %1;" ::"r"(hring + 256u + 4u * lane), "r"((uint32_t)pv.y3b) : "memory");
   }
 
   // ---- stage 1 on the tensor cores (slots in the TMA layout) ----
@@ -562,6 +592,24 @@ struct AmSsbTile {
       hilbert<K + 2>(h, cur, prev, lane);
     }
   }
+  // stage 3's window from the ring: q[7 - j] = the word of the lane j below, j = 1..7
+  template <int J>
+  __device__ __forceinline__ static void window_ring(uint32_t (&q)[8], uint32_t at) {
+    if constexpr (J < 8) {
+      asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(q[7 - J]) : "r"(at), "n"(-4 * J) : "memory");
+      window_ring<J + 1>(q, at);
+    }
+  }
+  // the same from the ring: `at` = shared address of the lane's own word in [32, 64)
+  template <int K>
+  __device__ __forceinline__ static void hilbert_ring(int &h, uint32_t at) {
+    if constexpr (K <= 30) {
+      int v;
+      asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(at), "n"(-4 * K) : "memory");
+      h += taps::SSB_HILBERT::tap(K) * v;
+      hilbert_ring<K + 2>(h, at);
+    }
+  }
 };
 
 // AM / SSB run as two kernels.
@@ -593,6 +641,7 @@ __global__ void __launch_bounds__(128, MINB) amssb_fir_kernel(const __grid_const
   extern __shared__ __align__(1024) uint4 smem_raw[];
   __shared__ uint64_t s_bar[4][NST];
   __shared__ uint4 s_mma[MMA ? 4 : 1][34];  // per warp: 32 bytes of raw history, 512 bytes of transpose buffer
+  __shared__ uint32_t s_ring[4][SSB ? 128 : 64];  // per warp: the window rings of AmSsbTile::rest
   // the warp index through a shuffle: the compiler then knows that everything derived from it (the
   // warp's share, its slot and barrier addresses, the TMA coordinates) is warp-uniform
   const int lane = threadIdx.x & 31, warp = __shfl_sync(FULL, (int)(threadIdx.x >> 5), 0);
@@ -646,6 +695,8 @@ __global__ void __launch_bounds__(128, MINB) amssb_fir_kernel(const __grid_const
       pv.y3a = pv.y3b = 0;
     }
     const bool lsb = SSB && p.lsb[ch] != 0;
+    const uint32_t hring = (uint32_t)__cvta_generic_to_shared(s_ring[warp]);
+    T::ring_init(hring, pv, lane);
     // tensor-core stage 1: the raw bytes before the piece's first tile. force_simt: they (or,
     // later, the tile before) hold a byte the GEMM cannot represent. planes_ok: pv.a7 / pv.b7
     // hold the last rotation group (they do not after a tensor-core tile).
@@ -714,7 +765,7 @@ __global__ void __launch_bounds__(128, MINB) amssb_fir_kernel(const __grid_const
           asm volatile("st.shared.u32 [%0], %1;" ::"r"(mm.hist_s + 4 * lane), "r"(hv) : "memory");
         }
         __syncwarp();  // the slot may be refilled, the history read
-        d = T::template rest<true>(cu, lsb, pv, lane, 32, pm);
+        d = T::template rest<true, true>(cu, lsb, pv, lane, 32, pm, hring);
       } else {
         if constexpr (TMA) {
           tio.wait(buf);
@@ -725,7 +776,7 @@ __global__ void __launch_bounds__(128, MINB) amssb_fir_kernel(const __grid_const
           io.read(buf * TILE_BYTES, w);
         }
         __syncwarp();  // this buffer may be refilled once every lane has read it
-        d = T::template tile<true>(w, fmt, lsb, pv, lane, 32, pm);
+        d = T::template tile<true, true>(w, fmt, lsb, pv, lane, 32, pm, hring);
       }
       if (t >= t0) *sp = (int16_t)d;
       sp += 32;
@@ -740,7 +791,7 @@ __global__ void __launch_bounds__(128, MINB) amssb_fir_kernel(const __grid_const
       uint32_t w[16];
       tile_read(slots + buf * TILE_BYTES, lane, w);
       const int r = (int)(p.n_samples - tf * TILE) >> 5;
-      const int d = T::template tile<false>(w, fmt, lsb, pv, lane, r, pm);
+      const int d = T::template tile<false, true>(w, fmt, lsb, pv, lane, r, pm, hring);
       if (lane < r) *sp = (int16_t)d;  // tf >= t0 always
     }
     // Only the piece that ends the block leaves the channel's state: into the carry buffer

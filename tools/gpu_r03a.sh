@@ -1,0 +1,11 @@
+#!/bin/bash
+# SSB: the Hilbert transformer's window through a shared-memory ring instead of 15 select-and-shuffle pairs
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+run() { echo "== $*"; env "$@" timeout 300 python bench.py --workload $WL --steps 200 --warmup 10 --no-extras --no-cpu --no-e2e 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['frac'], d['parity']['gpu_pcm_identical'], d['clocks']['sm_mhz'], d['clocks']['reasons'])"; }
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_vs_reference.py tests/test_gpu_full_size.py tests/test_gpu_tma.py tests/test_gpu_recurrence.py -x -q 2>&1 | tail -3
+WL=ssb; run A=1; run A=2
+WL=am; run A=1
+timeout 300 ncu --set full --clock-control none -k "regex:amssb_fir" -s 4 -c 1 -f -o gpurun_out/prof_ssb_r03a python bench.py --workload ssb --steps 3 --warmup 3 --no-extras --no-cpu --no-e2e > /dev/null 2>&1
