@@ -140,6 +140,39 @@ SDR_DEV void front_end_group(int fmt, uint32_t w0, uint32_t w1, uint32_t &a, uin
   }
 }
 
+// The same front end with the bytes grouped by what has to be done to them (AM / SSB stage 1): of a rotation
+// period's eight bytes the Fs/4 rotation negates four (Q1, I2, Q2, I3) and leaves four alone, so gathering
+// the negated ones into one word makes the offset a single XOR for one word and the wrapping negation a
+// three-instruction SWAR subtraction for the other -- six instructions per period instead of ten. The words:
+//   a = (s0 of I', s3 of I', s0 of Q', s1 of Q')      b = (s1 of I', s2 of I', s2 of Q', s3 of Q')
+// with s0..s3 the period's four samples in time order: I' lives in the low halves (a.b0, b.b0, b.b1, a.b1),
+// Q' in the high halves (a.b2, a.b3, b.b2, b.b3), which is all a dot product with compile-time tap pairs needs.
+//   u8 input:      a = (I0, Q3, Q0, I1) - 128            b = -(Q1, I2, Q2, I3) + 128 as int8 (so -(-128) = -128)
+//   signed input:  a = (I0, I3, Q0, Q1)                  b = (I1, I2, Q2, Q3)
+SDR_DEV void front_end_ab(int fmt, uint32_t w0, uint32_t w1, uint32_t &a, uint32_t &b) {
+  if (fmt == FMT_U8_OFFSET_ROTATE) {
+    a = byte_perm(w0, w1, 0x2170) ^ 0x80808080u;
+    const uint32_t u = byte_perm(w0, w1, 0x6543);
+    // per byte (0x80 - u) mod 256: 0x80808080 - (u & 0x7f..) cannot borrow across bytes; bit 7 comes from u's
+    b = (0x80808080u - (u & 0x7f7f7f7fu)) ^ (u & 0x80808080u);
+  } else {
+    a = byte_perm(w0, w1, 0x3160);
+    b = byte_perm(w0, w1, 0x7542);
+  }
+}
+// and back: the raw bytes of a rotation period from (a, b) (both steps are involutions)
+SDR_DEV void raw_from_ab(int fmt, uint32_t a, uint32_t b, uint32_t &w0, uint32_t &w1) {
+  if (fmt == FMT_U8_OFFSET_ROTATE) {
+    const uint32_t ar = a ^ 0x80808080u;
+    const uint32_t br = (0x80808080u - (b & 0x7f7f7f7fu)) ^ (b & 0x80808080u);
+    w0 = byte_perm(ar, br, 0x4320);  // I0 Q0 I1 Q1
+    w1 = byte_perm(ar, br, 0x1765);  // I2 Q2 I3 Q3
+  } else {
+    w0 = byte_perm(a, b, 0x3420);
+    w1 = byte_perm(a, b, 0x7165);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Q15 FIR cores
 // ---------------------------------------------------------------------------

@@ -232,7 +232,7 @@ __device__ __forceinline__ uint32_t f2i16x2_wrap(float v0, float v1) {
 // registers a worker carries from tile to tile (per lane)
 template <bool SSB>
 struct AmSsbCarry {
-  uint32_t a7, b7;            // last rotation group of the lane: I' and Q' words
+  uint32_t a7, b7;            // last rotation period of the lane, in front_end_ab's grouping
   uint32_t s1a0, s1a1, s1b0, s1b1;  // the lane's eight stage-1 outputs per arm (int8 x 4)
   uint32_t p;                 // stage-2 outputs: I pair in bytes 0-1, Q pair in bytes 2-3
   int dem;                    // the lane's demodulated value (AM magnitude / SSB phased sum): a small integer
@@ -306,19 +306,26 @@ struct AmSsbTile {
   // last rotation group in `cu`.
   __device__ __forceinline__ static void stage1_simt(const uint32_t (&w)[16], int fmt, const AmSsbCarry<SSB> &pv,
                                                      AmSsbCarry<SSB> &cu, int lane) {
+    // a[g], b[g]: rotation period g in front_end_ab's grouping (I' in the low halves, Q' in the high halves)
     uint32_t a[8], b[8];
 #pragma unroll
-    for (int g = 0; g < 8; ++g) front_end_group(fmt, w[2 * g], w[2 * g + 1], a[g], b[g]);
+    for (int g = 0; g < 8; ++g) front_end_ab(fmt, w[2 * g], w[2 * g + 1], a[g], b[g]);
     cu.a7 = a[7];
     cu.b7 = b[7];
     const uint32_t am1 = shfl_prev(a[7], pv.a7, 1, lane), bm1 = shfl_prev(b[7], pv.b7, 1, lane);
+    // output m: taps 7..4 meet period m - 1's samples s0..s3, taps 3..0 period m's (Decimator_int16.cc:310-351)
+    using D = Doubled<taps::AM1>;
+    constexpr uint32_t ti0 = pack16(D::tap(7), D::tap(4)), ti1 = pack16(D::tap(6), D::tap(5));  // I': (a.b0, a.b1), (b.b0, b.b1)
+    constexpr uint32_t ti2 = pack16(D::tap(3), D::tap(0)), ti3 = pack16(D::tap(2), D::tap(1));
+    constexpr uint32_t tq0 = pack16(D::tap(7), D::tap(6)), tq1 = pack16(D::tap(5), D::tap(4));  // Q': (a.b2, a.b3), (b.b2, b.b3)
+    constexpr uint32_t tq2 = pack16(D::tap(3), D::tap(2)), tq3 = pack16(D::tap(1), D::tap(0));
     int ya[8], yb[8];
 #pragma unroll
     for (int m = 0; m < 8; ++m) {
-      const uint32_t wa[2] = {m == 0 ? am1 : a[m == 0 ? 0 : m - 1], a[m]};
-      const uint32_t wb[2] = {m == 0 ? bm1 : b[m == 0 ? 0 : m - 1], b[m]};
-      ya[m] = fir_s8<Doubled<taps::AM1>, 7, 2>(wa, 1 << 15);  // the int8 result is byte 2
-      yb[m] = fir_s8<Doubled<taps::AM1>, 7, 2>(wb, 1 << 15);
+      const uint32_t pa = m == 0 ? am1 : a[m == 0 ? 0 : m - 1], pb = m == 0 ? bm1 : b[m == 0 ? 0 : m - 1];
+      // the int8 result is byte 2 of the doubled accumulator
+      ya[m] = dp2a_lo_ss(ti3, b[m], dp2a_lo_ss(ti2, a[m], dp2a_lo_ss(ti1, pb, dp2a_lo_ss(ti0, pa, 1 << 15))));
+      yb[m] = dp2a_hi_ss(tq3, b[m], dp2a_hi_ss(tq2, a[m], dp2a_hi_ss(tq1, pb, dp2a_hi_ss(tq0, pa, 1 << 15))));
     }
     cu.s1a0 = pack_b2x4(ya[0], ya[1], ya[2], ya[3]);
     cu.s1a1 = pack_b2x4(ya[4], ya[5], ya[6], ya[7]);
@@ -560,19 +567,12 @@ struct AmSsbTile {
   __device__ __forceinline__ static void planes_from_history(uint32_t hist_s, int fmt, AmSsbCarry<SSB> &pv) {
     uint32_t w0, w1;
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(hist_s + 24) : "memory");
-    front_end_group(fmt, w0, w1, pv.a7, pv.b7);
+    front_end_ab(fmt, w0, w1, pv.a7, pv.b7);
   }
   // and back: the raw bytes of a rotation group from its planes (front_end_group's inverse;
   // wrapping int8 negation is its own inverse)
   __device__ __forceinline__ static void raw_from_planes(uint32_t a, uint32_t b, int fmt, uint32_t &w0, uint32_t &w1) {
-    if (fmt == FMT_U8_OFFSET_ROTATE) {
-      // I0 = I'0, Q0 = Q'0, I1 = Q'1, Q1 = -I'1  |  I2 = -I'2, Q2 = -Q'2, I3 = -Q'3, Q3 = I'3
-      w0 = offset_and_negate(byte_perm(a, b, 0x1540), 0xff000000u, 0x01000000u);
-      w1 = offset_and_negate(byte_perm(a, b, 0x3762), 0x00ffffffu, 0x00010101u);
-    } else {
-      w0 = byte_perm(a, b, 0x5140);
-      w1 = byte_perm(a, b, 0x7362);
-    }
+    raw_from_ab(fmt, a, b, w0, w1);
   }
 
   template <int I>
