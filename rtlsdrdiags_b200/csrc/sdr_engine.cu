@@ -337,7 +337,12 @@ int launch_amssb(sdr_engine *e, int kind, const uint8_t *iq, uint64_t ch_stride,
   static const int wps_env = getenv("SDR_AM_WARPS_PER_SM") ? atoi(getenv("SDR_AM_WARPS_PER_SM")) : 0;
   const uint64_t total_tiles = (uint64_t)n_list * n_tiles;
   uint64_t n_warps = (uint64_t)e->n_sm * (wps_env > 0 ? wps_env : (SSB ? 48 : 72));
-  n_warps = std::min<uint64_t>(n_warps, (total_tiles + 7) / 8);
+  // ... and no shorter than 16 tiles: in a small bank (the AM / SSB shares of a mixed bank: 32 tiles per channel and call) a
+  // share of 8 spends 1/9 (AM) or 2/10 (SSB) of its work on warm-up tiles. mixed x8192: 0.3388 ms with 8, 0.3175-0.3188
+  // with 16, 0.3262 with 24, 0.3190-0.3201 with 32 (profiles/r02_window_rings.txt). NBFM keeps 8: it wants the warps more.
+  static const int min_share_env = getenv("SDR_AM_MIN_SHARE") ? atoi(getenv("SDR_AM_MIN_SHARE")) : 0;  // tuning override
+  const uint64_t min_share = min_share_env > 0 ? (uint64_t)min_share_env : 16;
+  n_warps = std::min<uint64_t>(n_warps, (total_tiles + min_share - 1) / min_share);
   n_warps = std::max<uint64_t>(n_warps, 1);
   LaunchParams p = {};
   p.iq = iq;
@@ -587,7 +592,9 @@ int launch_fm_tile(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint32_
   const uint32_t n_tiles = (n_samples + TILE - 1) / TILE;
   const uint64_t total_tiles = (uint64_t)n_list * n_tiles;
   uint64_t n_warps = (uint64_t)e->n_sm * (wps_env > 0 ? wps_env : 48);
-  n_warps = std::min<uint64_t>(n_warps, (total_tiles + 7) / 8);
+  static const int min_share_env = getenv("SDR_FM_MIN_SHARE") ? atoi(getenv("SDR_FM_MIN_SHARE")) : 0;  // tuning override
+  const uint64_t min_share = min_share_env > 0 ? (uint64_t)min_share_env : 8;
+  n_warps = std::min<uint64_t>(n_warps, (total_tiles + min_share - 1) / min_share);
   n_warps = std::max<uint64_t>(n_warps, 1);
   LaunchParams p = {};
   p.iq = iq;
