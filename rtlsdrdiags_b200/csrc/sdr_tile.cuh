@@ -51,26 +51,6 @@ __device__ __forceinline__ T roll_prev(T cur, T prev, int r, int lane) {
   return __shfl_sync(FULL, lane >= r ? prev : cur, (lane + r) & 31);
 }
 
-// shfl_prev with the source-lane choice done by one LOP3 on a precomputed lane mask
-// (all-ones where lane >= 32 - j) instead of ISETP + SEL: in a loop with many different j the
-// compiler runs out of predicate registers and recomputes the comparisons every tile.
-struct PrevMasks {
-  uint32_t m[8];  // m[j], j = 1..7
-  __device__ __forceinline__ void init(int lane) {
-#pragma unroll
-    for (int j = 1; j < 8; ++j) {
-      m[j] = lane >= 32 - j ? 0xffffffffu : 0u;
-      asm volatile("" : "+r"(m[j]));  // keep it a register value, not a re-derived predicate
-    }
-    m[0] = 0;
-  }
-};
-__device__ __forceinline__ uint32_t shfl_prev_m(uint32_t cur, uint32_t prev, int j, int lane, const PrevMasks &pm) {
-  uint32_t v;
-  asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(v) : "r"(pm.m[j]), "r"(prev), "r"(cur));  // m ? prev : cur
-  return __shfl_sync(FULL, v, (lane - j) & 31);
-}
-
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
@@ -293,12 +273,12 @@ struct AmSsbTile {
   // 181/122, Hilbert 372/181), so the float difference is exact and travels as an int16.
   // Updates the carry to this tile's registers rolled by r valid lanes.
   // FULL_TILE: r == 32 is known at compile time (the hot loop); otherwise 1 <= r <= 32.
-  template <bool FULL_TILE = false, bool RING = false>
+  template <bool FULL_TILE = false>
   __device__ __forceinline__ static int tile(const uint32_t (&w)[16], int fmt, bool lsb, AmSsbCarry<SSB> &pv, int lane, int r,
-                                             const PrevMasks &pm, uint32_t hring = 0) {
+                                             uint32_t hring) {
     AmSsbCarry<SSB> cu;
     stage1_simt(w, fmt, pv, cu, lane);
-    return rest<FULL_TILE, RING>(cu, lsb, pv, lane, r, pm, hring);
+    return rest<FULL_TILE>(cu, lsb, pv, lane, r, hring);
   }
 
   // stage 1 on the CUDA cores: front end, then 8 taps 4:1 on each arm (AmDemodulator.cc:349-374
@@ -334,13 +314,13 @@ struct AmSsbTile {
   }
 
   // Everything after stage 1, from cu.s1a0..s1b1 (cu.a7 / cu.b7 are carried along untouched).
-  // RING: hring = shared address of the warp's window rings (else: shuffles). A ring is 64 words: [0, 32) = the value of
+  // hring = shared address of the warp's window rings. A ring is 64 words: [0, 32) = the value of
   // the 32 lanes before the tile (the carry), [32, 64) = this tile's, so "the lane j below" is a load at an immediate
   // offset instead of a select, a lane index and a shuffle. Words 0-63: stage 3's window (pv.p / cu.p); words 64-127
   // (SSB): the Hilbert transformer's (y3b). The caller sets both carries at a piece's start (ring_init).
-  template <bool FULL_TILE = false, bool RING = false>
+  template <bool FULL_TILE = false>
   __device__ __forceinline__ static int rest(AmSsbCarry<SSB> &cu, bool lsb, AmSsbCarry<SSB> &pv, int lane, int r,
-                                             const PrevMasks &pm, uint32_t hring = 0) {
+                                             uint32_t hring) {
     // stage 2: 12 taps, 4:1
     const uint32_t pa0 = shfl_prev(cu.s1a0, pv.s1a0, 1, lane), pa1 = shfl_prev(cu.s1a1, pv.s1a1, 1, lane);
     const uint32_t pb0 = shfl_prev(cu.s1b0, pv.s1b0, 1, lane), pb1 = shfl_prev(cu.s1b1, pv.s1b1, 1, lane);
@@ -359,14 +339,11 @@ struct AmSsbTile {
     // (I in bytes 0-1, Q in bytes 2-3); position pos meets tap 15 - pos.
     uint32_t q[8];
     q[7] = cu.p;
-    if constexpr (RING) {
+    {
       const uint32_t at = hring + 128u + 4u * lane;
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(at), "r"(cu.p) : "memory");
       __syncwarp();
       window_ring<1>(q, at);
-    } else {
-#pragma unroll
-      for (int j = 1; j < 8; ++j) q[7 - j] = shfl_prev_m(cu.p, pv.p, j, lane, pm);
     }
     int acc_i = 1 << 14, acc_q = 1 << 14;
     stage3<0>(q, acc_i, acc_q);
@@ -387,15 +364,11 @@ struct AmSsbTile {
       acc = acc < -0x40000000 ? -0x40000000 : acc;
       const int i_delayed = (int)(int16_t)(acc >> 15);
       int h = (1 << 14) + taps::SSB_HILBERT::tap(0) * cu.y3b;
-      if constexpr (RING) {
-        // the 15 even lanes below through the ring: a store, a warp barrier and 15 loads at immediate offsets
-        // instead of 15 select-and-shuffle pairs
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(hring + 256u + 128u + 4u * lane), "r"(cu.y3b) : "memory");
-        __syncwarp();
-        hilbert_ring<2>(h, hring + 256u + 128u + 4u * lane);
-      } else {
-        hilbert<2>(h, cu.y3b, pv.y3b, lane);
-      }
+      // the 15 even lanes below through the ring: a store, a warp barrier and 15 loads at immediate offsets
+      // instead of 15 select-and-shuffle pairs
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(hring + 256u + 128u + 4u * lane), "r"(cu.y3b) : "memory");
+      __syncwarp();
+      hilbert_ring<2>(h, hring + 256u + 128u + 4u * lane);
       const int q_shifted = (int)(int16_t)(h >> 15);
       cu.dem = lsb ? i_delayed - q_shifted : i_delayed + q_shifted;
     }
@@ -417,7 +390,7 @@ struct AmSsbTile {
         pv.y3b = roll_prev(cu.y3b, pv.y3b, r, lane);
       }
     }
-    if constexpr (RING) {
+    {
       __syncwarp();  // every lane has read its windows
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(hring + 4u * lane), "r"(pv.p) : "memory");
       if constexpr (SSB) asm volatile("st.shared.u32 [%0], %1;" ::"r"(hring + 256u + 4u * lane), "r"(pv.y3b) : "memory");
@@ -584,14 +557,6 @@ struct AmSsbTile {
       stage3<I + 1>(q, acc_i, acc_q);
     }
   }
-  // even taps only (odd taps are zero); |x| <= 179 so the per-tap clamp cannot fire
-  template <int K>
-  __device__ __forceinline__ static void hilbert(int &h, int cur, int prev, int lane) {
-    if constexpr (K <= 30) {
-      h += taps::SSB_HILBERT::tap(K) * shfl_prev(cur, prev, K, lane);
-      hilbert<K + 2>(h, cur, prev, lane);
-    }
-  }
   // stage 3's window from the ring: q[7 - j] = the word of the lane j below, j = 1..7
   template <int J>
   __device__ __forceinline__ static void window_ring(uint32_t (&q)[8], uint32_t at) {
@@ -600,7 +565,8 @@ struct AmSsbTile {
       window_ring<J + 1>(q, at);
     }
   }
-  // the same from the ring: `at` = shared address of the lane's own word in [32, 64)
+  // the Hilbert transformer's window from its ring: even taps only (odd taps are zero); |x| <= 179 so the per-tap
+  // clamp cannot fire. `at` = shared address of the lane's own word in [32, 64)
   template <int K>
   __device__ __forceinline__ static void hilbert_ring(int &h, uint32_t at) {
     if constexpr (K <= 30) {
@@ -661,8 +627,6 @@ __global__ void __launch_bounds__(128, MINB) amssb_fir_kernel(const __grid_const
   TmaIo tio;
   if constexpr (TMA) tio.init(slots, s_bar[warp], lane, NST);
   else io.init(slots, lane);
-  PrevMasks pm;
-  pm.init(lane);
   const int fmt = p.fmt;
   typename T::Mma mm;
   if constexpr (MMA) {
@@ -765,7 +729,7 @@ __global__ void __launch_bounds__(128, MINB) amssb_fir_kernel(const __grid_const
           asm volatile("st.shared.u32 [%0], %1;" ::"r"(mm.hist_s + 4 * lane), "r"(hv) : "memory");
         }
         __syncwarp();  // the slot may be refilled, the history read
-        d = T::template rest<true, true>(cu, lsb, pv, lane, 32, pm, hring);
+        d = T::template rest<true>(cu, lsb, pv, lane, 32, hring);
       } else {
         if constexpr (TMA) {
           tio.wait(buf);
@@ -776,7 +740,7 @@ __global__ void __launch_bounds__(128, MINB) amssb_fir_kernel(const __grid_const
           io.read(buf * TILE_BYTES, w);
         }
         __syncwarp();  // this buffer may be refilled once every lane has read it
-        d = T::template tile<true, true>(w, fmt, lsb, pv, lane, 32, pm, hring);
+        d = T::template tile<true>(w, fmt, lsb, pv, lane, 32, hring);
       }
       if (t >= t0) *sp = (int16_t)d;
       sp += 32;
@@ -791,7 +755,7 @@ __global__ void __launch_bounds__(128, MINB) amssb_fir_kernel(const __grid_const
       uint32_t w[16];
       tile_read(slots + buf * TILE_BYTES, lane, w);
       const int r = (int)(p.n_samples - tf * TILE) >> 5;
-      const int d = T::template tile<false, true>(w, fmt, lsb, pv, lane, r, pm, hring);
+      const int d = T::template tile<false>(w, fmt, lsb, pv, lane, r, hring);
       if (lane < r) *sp = (int16_t)d;  // tf >= t0 always
     }
     // Only the piece that ends the block leaves the channel's state: into the carry buffer
