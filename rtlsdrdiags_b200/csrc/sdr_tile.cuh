@@ -597,7 +597,8 @@ struct AmSsbTile {
 // tile; false: by four cp.async per lane (TileIo). A partial last tile takes cp.async either way.
 // NST = slot buffers per warp: NST - 1 tiles are in flight while one is computed.
 // MMA (with TMA only): stage 1 on the tensor cores (AmSsbTile::stage1_mma).
-// MINB = CTAs resident per SM the register budget is cut for (5: 96 registers, 6: 80).
+// MINB = CTAs resident per SM the register budget is cut for (5: up to 96 registers, 6: 80; since the window rings the
+// kernel needs 78-80 either way and six CTAs are resident).
 template <bool SSB, bool TMA, int NST, bool MMA, int MINB = 5>
 __global__ void __launch_bounds__(128, MINB) amssb_fir_kernel(const __grid_constant__ LaunchParams p,
                                                            const __grid_constant__ CUtensorMap tmap) {
@@ -800,7 +801,7 @@ __global__ void __launch_bounds__(128, MINB) amssb_fir_kernel(const __grid_const
 // instructions (the first version converted and stored in the same warp: 1500 cycles per row against
 // ~350, the float -> int conversions queue on the quarter-rate XU pipe; profiles/r02_dc_block_ncu.txt).
 // Warp 1 is the CONVERTER, one row behind: gain, (int16_t) and the row's 64 bytes of PCM. One
-// CTA barrier per row. At 64 threads x 64 registers a CTA fits beside the five resident CTAs of the
+// CTA barrier per row. At 64 threads x 64 registers a CTA fits beside the resident CTAs of the
 // next call's FIR kernel without taking one's place.
 constexpr int DC_PF = 8;             // rows in flight per lane
 constexpr int DC_LANE_PITCH = 80;    // 64 + 16: lane-per-row 128-bit reads are bank-conflict free
