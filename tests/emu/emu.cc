@@ -109,4 +109,23 @@ uint64_t emu_wrap_table_check(const float *vals, uint32_t n) {
     }
   return bad;
 }
+
+// front_end_ab (AM / SSB stage 1: a rotation period's bytes grouped by what is done to them) on one period of eight
+// raw bytes: the eight samples in the order (I'0, I'1, I'2, I'3, Q'0, Q'1, Q'2, Q'3), picked from the low / high halves
+// of (a, b) exactly where stage1_simt's tap pairs expect them; and raw_from_ab's round trip. Returns 0 if the round
+// trip is the identity.
+int emu_front_end_ab(int fmt, const uint8_t *raw8, int8_t *out8) {
+  uint32_t w0, w1, a, b, r0, r1;
+  memcpy(&w0, raw8, 4);
+  memcpy(&w1, raw8 + 4, 4);
+  sdr::front_end_ab(fmt, w0, w1, a, b);
+  const uint32_t i_bytes[4] = {a & 0xff, b & 0xff, (b >> 8) & 0xff, (a >> 8) & 0xff};              // s0 s1 s2 s3 of I'
+  const uint32_t q_bytes[4] = {(a >> 16) & 0xff, (a >> 24) & 0xff, (b >> 16) & 0xff, (b >> 24) & 0xff};  // of Q'
+  for (int k = 0; k < 4; ++k) {
+    out8[k] = (int8_t)i_bytes[k];
+    out8[4 + k] = (int8_t)q_bytes[k];
+  }
+  sdr::raw_from_ab(fmt, a, b, r0, r1);
+  return (r0 == w0 && r1 == w1) ? 0 : 1;
+}
 }

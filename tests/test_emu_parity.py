@@ -107,3 +107,30 @@ def test_wbfm_table_is_odd_in_q():
         assert np.array_equal(t[128 - q], -t[128 + q])
         assert np.all(np.signbit(t[128 - q]) != np.signbit(t[128 + q]))
     assert np.array_equal(t[0], -np.array([O.oracle().sdro_atan2f(128, i) for i in range(-128, 128)], dtype=np.float32))
+
+
+def test_grouped_front_end_is_the_reference_front_end():
+    """front_end_ab (AM / SSB stage 1) groups a rotation period's eight bytes by what has to be done to them
+    -- the four the Fs/4 rotation negates in one word -- instead of by arm. Against the oracle's front end
+    (IqDataProcessor.cc:735-738, 567-611) for every byte value in every position, -(-128) = -128 included,
+    and raw_from_ab as its inverse; for input that is already signed and rotated it is a plain regrouping."""
+    import ctypes as C
+    L = E.lib()
+    L.emu_front_end_ab.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(11)
+    out = np.zeros(8, dtype=np.int8)
+    cases = [np.full(8, v, dtype=np.uint8) for v in range(256)]
+    for pos in range(8):
+        for v in (0, 1, 127, 128, 129, 255):
+            c = rng.integers(0, 256, size=8, dtype=np.uint8)
+            c[pos] = v
+            cases.append(c)
+    cases += [rng.integers(0, 256, size=8, dtype=np.uint8) for _ in range(2000)]
+    for raw in cases:
+        raw = np.ascontiguousarray(raw)
+        assert L.emu_front_end_ab(E.FMT_U8, raw.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)) == 0
+        want = O.front_end(raw)                      # I'0 Q'0 I'1 Q'1 ... as the reference leaves them
+        assert np.array_equal(out[:4], want[0::2]) and np.array_equal(out[4:], want[1::2]), raw
+        s8 = raw.view(np.int8)
+        assert L.emu_front_end_ab(E.FMT_S8, raw.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)) == 0
+        assert np.array_equal(out[:4], s8[0::2]) and np.array_equal(out[4:], s8[1::2]), raw
