@@ -849,7 +849,10 @@ int launch_wbfm_tile4(sdr_engine *e, const uint8_t *iq, uint64_t ch_stride, uint
   SDR_CK(e, cudaGetLastError());
   // how many (half-)tiles clipping bytes kept off the tensor cores, for launch_wbfm_tile's choice of kernel: read by
   // a later call, whenever the copy has landed
-  if (!e->h_wb_clip) SDR_CK(e, cudaHostAlloc(&e->h_wb_clip, 16, cudaHostAllocDefault));
+  if (!e->h_wb_clip) {
+    SDR_CK(e, cudaHostAlloc(&e->h_wb_clip, 16, cudaHostAllocDefault));
+    *e->h_wb_clip = 0;  // what counters[3] starts from: a read before the first copy lands sees "nothing clipped"
+  }
   SDR_CK(e, cudaMemcpyAsync((void *)e->h_wb_clip, e->d_counters + 3, 4, cudaMemcpyDeviceToHost, stream));
   e->wb4_units = (uint64_t)((n_list + (two ? 1 : 0)) / (two ? 2 : 1)) * ((n_samples + (two ? 511 : 1023)) / (two ? 512 : 1024));
   e->launches++;
